@@ -1,0 +1,114 @@
+// kernels.h -- the C ABI of the B200 wavefront path tracer (libcrt_b200.so).
+//
+// Part 1 is the drop-in boundary: the three entry points of the reference's
+// kernels.h:6-8 with identical names, argument order, by-value PODs and
+// blocking semantics (implementation reference: kernels.cu:571-680).  A host
+// program written against the reference headers (reference main.cpp:94,98,138)
+// links against this library unchanged; oracle/ref_driver.cpp is built both
+// ways to prove it.
+//
+// Part 2 is strictly additive: entry points the reference lacks but its
+// README scenes / BASELINE configs need (SURVEY.md 8b "gaps"): a sphere-scene
+// initialiser, a ray-batch intersector, options (device, sample stream,
+// deferred finalisation for the multi-GPU reduce) and counters.
+//
+// Error behaviour (all entry points), as reference kernels.cu:30-37: a CUDA
+// failure prints "CUDA error = ... at file:line 'call'" to stderr, resets the
+// device and calls exit(99).  There are no return codes on part 1.
+#pragma once
+
+#include "rt_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+// ---------------------------------------------------------------- part 1 ----
+// reference kernels.h:6 / kernels.cu:571.  Copies the scene to the device
+// (nothing host-side is retained), allocates the frame buffer as managed
+// memory and returns it through *fb (host-dereferenceable after runRenderer,
+// valid until cleanupRenderer).  fb[j*nx+i] is linear RGB, row 0 = bottom.
+void initRenderer(const kernel_scene sc, const camera cam, vec3** fb, int nx, int ny, int maxDepth);
+
+// reference kernels.h:7 / kernels.cu:652.  Blocking.  Overwrites fb with the
+// mean of `ns` samples per pixel.  tx,ty were the reference's block shape; the
+// wavefront kernels choose their own launch shapes, so they are accepted and
+// ignored (they never changed the image).
+void runRenderer(int ns, int tx, int ty);
+
+// reference kernels.h:8 / kernels.cu:666.  Frees everything initRenderer made.
+// (The reference also calls cudaDeviceReset(); see renderer_options.)
+void cleanupRenderer();
+
+// ---------------------------------------------------------------- part 2 ----
+typedef struct renderer_options {
+    int device;               // CUDA ordinal to render on; -1 = keep the current device
+    unsigned int sampleStream;// g: per-pixel seed is wang_hash(pixelId + g*nx*ny) (reference kernels.cu:542 is g = 0)
+    int deferFinalize;        // 0: runRenderer writes fb = sum/ns (reference).  1: keep un-normalised sums
+                              //    on the device for an external reduce; call finalizeFrame afterwards
+    int resetDeviceOnCleanup; // 1: cleanupRenderer ends with cudaDeviceReset() like kernels.cu:679
+                              //    (default 0: fatal inside a process that shares the device, e.g. torch)
+    int megaBatch;            // iterations launched between host checks of the live-path counter (0 = default)
+    int reserved[3];
+} renderer_options;
+
+// Applies to the NEXT initRenderer* call.  Passing NULL restores the defaults.
+void setRendererOptions(const renderer_options* opt);
+
+// Sphere scenes (README era; no entry point exists at the reference's HEAD).
+// `spheres[i]` uses `materials[i]`; both arrays are copied into __constant__
+// memory (n <= 1024).  Sky is the gradient of kernels.cu:419-421, there is no
+// light and no next-event estimation; everything else follows color().
+void initRendererSpheres(const sphere* spheres, const material* materials, int n, const camera cam, vec3** fb,
+                         int nx, int ny, int maxDepth);
+
+// Closest-hit query of a ray batch against the scene given to initRenderer:
+// the arithmetic of hit()/hitMesh()/hitBvh() (kernels.cu:325,296,154) on
+// `n` rays.  origins/dirs are n*3 floats (dirs are normalised inside exactly
+// as the reference's ray constructor does, ray.h:9).  Outputs: t (FLT_MAX on
+// miss), triangle slot id (-1 on miss), meshID (-1 on miss).  All pointers are
+// HOST pointers; copies are part of the call.
+void intersectBatch(const float* origins, const float* dirs, long long n, float tMin, float tMax, float* outT,
+                    int* outTriId, int* outMeshId);
+
+// Same query with DEVICE-resident SoA buffers: rays as float4 (ox,oy,oz,tMin)
+// and (dx,dy,dz,tMax), result float4 (t,u,v, triId as int bits) plus meshID.
+// Used by the 64 Mi-ray microbench (BASELINE config 5).  Returns kernel ms.
+float intersectBatchDevice(const void* dRayO, const void* dRayD, long long n, void* dHit, int* dMeshId);
+
+// Fills device ray buffers with the config-5 batch: even
+// indices are jittered camera rays over a virtual filmW x filmH film, odd
+// indices are incoherent rays (origin uniform in the scene bounds, direction
+// from the unit-sphere rejection sampler), seeded per ray with the
+// kernels.cu:542 formula applied to the ray index.
+void generateRayBatchDevice(void* dRayO, void* dRayD, long long n, int filmW, int filmH, float tMin, float tMax);
+
+void* rendererDeviceAlloc(size_t bytes);
+void rendererDeviceFree(void* p);
+void rendererCopyToHost(void* dst, const void* dSrc, size_t bytes);
+void rendererCopyToDevice(void* dDst, const void* src, size_t bytes);
+
+typedef struct renderer_stats {
+    unsigned long long raysExtend;  // closest-hit rays traced by the last runRenderer (primary + secondary)
+    unsigned long long raysShadow;  // any-hit rays traced by the last runRenderer
+    unsigned long long samples;     // nx*ny*ns
+    unsigned long long kernelLaunches; // kernels launched by the last runRenderer
+    unsigned long long iterations;  // wavefront iterations
+    float msTotal;                  // device time of the last runRenderer (CUDA events on the render stream)
+    float msExtend, msShade, msShadow, msOther; // per-kernel-family device time (only when profiling is on)
+    int profiled;
+} renderer_stats;
+
+void getRendererStats(renderer_stats* out);
+// 1: time every kernel family with CUDA events (serialises the iteration; for roofline numbers).
+void setRendererProfiling(int on);
+
+// Multi-GPU support: the per-pixel un-normalised radiance sums (float4 per
+// pixel: r,g,b,unused) live on the device.  A launcher with one process per
+// GPU reduces them with NCCL and calls finalizeFrame on the root.
+void* getRendererAccumDevice();   // device pointer, nx*ny float4
+void finalizeFrame(int nsTotal);  // fb = accum / nsTotal (blocking)
+
+#ifdef __cplusplus
+}
+#endif
