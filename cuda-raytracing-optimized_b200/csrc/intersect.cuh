@@ -1,0 +1,175 @@
+// intersect.cuh -- ray/box, ray/triangle, ray/sphere tests and the BVH walk.
+//
+// Arithmetic follows the reference so that hit ids are bit-exact:
+//   slab test            intersections.h:7-41   ((b - o) * (1.0f/d), box t_min fixed at 0.001f)
+//   Moller-Trumbore      intersections.h:54-83  (reject |a| < 1e-7, u, v, u+v, t in (t_min,t_max))
+//   sphere               intersections.h:85-104 (both roots)
+//   dual-node traversal  kernels.cu:148-224     (near child first, tie -> left, bit-stack pop)
+// Layout differences (the device layout is ours):
+//   * nodes: the reference's bvh_node[] bytes, read as three 16-byte loads per
+//     internal node (children 2i and 2i+1 are adjacent = floats [12i,12i+12));
+//   * triangles: 48-byte tiles {v0, e1 = v1-v0, e2 = v2-v0} in three float4
+//     (the subtractions are the ones triangleHit does first; precomputing them
+//     does not change a bit), +inf in v0.x marks an unused leaf slot.
+#pragma once
+
+#include <cfloat>
+
+#include "vecmath.cuh"
+
+#define RT_EPSILON 0.01f // kernels.cu:19
+
+struct RayPrep {
+    f3 o;    // origin
+    f3 d;    // unit direction (ray.h:9)
+    f3 inv;  // 1.0f / d  (IEEE)
+};
+
+__device__ __forceinline__ RayPrep prepRay(const f3& o, const f3& dirNormalised) {
+    RayPrep r;
+    r.o = o;
+    r.d = dirNormalised;
+    r.inv = mk3(1.0f / dirNormalised.x, 1.0f / dirNormalised.y, 1.0f / dirNormalised.z);
+    return r;
+}
+
+// One axis of the slab loop (intersections.h:27-36). NaNs (0 * inf) leave tMin/tMax unchanged,
+// exactly like the reference's `t0 > t_min ? t0 : t_min` selects.
+__device__ __forceinline__ void slabAxis(float bmin, float bmax, float o, float inv, float& tMin, float& tMax) {
+    float t0 = (bmin - o) * inv;
+    float t1 = (bmax - o) * inv;
+    if (inv < 0.0f) {
+        float tmp = t0; t0 = t1; t1 = tmp;
+    }
+    tMin = t0 > tMin ? t0 : tMin;
+    tMax = t1 < tMax ? t1 : tMax;
+}
+
+// hit_bbox_dist: entry distance, or FLT_MAX. tMin only grows and tMax only shrinks, so testing
+// once after the third axis equals the reference's per-axis early return.
+__device__ __forceinline__ float boxDist(const f3& bmin, const f3& bmax, const RayPrep& r, float tMax) {
+    float tMin = 0.001f;
+    slabAxis(bmin.x, bmax.x, r.o.x, r.inv.x, tMin, tMax);
+    slabAxis(bmin.y, bmax.y, r.o.y, r.inv.y, tMin, tMax);
+    slabAxis(bmin.z, bmax.z, r.o.z, r.inv.z, tMin, tMax);
+    return tMax < tMin ? FLT_MAX : tMin;
+}
+
+// hit_bbox (intersections.h:7-23): same slabs, boolean result.
+__device__ __forceinline__ bool boxHit(const f3& bmin, const f3& bmax, const RayPrep& r, float tMax) {
+    float tMin = 0.001f;
+    slabAxis(bmin.x, bmax.x, r.o.x, r.inv.x, tMin, tMax);
+    slabAxis(bmin.y, bmax.y, r.o.y, r.inv.y, tMin, tMax);
+    slabAxis(bmin.z, bmax.z, r.o.z, r.inv.z, tMin, tMax);
+    return !(tMax < tMin);
+}
+
+// triangleHit on a prepared tile. Returns FLT_MAX or t in (tMin, tMax).
+__device__ __forceinline__ float triHit(const f3& v0, const f3& edge1, const f3& edge2, const RayPrep& r, float tMin, float tMax,
+                                        float& hitU, float& hitV) {
+    const float EPS = 0.0000001f;
+    f3 h = cross(r.d, edge2);
+    float a = dot(edge1, h);
+    if (a > -EPS && a < EPS) return FLT_MAX;
+    float f = 1.0f / a;
+    f3 s = r.o - v0;
+    float u = f * dot(s, h);
+    if (u < 0.0f || u > 1.0f) return FLT_MAX;
+    f3 q = cross(s, edge1);
+    float v = f * dot(r.d, q);
+    if (v < 0.0f || u + v > 1.0f) return FLT_MAX;
+    float t = f * dot(edge2, q);
+    if (t > tMin && t < tMax) {
+        hitU = u;
+        hitV = v;
+        return t;
+    }
+    return FLT_MAX;
+}
+
+__device__ __forceinline__ float sphereHitT(const f3& center, float radius, const f3& o, const f3& d, float tMin, float tMax) {
+    f3 oc = o - center;
+    float a = dot(d, d);
+    float b = dot(oc, d);
+    float c = dot(oc, oc) - radius * radius;
+    float discriminant = b * b - a * c;
+    if (discriminant > 0) {
+        float temp = (-b - sqrtf(discriminant)) / a;
+        if (temp < tMax && temp > tMin) return temp;
+        temp = (-b + sqrtf(discriminant)) / a;
+        if (temp < tMax && temp > tMin) return temp;
+    }
+    return FLT_MAX;
+}
+
+struct MeshView {
+    const float4* __restrict__ nodes; // 3 float4 per internal node index (children pair)
+    const float4* __restrict__ tris;  // 3 float4 per triangle slot
+    unsigned int firstLeaf;
+    unsigned int primsPerLeaf;
+    f3 boundsMin, boundsMax;
+};
+
+struct TravCounters {
+    unsigned int nodeVisits; // internal (dual) node visits
+    unsigned int triTests;
+};
+
+// hitMesh (kernels.cu:296-323) + hitBvh (kernels.cu:154-224).
+// ANY = true is the reference's isShadow: return 0.0f on the first accepted triangle.
+// COUNT adds visit counters (used for the flop side of the roofline, never in timed runs).
+template <bool ANY, bool COUNT>
+__device__ __forceinline__ float traverseRefOrder(const MeshView& m, const RayPrep& r, float tMin, float tMax, unsigned int& triId,
+                                                  float& hitU, float& hitV, TravCounters* cnt) {
+    if (!boxHit(m.boundsMin, m.boundsMax, r, tMax)) return FLT_MAX;
+
+    unsigned int idx = 1;
+    float closest = tMax;
+    unsigned int bitStack = 1;
+    while (idx) {
+        if (idx < m.firstLeaf) {
+            const float4 a = __ldg(m.nodes + 3 * idx);
+            const float4 b = __ldg(m.nodes + 3 * idx + 1);
+            const float4 c = __ldg(m.nodes + 3 * idx + 2);
+            if (COUNT) cnt->nodeVisits++;
+            float leftHit = boxDist(mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), r, closest);
+            float rightHit = boxDist(mk3(b.z, b.w, c.x), mk3(c.y, c.z, c.w), r, closest);
+            bool traverseLeft = leftHit < closest;
+            bool traverseRight = rightHit < closest;
+            unsigned int swap = rightHit < leftHit ? 1u : 0u;
+            if (traverseLeft && traverseRight) {
+                idx = 2 * idx + swap;
+                bitStack = (bitStack << 1) + 1;
+            } else if (traverseLeft || traverseRight) {
+                idx = 2 * idx + swap;
+                bitStack = bitStack << 1;
+            } else {
+                int s = __ffs(bitStack) - 1;
+                bitStack = (bitStack >> s) ^ 1u;
+                idx = (idx >> s) ^ 1u;
+            }
+        } else {
+            unsigned int first = (idx - m.firstLeaf) * m.primsPerLeaf;
+            for (unsigned int i = 0; i < m.primsPerLeaf; i++) {
+                const float4 t0 = __ldg(m.tris + 3 * (first + i));
+                if (isinf(t0.x)) break;
+                const float4 t1 = __ldg(m.tris + 3 * (first + i) + 1);
+                const float4 t2 = __ldg(m.tris + 3 * (first + i) + 2);
+                if (COUNT) cnt->triTests++;
+                float u, v;
+                float hitT = triHit(mk3(t0.x, t0.y, t0.z), mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), r, tMin, closest, u, v);
+                if (hitT < closest) {
+                    if (ANY) return 0.0f;
+                    closest = hitT;
+                    triId = first + i;
+                    hitU = u;
+                    hitV = v;
+                }
+            }
+            int s = __ffs(bitStack) - 1;
+            bitStack = (bitStack >> s) ^ 1u;
+            idx = (idx >> s) ^ 1u;
+        }
+    }
+    return closest;
+}

@@ -1,0 +1,75 @@
+// raybatch_kernels.cuh -- closest-hit queries on a flat ray batch (BASELINE config 5) and its generator.
+//
+// The query is the arithmetic of hit() -> hitMesh() -> hitBvh() (kernels.cu:325-339, :296, :154) for one ray:
+// the direction is normalised by the ray constructor (ray.h:9), the scene bounds are tested first, then the
+// dual-node traversal runs.  Per ray the kernel moves 32 B in and 20 B out.
+#pragma once
+
+#include "device_scene.cuh"
+#include "rng.cuh"
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256) intersectBatchKernel(MeshView mesh, const float4* __restrict__ triShade,
+                                                            const float4* __restrict__ rayO, const float4* __restrict__ rayD,
+                                                            unsigned long long n, float4* __restrict__ outHit, int* __restrict__ outMesh,
+                                                            unsigned int* cursor, unsigned long long* counts) {
+    TravCounters cnt = {0u, 0u};
+    const unsigned int lane = threadIdx.x & 31u;
+    while (true) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(cursor, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if ((unsigned long long)base >= n) break;
+        const unsigned long long i = (unsigned long long)base + lane;
+        if (i < n) {
+            const float4 ro = __ldg(rayO + i);
+            const float4 rd = __ldg(rayD + i);
+            const RayPrep r = prepRay(xyz(ro), unit(xyz(rd)));
+            unsigned int triId = 0xFFFFFFFFu;
+            float u = 0.0f, v = 0.0f;
+            float t = traverseRefOrder<false, COUNT>(mesh, r, ro.w, rd.w, triId, u, v, &cnt);
+            int meshID = -1;
+            if (t < rd.w) {
+                meshID = __float_as_int(__ldg(triShade + 3 * triId).w);
+            } else {
+                t = FLT_MAX;
+                triId = 0xFFFFFFFFu;
+                u = v = 0.0f;
+            }
+            outHit[i] = make_float4(t, u, v, __uint_as_float(triId));
+            outMesh[i] = meshID;
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&counts[0], (unsigned long long)cnt.nodeVisits);
+        atomicAdd(&counts[1], (unsigned long long)cnt.triTests);
+    }
+}
+
+// First half of the batch: jittered camera rays over a filmW x filmH virtual film (coherent).
+// Second half: origin uniform in the scene bounds, direction from the unit-sphere sampler (incoherent).
+// Every ray has its own stream, seeded like a pixel (kernels.cu:542) from its index.
+__global__ void generateRayBatchKernel(float4* __restrict__ rayO, float4* __restrict__ rayD, unsigned long long n, CameraDev cam,
+                                       f3 bmin, f3 bmax, int filmW, int filmH, float tMin, float tMax) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned int rng = pathSeed((unsigned int)i);
+    f3 o, d;
+    if (i < n / 2) {
+        const unsigned long long film = (unsigned long long)filmW * filmH;
+        const unsigned long long p = i % film;
+        const int px = (int)(p % filmW), py = (int)(p / filmW);
+        const float u = float(px + rnd(rng)) / float(filmW);
+        const float v = float(py + rnd(rng)) / float(filmH);
+        o = cam.origin;
+        d = unit(cam.lowerLeft + u * cam.horizontal + v * cam.vertical - cam.origin);
+    } else {
+        const float a = rnd(rng);
+        const float b = rnd(rng);
+        const float c = rnd(rng);
+        o = mk3(bmin.x + a * (bmax.x - bmin.x), bmin.y + b * (bmax.y - bmin.y), bmin.z + c * (bmax.z - bmin.z));
+        d = unit(randomInUnitSphere(rng));
+    }
+    rayO[i] = mk4(o, tMin);
+    rayD[i] = mk4(d, tMax);
+}

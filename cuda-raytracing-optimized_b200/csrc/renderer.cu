@@ -1,0 +1,461 @@
+// renderer.cu -- the C ABI of libcrt_b200.so (include/kernels.h) for the triangle-mesh path.
+//
+// Replaces the host half of the reference's kernels.cu:
+//   initRenderer     kernels.cu:571-650   scene upload (+ re-tiling into 16-byte tiles)
+//   runRenderer      kernels.cu:652-664   one frame; here a loop of wavefront iterations, captured in a CUDA graph
+//   cleanupRenderer  kernels.cu:666-680
+// and keeps the reference's error behaviour (check_cuda, kernels.cu:30-37).
+// There is no CPU fallback: without a CUDA device every entry point exits(99).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "kernels.h"
+#include "raybatch_kernels.cuh"
+#include "renderer_internal.h"
+#include "wavefront_kernels.cuh"
+
+void crtCheckCuda(cudaError_t result, const char* func, const char* file, int line) {
+    if (result) {
+        std::fprintf(stderr, "CUDA error = %s at %s:%d '%s' \n", cudaGetErrorString(result), file, line, func);
+        cudaDeviceReset();
+        std::exit(99);
+    }
+}
+
+RendererContext g_ctx;
+renderer_options g_opts = {-1, 0u, 0, 0, 0, {0, 0, 0}};
+static int g_profiling = 0;
+
+static f3 toF3(const vec3& v) { return mk3(v.e[0], v.e[1], v.e[2]); }
+
+template <class T>
+static T* devAlloc(size_t count) {
+    T* p = nullptr;
+    CRT_CHECK(cudaMalloc((void**)&p, count * sizeof(T) > 0 ? count * sizeof(T) : 16));
+    return p;
+}
+
+static void freeWavefront(RendererContext& c) { // everything sized by the slot count; `accum` is per pixel and stays
+    WfState& s = c.wf;
+    cudaFree(s.rayO); cudaFree(s.rayD); cudaFree(s.atten); cudaFree(s.pcol); cudaFree(s.hit);
+    cudaFree(s.shO); cudaFree(s.shD); cudaFree(s.shL);
+    cudaFree(s.queueA); cudaFree(s.queueB); cudaFree(s.regen);
+    cudaFree(s.ctl);
+    float4* accum = s.accum;
+    std::memset(&s, 0, sizeof(s));
+    s.accum = accum;
+    if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
+    c.graphKey = -1;
+}
+
+static void allocWavefront(RendererContext& c, unsigned int numSlots) {
+    if (c.wf.numSlots == numSlots && c.wf.rayO) return;
+    freeWavefront(c);
+    WfState& s = c.wf;
+    s.numSlots = numSlots;
+    s.rayO = devAlloc<float4>(numSlots);
+    s.rayD = devAlloc<float4>(numSlots);
+    s.atten = devAlloc<float4>(numSlots);
+    s.pcol = devAlloc<float4>(numSlots);
+    s.hit = devAlloc<float4>(numSlots);
+    s.shO = devAlloc<float4>(numSlots);
+    s.shD = devAlloc<float4>(numSlots);
+    s.shL = devAlloc<float4>(numSlots);
+    s.queueA = devAlloc<unsigned int>(numSlots);
+    s.queueB = devAlloc<unsigned int>(numSlots);
+    s.regen = devAlloc<unsigned int>(numSlots);
+    s.ctl = devAlloc<WfControl>(1);
+}
+
+extern "C" void setRendererOptions(const renderer_options* opt) {
+    if (opt) g_opts = *opt;
+    else g_opts = renderer_options{-1, 0u, 0, 0, 0, {0, 0, 0}};
+}
+
+extern "C" void setRendererProfiling(int on) { g_profiling = on; }
+
+static void initCommon(RendererContext& c, const camera& cam, vec3** fb, int nx, int ny, int maxDepth) {
+    if (g_opts.device >= 0) CRT_CHECK(cudaSetDevice(g_opts.device));
+    int dev = 0;
+    CRT_CHECK(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CRT_CHECK(cudaGetDeviceProperties(&prop, dev));
+    c.numSMs = prop.multiProcessorCount;
+    c.opts = g_opts;
+    c.nx = nx;
+    c.ny = ny;
+    c.maxDepth = maxDepth;
+    c.cam.origin = toF3(cam.origin);
+    c.cam.lowerLeft = toF3(cam.lower_left_corner);
+    c.cam.horizontal = toF3(cam.horizontal);
+    c.cam.vertical = toF3(cam.vertical);
+    c.cam.u = toF3(cam.u);
+    c.cam.v = toF3(cam.v);
+    c.cam.w = toF3(cam.w);
+    c.cam.lensRadius = cam.lens_radius;
+    CRT_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    CRT_CHECK(cudaEventCreate(&c.evStart));
+    CRT_CHECK(cudaEventCreate(&c.evStop));
+    const size_t npix = (size_t)nx * ny;
+    CRT_CHECK(cudaMallocManaged((void**)&c.fb, (npix ? npix : 1) * sizeof(vec3))); // kernels.cu:578-580
+    if (fb) *fb = c.fb;
+    c.wf.accum = devAlloc<float4>(npix);
+    c.ownsAccum = true;
+    CRT_CHECK(cudaMallocHost((void**)&c.hostCtl, sizeof(WfControl)));
+    std::memset(&c.stats, 0, sizeof(c.stats));
+    c.initialised = true;
+}
+
+extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb, int nx, int ny, int maxDepth) {
+    RendererContext& c = g_ctx;
+    if (c.initialised) cleanupRenderer();
+    initCommon(c, cam, fb, nx, ny, maxDepth);
+    c.kind = SCENE_MESH;
+
+    const mesh* m = sc.m;
+    const unsigned int numSlots = m->numTris;
+    // triangles: upload the caller's 64-byte records once, re-tile on the device, drop the staging copy
+    float* staging = nullptr;
+    CRT_CHECK(cudaMalloc((void**)&staging, (size_t)(numSlots ? numSlots : 1) * sizeof(triangle)));
+    CRT_CHECK(cudaMemcpy(staging, m->tris, (size_t)numSlots * sizeof(triangle), cudaMemcpyHostToDevice));
+    c.triGeom = devAlloc<float4>(3 * (size_t)numSlots);
+    c.triShade = devAlloc<float4>(3 * (size_t)numSlots);
+    if (numSlots) {
+        retileTrianglesKernel<<<(numSlots + 255) / 256, 256>>>(staging, numSlots, c.triGeom, c.triShade);
+        CRT_CHECK(cudaGetLastError());
+    }
+    CRT_CHECK(cudaDeviceSynchronize());
+    CRT_CHECK(cudaFree(staging));
+    c.numTriSlots = numSlots;
+
+    // nodes: the caller's bytes, padded so the last 48-byte child-pair load stays in bounds
+    const size_t nodeBytes = (size_t)m->numBvhNodes * sizeof(bvh_node);
+    CRT_CHECK(cudaMalloc((void**)&c.nodes, nodeBytes + 64));
+    CRT_CHECK(cudaMemset(c.nodes, 0, nodeBytes + 64));
+    CRT_CHECK(cudaMemcpy(c.nodes, m->bvh, nodeBytes, cudaMemcpyHostToDevice));
+
+    c.mesh.nodes = c.nodes;
+    c.mesh.tris = c.triGeom;
+    c.mesh.firstLeaf = (unsigned int)(m->numBvhNodes / 2); // kernels.cu:614
+    c.mesh.primsPerLeaf = (unsigned int)sc.numPrimitivesPerLeaf;
+    c.mesh.boundsMin = toF3(m->bounds.min);
+    c.mesh.boundsMax = toF3(m->bounds.max);
+
+    // materials (helper_structs.h:133-138) as two float4 each
+    std::vector<float4> mats(2 * (size_t)(sc.numMaterials > 0 ? sc.numMaterials : 1));
+    for (int i = 0; i < sc.numMaterials; i++) {
+        const material& mt = sc.materials[i];
+        mats[2 * i] = make_float4(mt.color.e[0], mt.color.e[1], mt.color.e[2], mt.param);
+        int type = (int)mt.type, tex = mt.texId;
+        float4 b;
+        std::memcpy(&b.x, &type, 4);
+        std::memcpy(&b.y, &tex, 4);
+        b.z = b.w = 0.0f;
+        mats[2 * i + 1] = b;
+    }
+    c.materials = devAlloc<float4>(mats.size());
+    CRT_CHECK(cudaMemcpy(c.materials, mats.data(), mats.size() * sizeof(float4), cudaMemcpyHostToDevice));
+
+    // textures: float RGB, nearest lookup (kernels.cu:620-645)
+    c.numTextures = sc.numTextures;
+    std::vector<float*> texPtr(sc.numTextures > 0 ? sc.numTextures : 1, nullptr);
+    std::vector<int> texW(texPtr.size(), 0), texH(texPtr.size(), 0);
+    for (int i = 0; i < sc.numTextures; i++) {
+        const stexture& t = sc.textures[i];
+        texW[i] = t.width;
+        texH[i] = t.height;
+        const size_t bytes = (size_t)t.width * t.height * 3 * sizeof(float);
+        CRT_CHECK(cudaMalloc((void**)&texPtr[i], bytes ? bytes : 16));
+        CRT_CHECK(cudaMemcpy(texPtr[i], t.data, bytes, cudaMemcpyHostToDevice));
+    }
+    c.texPtrHost = texPtr;
+    c.texData = devAlloc<float*>(texPtr.size());
+    c.texWidth = devAlloc<int>(texPtr.size());
+    c.texHeight = devAlloc<int>(texPtr.size());
+    CRT_CHECK(cudaMemcpy(c.texData, texPtr.data(), texPtr.size() * sizeof(float*), cudaMemcpyHostToDevice));
+    CRT_CHECK(cudaMemcpy(c.texWidth, texW.data(), texW.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CRT_CHECK(cudaMemcpy(c.texHeight, texH.data(), texH.size() * sizeof(int), cudaMemcpyHostToDevice));
+
+    // light: RenderContext default members, kernels.cu:93-94
+    c.light.center = mk3(52.514355f, 715.686951f, -272.620972f);
+    c.light.radius = 50.0f;
+    c.light.color = mk3(20.0f, 20.0f, 20.0f);
+}
+
+static ShadeScene shadeScene(const RendererContext& c) {
+    ShadeScene s;
+    s.triShade = c.triShade;
+    s.mats.mats = c.materials;
+    s.mats.texData = c.texData;
+    s.mats.texWidth = c.texWidth;
+    s.mats.texHeight = c.texHeight;
+    s.light = c.light;
+    s.maxDepth = c.maxDepth;
+    return s;
+}
+
+// One wavefront iteration on `stream`: extend -> shade -> shadow -> raygen -> advance.
+static void launchIteration(RendererContext& c, cudaStream_t stream, unsigned int* qCur, unsigned int* qNext, int samplesPerSlot,
+                            int slotsPerPixel, cudaEvent_t* ev) {
+    const int persistent = c.numSMs * 8;
+    const int wide = c.numSMs * 8;
+    if (ev) cudaEventRecord(ev[0], stream);
+    if (c.counting) extendKernel<true><<<persistent, WF_BLOCK, 0, stream>>>(c.wf, c.mesh, qCur);
+    else extendKernel<false><<<persistent, WF_BLOCK, 0, stream>>>(c.wf, c.mesh, qCur);
+    if (ev) cudaEventRecord(ev[1], stream);
+    shadeKernel<<<wide, WF_BLOCK, 0, stream>>>(c.wf, shadeScene(c), qCur, qNext);
+    if (ev) cudaEventRecord(ev[2], stream);
+    if (c.counting) shadowKernel<true><<<persistent, WF_BLOCK, 0, stream>>>(c.wf, c.mesh);
+    else shadowKernel<false><<<persistent, WF_BLOCK, 0, stream>>>(c.wf, c.mesh);
+    if (ev) cudaEventRecord(ev[3], stream);
+    raygenKernel<false><<<wide, WF_BLOCK, 0, stream>>>(c.wf, c.cam, qNext, c.nx, c.ny, samplesPerSlot, slotsPerPixel, c.opts.sampleStream);
+    advanceKernel<<<1, 1, 0, stream>>>(c.wf.ctl);
+    if (ev) cudaEventRecord(ev[4], stream);
+}
+
+#define KERNELS_PER_ITERATION 5
+
+void crtRunMesh(RendererContext& c, int ns) {
+    const unsigned int npix = (unsigned int)c.nx * (unsigned int)c.ny;
+    int slotsPerPixel = c.opts.reserved[0] > 0 ? c.opts.reserved[0] : 1;
+    if (ns % slotsPerPixel != 0) slotsPerPixel = 1;
+    const int samplesPerSlot = ns / slotsPerPixel;
+    allocWavefront(c, npix * (unsigned int)slotsPerPixel);
+    cudaStream_t stream = c.stream;
+
+    std::memset(&c.stats, 0, sizeof(c.stats));
+    c.stats.samples = (unsigned long long)npix * (unsigned long long)(ns > 0 ? ns : 0);
+    CRT_CHECK(cudaEventRecord(c.evStart, stream));
+    CRT_CHECK(cudaMemsetAsync(c.wf.accum, 0, (size_t)npix * sizeof(float4), stream));
+    CRT_CHECK(cudaMemsetAsync(c.wf.ctl, 0, sizeof(WfControl), stream));
+    unsigned long long launches = 0;
+
+    if (npix > 0 && ns > 0 && c.maxDepth > 0) {
+        const int wide = c.numSMs * 8;
+        raygenKernel<true><<<wide, WF_BLOCK, 0, stream>>>(c.wf, c.cam, c.wf.queueA, c.nx, c.ny, samplesPerSlot, slotsPerPixel,
+                                                          c.opts.sampleStream);
+        advanceKernel<<<1, 1, 0, stream>>>(c.wf.ctl);
+        launches += 2;
+        CRT_CHECK(cudaGetLastError());
+
+        int batch = c.opts.megaBatch > 0 ? c.opts.megaBatch : 16;
+        batch = (batch + 1) & ~1; // even: the two queues swap roles every iteration
+        if (g_profiling) {
+            cudaEvent_t ev[5];
+            for (auto& e : ev) CRT_CHECK(cudaEventCreate(&e));
+            c.stats.profiled = 1;
+            bool flip = false;
+            while (true) {
+                launchIteration(c, stream, flip ? c.wf.queueB : c.wf.queueA, flip ? c.wf.queueA : c.wf.queueB, samplesPerSlot,
+                                slotsPerPixel, ev);
+                flip = !flip;
+                launches += KERNELS_PER_ITERATION;
+                CRT_CHECK(cudaMemcpyAsync(c.hostCtl, c.wf.ctl, sizeof(WfControl), cudaMemcpyDeviceToHost, stream));
+                CRT_CHECK(cudaStreamSynchronize(stream));
+                float ms;
+                cudaEventElapsedTime(&ms, ev[0], ev[1]); c.stats.msExtend += ms;
+                cudaEventElapsedTime(&ms, ev[1], ev[2]); c.stats.msShade += ms;
+                cudaEventElapsedTime(&ms, ev[2], ev[3]); c.stats.msShadow += ms;
+                cudaEventElapsedTime(&ms, ev[3], ev[4]); c.stats.msOther += ms;
+                if (c.hostCtl->countActive == 0) break;
+            }
+            if (flip) { /* an odd number of iterations ran: harmless, queues are scratch */ }
+            for (auto& e : ev) cudaEventDestroy(e);
+        } else {
+            const long long key = ((long long)samplesPerSlot << 24) ^ ((long long)slotsPerPixel << 8) ^ batch ^
+                                  ((long long)c.counting << 60) ^ ((long long)c.maxDepth << 40);
+            if (!c.graphExec || c.graphKey != key) {
+                if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
+                cudaGraph_t graph;
+                CRT_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+                for (int k = 0; k < batch; k++) {
+                    const bool flip = (k & 1) != 0;
+                    launchIteration(c, stream, flip ? c.wf.queueB : c.wf.queueA, flip ? c.wf.queueA : c.wf.queueB, samplesPerSlot,
+                                    slotsPerPixel, nullptr);
+                }
+                CRT_CHECK(cudaStreamEndCapture(stream, &graph));
+                CRT_CHECK(cudaGraphInstantiate(&c.graphExec, graph, 0));
+                CRT_CHECK(cudaGraphDestroy(graph));
+                c.graphKey = key;
+            }
+            while (true) {
+                CRT_CHECK(cudaGraphLaunch(c.graphExec, stream));
+                launches += (unsigned long long)batch * KERNELS_PER_ITERATION;
+                CRT_CHECK(cudaMemcpyAsync(c.hostCtl, c.wf.ctl, sizeof(WfControl), cudaMemcpyDeviceToHost, stream));
+                CRT_CHECK(cudaStreamSynchronize(stream));
+                if (c.hostCtl->countActive == 0) break;
+            }
+        }
+    } else {
+        CRT_CHECK(cudaMemcpyAsync(c.hostCtl, c.wf.ctl, sizeof(WfControl), cudaMemcpyDeviceToHost, stream));
+    }
+
+    if (!c.opts.deferFinalize) {
+        if (npix) finalizeKernel<<<(npix + 255) / 256, 256, 0, stream>>>(c.wf.accum, (float*)c.fb, npix, float(ns));
+        launches += 1;
+    }
+    CRT_CHECK(cudaEventRecord(c.evStop, stream));
+    CRT_CHECK(cudaStreamSynchronize(stream));
+    CRT_CHECK(cudaGetLastError());
+    CRT_CHECK(cudaEventElapsedTime(&c.stats.msTotal, c.evStart, c.evStop));
+    c.stats.raysExtend = c.hostCtl->raysExtend;
+    c.stats.raysShadow = c.hostCtl->raysShadow;
+    c.stats.iterations = c.hostCtl->iterations;
+    c.stats.kernelLaunches = launches;
+    c.lastNodeVisits = c.hostCtl->nodeVisits;
+    c.lastTriTests = c.hostCtl->triTests;
+}
+
+extern "C" void runRenderer(int ns, int tx, int ty) {
+    (void)tx; (void)ty; // launch-shape hints of the megakernel; the wavefront kernels size themselves
+    RendererContext& c = g_ctx;
+    if (!c.initialised) {
+        std::fprintf(stderr, "runRenderer called before initRenderer\n");
+        std::exit(99);
+    }
+    if (c.kind == SCENE_MESH) crtRunMesh(c, ns);
+    else crtRunSpheres(c, ns);
+}
+
+extern "C" void finalizeFrame(int nsTotal) {
+    RendererContext& c = g_ctx;
+    if (!c.initialised) return;
+    const unsigned int npix = (unsigned int)c.nx * (unsigned int)c.ny;
+    if (npix) finalizeKernel<<<(npix + 255) / 256, 256, 0, c.stream>>>(c.wf.accum, (float*)c.fb, npix, float(nsTotal));
+    CRT_CHECK(cudaGetLastError());
+    CRT_CHECK(cudaStreamSynchronize(c.stream));
+}
+
+extern "C" void* getRendererAccumDevice() { return g_ctx.initialised ? (void*)g_ctx.wf.accum : nullptr; }
+
+extern "C" void setRendererAccumDevice(void* dAccum) {
+    RendererContext& c = g_ctx;
+    if (!c.initialised || !dAccum) return;
+    if (c.ownsAccum) cudaFree(c.wf.accum);
+    c.wf.accum = (float4*)dAccum;
+    c.ownsAccum = false;
+}
+
+extern "C" void getRendererStats(renderer_stats* out) {
+    if (out) *out = g_ctx.stats;
+}
+
+extern "C" void setRendererCounting(int on) {
+    g_ctx.counting = on != 0;
+}
+
+extern "C" void getRendererTraversalCounts(unsigned long long* nodeVisits, unsigned long long* triTests) {
+    if (nodeVisits) *nodeVisits = g_ctx.lastNodeVisits;
+    if (triTests) *triTests = g_ctx.lastTriTests;
+}
+
+extern "C" void cleanupRenderer() {
+    RendererContext& c = g_ctx;
+    if (!c.initialised) return;
+    CRT_CHECK(cudaDeviceSynchronize());
+    freeWavefront(c);
+    if (c.ownsAccum) cudaFree(c.wf.accum);
+    c.wf.accum = nullptr;
+    cudaFree(c.fb);
+    cudaFree(c.triGeom); cudaFree(c.triShade); cudaFree(c.nodes); cudaFree(c.materials);
+    for (float* p : c.texPtrHost) cudaFree(p);
+    c.texPtrHost.clear();
+    cudaFree(c.texData); cudaFree(c.texWidth); cudaFree(c.texHeight);
+    cudaFreeHost(c.hostCtl);
+    cudaEventDestroy(c.evStart); cudaEventDestroy(c.evStop);
+    cudaStreamDestroy(c.stream);
+    const bool reset = c.opts.resetDeviceOnCleanup != 0;
+    c = RendererContext();
+    if (reset) cudaDeviceReset(); // kernels.cu:679
+}
+
+// ------------------------------------------------------------- ray batches --
+extern "C" float intersectBatchDevice(const void* dRayO, const void* dRayD, long long n, void* dHit, int* dMeshId) {
+    RendererContext& c = g_ctx;
+    if (!c.initialised || c.kind != SCENE_MESH) {
+        std::fprintf(stderr, "intersectBatchDevice needs a mesh scene (initRenderer)\n");
+        std::exit(99);
+    }
+    unsigned int* cursor = devAlloc<unsigned int>(2);
+    unsigned long long* counts = devAlloc<unsigned long long>(2);
+    CRT_CHECK(cudaMemsetAsync(cursor, 0, 2 * sizeof(unsigned int), c.stream));
+    CRT_CHECK(cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), c.stream));
+    const int blocks = c.numSMs * 8;
+    CRT_CHECK(cudaEventRecord(c.evStart, c.stream));
+    if (c.counting)
+        intersectBatchKernel<true><<<blocks, WF_BLOCK, 0, c.stream>>>(c.mesh, c.triShade, (const float4*)dRayO, (const float4*)dRayD,
+                                                                    (unsigned long long)n, (float4*)dHit, dMeshId, cursor, counts);
+    else
+        intersectBatchKernel<false><<<blocks, WF_BLOCK, 0, c.stream>>>(c.mesh, c.triShade, (const float4*)dRayO, (const float4*)dRayD,
+                                                                     (unsigned long long)n, (float4*)dHit, dMeshId, cursor, counts);
+    CRT_CHECK(cudaEventRecord(c.evStop, c.stream));
+    CRT_CHECK(cudaGetLastError());
+    CRT_CHECK(cudaStreamSynchronize(c.stream));
+    float ms = 0.0f;
+    CRT_CHECK(cudaEventElapsedTime(&ms, c.evStart, c.evStop));
+    if (c.counting) {
+        unsigned long long h[2];
+        CRT_CHECK(cudaMemcpy(h, counts, sizeof(h), cudaMemcpyDeviceToHost));
+        c.lastNodeVisits = h[0];
+        c.lastTriTests = h[1];
+    }
+    cudaFree(cursor);
+    cudaFree(counts);
+    return ms;
+}
+
+extern "C" void generateRayBatchDevice(void* dRayO, void* dRayD, long long n, int filmW, int filmH, float tMin, float tMax) {
+    RendererContext& c = g_ctx;
+    if (!c.initialised) {
+        std::fprintf(stderr, "generateRayBatchDevice called before initRenderer\n");
+        std::exit(99);
+    }
+    const unsigned int blocks = (unsigned int)((n + 255) / 256);
+    if (n > 0)
+        generateRayBatchKernel<<<blocks, 256, 0, c.stream>>>((float4*)dRayO, (float4*)dRayD, (unsigned long long)n, c.cam, c.mesh.boundsMin,
+                                                            c.mesh.boundsMax, filmW, filmH, tMin, tMax);
+    CRT_CHECK(cudaGetLastError());
+    CRT_CHECK(cudaStreamSynchronize(c.stream));
+}
+
+extern "C" void intersectBatch(const float* origins, const float* dirs, long long n, float tMin, float tMax, float* outT, int* outTriId,
+                               int* outMeshId) {
+    if (n <= 0) return;
+    std::vector<float4> o((size_t)n), d((size_t)n);
+    for (long long i = 0; i < n; i++) {
+        o[i] = make_float4(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2], tMin);
+        d[i] = make_float4(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], tMax);
+    }
+    float4* dO = devAlloc<float4>((size_t)n);
+    float4* dD = devAlloc<float4>((size_t)n);
+    float4* dH = devAlloc<float4>((size_t)n);
+    int* dM = devAlloc<int>((size_t)n);
+    CRT_CHECK(cudaMemcpy(dO, o.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice));
+    CRT_CHECK(cudaMemcpy(dD, d.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice));
+    intersectBatchDevice(dO, dD, n, dH, dM);
+    std::vector<float4> h((size_t)n);
+    CRT_CHECK(cudaMemcpy(h.data(), dH, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));
+    if (outMeshId) CRT_CHECK(cudaMemcpy(outMeshId, dM, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    for (long long i = 0; i < n; i++) {
+        if (outT) outT[i] = h[i].x;
+        if (outTriId) std::memcpy(&outTriId[i], &h[i].w, 4);
+    }
+    cudaFree(dO); cudaFree(dD); cudaFree(dH); cudaFree(dM);
+}
+
+extern "C" void* rendererDeviceAlloc(size_t bytes) {
+    void* p = nullptr;
+    CRT_CHECK(cudaMalloc(&p, bytes ? bytes : 16));
+    return p;
+}
+extern "C" void rendererDeviceFree(void* p) { cudaFree(p); }
+extern "C" void rendererCopyToHost(void* dst, const void* dSrc, size_t bytes) {
+    CRT_CHECK(cudaMemcpy(dst, dSrc, bytes, cudaMemcpyDeviceToHost));
+}
+extern "C" void rendererCopyToDevice(void* dDst, const void* src, size_t bytes) {
+    CRT_CHECK(cudaMemcpy(dDst, src, bytes, cudaMemcpyHostToDevice));
+}
+
+#include "spheres_path.cuh"

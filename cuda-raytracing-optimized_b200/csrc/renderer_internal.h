@@ -1,0 +1,63 @@
+// renderer_internal.h -- process-wide renderer state shared by the translation units of libcrt_b200.so.
+// One context per process, like the reference's global `renderContext` (kernels.cu:145): the ABI is not
+// re-entrant and neither was the reference's.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "device_scene.cuh"
+#include "kernels.h"
+
+#define CRT_CHECK(val) crtCheckCuda((val), #val, __FILE__, __LINE__)
+void crtCheckCuda(cudaError_t result, const char* func, const char* file, int line);
+
+enum SceneKind { SCENE_NONE = 0, SCENE_MESH = 1, SCENE_SPHERES = 2 };
+
+struct RendererContext {
+    bool initialised = false;
+    SceneKind kind = SCENE_NONE;
+    renderer_options opts = {-1, 0u, 0, 0, 0, {0, 0, 0}};
+    int numSMs = 0;
+    int nx = 0, ny = 0, maxDepth = 0;
+    CameraDev cam;
+    LightDesc light;
+    vec3* fb = nullptr; // managed memory, handed to the caller (kernels.cu:578-580)
+
+    // mesh scene
+    float4* triGeom = nullptr;
+    float4* triShade = nullptr;
+    float4* nodes = nullptr;
+    float4* materials = nullptr;
+    float** texData = nullptr;
+    int* texWidth = nullptr;
+    int* texHeight = nullptr;
+    std::vector<float*> texPtrHost;
+    int numTextures = 0;
+    unsigned int numTriSlots = 0;
+    MeshView mesh;
+
+    // sphere scene
+    int numSpheres = 0;
+    int skyMode = 0;
+
+    // wavefront state
+    WfState wf = {};
+    bool ownsAccum = false;
+    WfControl* hostCtl = nullptr; // pinned
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    cudaGraphExec_t graphExec = nullptr;
+    long long graphKey = -1;
+
+    bool counting = false;
+    unsigned long long lastNodeVisits = 0, lastTriTests = 0;
+    renderer_stats stats = {};
+};
+
+extern RendererContext g_ctx;
+extern renderer_options g_opts;
+
+void crtRunMesh(RendererContext& c, int ns);
+void crtRunSpheres(RendererContext& c, int ns);

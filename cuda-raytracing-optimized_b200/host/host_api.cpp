@@ -217,7 +217,7 @@ void buildStaircase(MeshGen& g) {
 
     // two chairs: seat, back, four legs
     for (int c = 0; c < 2; c++) {
-        float cx = 130 + 120 * c, cz = 240 - 170 * c;
+        float cx = 150 + 110 * c, cz = -40 + 170 * c;
         g.box(vec3(cx - 24, 44, cz - 24), vec3(cx + 24, 50, cz + 24), 10, M_WOODCHAIR);
         g.box(vec3(cx - 22, 50, cz - 22), vec3(cx + 22, 56, cz + 22), 10, M_SEAT);
         g.box(vec3(cx - 24, 50, cz - 28), vec3(cx + 24, 112, cz - 23), 12, M_WOODCHAIR);
@@ -226,18 +226,18 @@ void buildStaircase(MeshGen& g) {
     }
 
     // side table with glass vase, candles, steel and gold balls
-    g.cylinder(vec3(210, 0, 330), 5, 70, 24, 6, M_ALU);
-    g.cylinder(vec3(210, 70, 330), 46, 4, 64, 1, M_ALU);
-    g.lathe(vec3(210, 74.5f, 330), [](float v) { return 7 + 9 * std::sin(2.6f * v) + 3 * v; }, [](float v) { return 58 * v; }, 96, 64,
+    g.cylinder(vec3(170, 0, 60), 5, 70, 24, 6, M_ALU);
+    g.cylinder(vec3(170, 70, 60), 46, 4, 64, 1, M_ALU);
+    g.lathe(vec3(170, 74.5f, 60), [](float v) { return 7 + 9 * std::sin(2.6f * v) + 3 * v; }, [](float v) { return 58 * v; }, 96, 64,
             M_GLASS); // open vase (single sheet: a thin glass shell)
-    g.sphereMesh(vec3(236, 86, 318), 11.5f, 96, M_STEEL);
-    g.sphereMesh(vec3(188, 84, 350), 9.5f, 96, M_GOLD);
-    for (int k = 0; k < 3; k++) g.cylinder(vec3(196.f + 9 * k, 74.5f, 306.f + 5 * k), 2.4f, 18.f + 5 * k, 20, 3, M_CANDLE);
+    g.sphereMesh(vec3(196, 86, 48), 11.5f, 96, M_STEEL);
+    g.sphereMesh(vec3(148, 84, 80), 9.5f, 96, M_GOLD);
+    for (int k = 0; k < 3; k++) g.cylinder(vec3(156.f + 9 * k, 74.5f, 36.f + 5 * k), 2.4f, 18.f + 5 * k, 20, 3, M_CANDLE);
 
     // big glass ball and plastic ball on the floor in front of the camera, steel torus
-    g.sphereMesh(vec3(40, 36.5f, 250), 36, 176, M_GLASS);
-    g.sphereMesh(vec3(-60, 24.5f, 330), 24, 128, M_PLASTIC);
-    g.torus(vec3(95, 10.5f, 360), 30, 10, 160, 48, M_STEEL);
+    g.sphereMesh(vec3(50, 36.5f, 110), 36, 176, M_GLASS);
+    g.sphereMesh(vec3(110, 24.5f, 190), 24, 128, M_PLASTIC);
+    g.torus(vec3(10, 10.5f, 200), 30, 10, 160, 48, M_STEEL);
 
     // floor lamp: wooden pole, fabric shade (open cone frustum), brass finial
     g.cylinder(vec3(300, 0, -60), 16, 5, 48, 1, M_WOODLAMP);

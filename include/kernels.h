@@ -49,7 +49,8 @@ typedef struct renderer_options {
     int resetDeviceOnCleanup; // 1: cleanupRenderer ends with cudaDeviceReset() like kernels.cu:679
                               //    (default 0: fatal inside a process that shares the device, e.g. torch)
     int megaBatch;            // iterations launched between host checks of the live-path counter (0 = default)
-    int reserved[3];
+    int reserved[3];          // [0]: path slots per pixel (0/1 = one slot per pixel = the reference's RNG streams;
+                              //      k > 1 = k independent streams per pixel, ns/k samples each, throughput mode)
 } renderer_options;
 
 // Applies to the NEXT initRenderer* call.  Passing NULL restores the defaults.
@@ -76,9 +77,9 @@ void intersectBatch(const float* origins, const float* dirs, long long n, float 
 // Used by the 64 Mi-ray microbench (BASELINE config 5).  Returns kernel ms.
 float intersectBatchDevice(const void* dRayO, const void* dRayD, long long n, void* dHit, int* dMeshId);
 
-// Fills device ray buffers with the config-5 batch: even
-// indices are jittered camera rays over a virtual filmW x filmH film, odd
-// indices are incoherent rays (origin uniform in the scene bounds, direction
+// Fills device ray buffers with the config-5 batch: the first
+// half are jittered camera rays over a virtual filmW x filmH film, the second
+// half are incoherent rays (origin uniform in the scene bounds, direction
 // from the unit-sphere rejection sampler), seeded per ray with the
 // kernels.cu:542 formula applied to the ray index.
 void generateRayBatchDevice(void* dRayO, void* dRayD, long long n, int filmW, int filmH, float tMin, float tMax);
@@ -107,7 +108,13 @@ void setRendererProfiling(int on);
 // pixel: r,g,b,unused) live on the device.  A launcher with one process per
 // GPU reduces them with NCCL and calls finalizeFrame on the root.
 void* getRendererAccumDevice();   // device pointer, nx*ny float4
+void setRendererAccumDevice(void* dAccum); // render into a caller-owned device buffer (e.g. a torch tensor) instead
 void finalizeFrame(int nsTotal);  // fb = accum / nsTotal (blocking)
+
+// Instrumentation for the flop side of the roofline: when on, the traversal kernels count
+// internal-node visits (two slab tests each) and triangle tests.  Never on in timed runs.
+void setRendererCounting(int on);
+void getRendererTraversalCounts(unsigned long long* nodeVisits, unsigned long long* triTests);
 
 #ifdef __cplusplus
 }
