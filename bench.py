@@ -1,0 +1,444 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark: Mrays/s of the staircase render path (BASELINE.json config 3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload staircase|rtiow|raybatch]
+
+A "step" is one frame: runRenderer(ns) over a scene that initRenderer has already put in HBM (`value`), or the whole
+reference-facing call sequence from HOST buffers -- initRenderer + runRenderer + reading the frame -- (`e2e`).
+Workload at N = 1: the procedural staircase-class mesh (~312 k triangles, BVH_00.04 layout, 17 levels x 5 per leaf),
+1200x800, 100 spp, depth 64, the reference's own RNG seeding -- the frame is bit-identical to the reference kernel's,
+so both arms trace exactly the same rays.  configs[1] (RTIOW spheres) is NOT the default because the reference's HEAD
+contains no sphere renderer to put in the reference arm; it is available as --workload rtiow.
+At N > 1 every rank renders `spp` samples of every pixel on its own RNG stream (weak scaling: N x spp in total) and
+the un-normalised float4 sums are combined with ONE NCCL reduce to rank 0 at frame end.
+
+The reference arm (--impl reference) is the reference's own CUDA kernel (oracle/_ref/libref.so, compiled unmodified
+from /root/reference for sm_100a) driven through its three entry points by oracle/_ref/ref_driver on the same GPU:
+the reference has no CPU path; a CPU restatement (oracle/cpu_oracle.cpp) is reported as `cpu_baseline`.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "cuda-raytracing-optimized_b200", "python"))
+
+FLT_MAX = 3.4028234663852886e38
+EXTEND_BYTES_PER_RAY = 52   # queue index 4 + {origin,rng} 16 + {dir,flags} 16 read, {t,u,v,id} 16 written
+BATCH_BYTES_PER_RAY = 52    # 32 in, 16 + 4 out
+
+
+def shard_samples(ns_total, world):
+    """Samples per rank: ns_total split as evenly as possible, larger shares first."""
+    base, extra = divmod(ns_total, world)
+    return [base + (1 if r < extra else 0) for r in range(world)]
+
+
+def reduce_and_finalize(acc, ns_total, rank):
+    """The frame-end exchange: one sum-reduce of the per-rank un-normalised radiance sums to rank 0, then / ns_total.
+    `acc` is a torch tensor (..., 4). Used with NCCL on device buffers by this file and with gloo by tests/test_multi_rank.py."""
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
+    return acc / float(ns_total) if rank == 0 else None
+
+
+def peaks():
+    p = dict(hbm_gbs=6650.0, src="fallback (B200_PROFILING.md)", sm_max_mhz=1965.0)
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        m = json.load(open(path))
+        p = dict(hbm_gbs=float(m["hbm_gbs"]), src="MEASURED_PEAKS.json", sm_max_mhz=float(m.get("sm_max_mhz", 1965.0)))
+    return p
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                                          str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 7 and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=float(self.rows[0][1]), reasons=reasons, samples=len(sm))
+
+
+def workload_params(args):
+    if args.workload == "staircase":
+        return dict(workload="staircase mesh %dx%d %dspp/GPU depth %d (BASELINE config 3)" % (args.nx, args.ny, args.spp, args.depth),
+                    scene="procedural staircase detail %.2f, %d^2 textures, 5 prims/leaf" % (args.detail, args.tex))
+    if args.workload == "rtiow":
+        return dict(workload="RTIOW 488 spheres %dx%d %dspp/GPU depth 50 (BASELINE config 2)" % (args.nx, args.ny, args.spp),
+                    scene="host LCG seed 1, spheres in __constant__")
+    return dict(workload="ray batch %d rays vs staircase BVH (BASELINE config 5)" % args.rays,
+                scene="procedural staircase detail %.2f" % args.detail)
+
+
+RAYCOUNT_FILE = os.path.join(ROOT, "profiles", "raycounts.json")
+
+
+def raycount_key(args, ns):
+    if args.workload == "rtiow":
+        return "rtiow:seed1:%dx%dx%d:d50" % (args.nx, args.ny, ns)
+    return "staircase:%.3f:%d:%dx%dx%d:d%d" % (args.detail, args.tex, args.nx, args.ny, ns, args.depth)
+
+
+def known_raycount(args, ns):
+    if os.path.exists(RAYCOUNT_FILE):
+        return json.load(open(RAYCOUNT_FILE)).get(raycount_key(args, ns))
+    return None
+
+
+# ------------------------------------------------------------------------------------------------ reference arm --
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    base = dict(impl="reference", n_gpus=world, steps=args.steps, warmup=args.warmup, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic")
+    if not oracle.have_ref():
+        print(json.dumps(dict(base, unavailable="oracle/_ref (the reference's CUDA build) is not present on this box")))
+        return
+    ns = args.spp * world  # the whole job of the other arm, on the one GPU the reference can use
+    cfg = dict(workload_params(args), gpus_used=1, total_spp=ns, l2="state + textures (>230 MB) exceed L2; rewritten every step")
+    if args.workload == "staircase":
+        _, info = oracle.ref_render(args.detail, args.tex, 5, args.nx, args.ny, ns, args.depth, "-", warmup=args.warmup, steps=args.steps)
+        e2e = oracle._run([os.path.join(oracle.REF_DIR, "ref_driver"), "render_e2e", str(args.detail), str(args.tex), "5", str(args.nx),
+                           str(args.ny), str(ns), str(args.depth), "1", str(min(args.steps, 3)), "-"])
+        kind = "reference"
+    elif args.workload == "rtiow":
+        _, info = oracle.ref_spheres(1, args.nx, args.ny, ns, 50, "-", warmup=args.warmup, steps=args.steps)
+        e2e = info
+        kind = "reference-derived (oracle/ref_spheres.cu: HEAD has no sphere renderer)"
+    else:
+        print(json.dumps(dict(base, unavailable="ray-batch reference timing is part of tools/parity_report.py")))
+        return
+    ms = sum(info["ms"]) / len(info["ms"])
+    rays = known_raycount(args, ns)
+    est = False
+    if rays is None:  # estimate from a row-strided CPU sample (the reference cannot count: its STATS build does not compile on Linux)
+        scene = oracle.crt.Scene.staircase(args.detail, args.tex, 5) if args.workload == "staircase" else None
+        stride = 40
+        if scene is not None:
+            _, cnt = oracle.render(scene, args.nx, args.ny, min(ns, 8), args.depth, count=True, row_stride=stride)
+            per_sample = (cnt["primary"] + cnt["secondary"] + cnt["shadow"]) / max(cnt["primary"], 1)
+        else:
+            _, cnt = oracle.render_spheres(oracle.crt.rtiow_scene(1), args.nx, args.ny, min(ns, 8), 50, count=True, row_stride=stride)
+            per_sample = (cnt["primary"] + cnt["secondary"]) / max(cnt["primary"], 1)
+        rays = int(per_sample * args.nx * args.ny * ns)
+        est = True
+    value = rays / (ms * 1e3)
+    e2e_ms = sum(e2e["ms"]) / len(e2e["ms"])
+    line = dict(base, metric="Mrays/s", value=value, unit="Mrays/s", ms_per_step=ms, config=cfg, rays_per_step=rays,
+                rays_estimated=est, msamples_per_s=args.nx * args.ny * ns / (ms * 1e3),
+                cpu_baseline=dict(value=value, unit="Mrays/s", cores=0, kind=kind,
+                                  sample="full frame on the GPU: the reference's render path is a CUDA kernel, it has no CPU implementation"),
+                e2e=dict(value=rays / (e2e_ms * 1e3), unit="Mrays/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0, ms_per_step=e2e_ms,
+                         note="initRenderer + runRenderer + frame read per step, through the same 3 entry points"),
+                gpu_launches=args.steps)
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------ our arm --
+def scene_bytes(scene):
+    ks = scene.ks
+    tex = sum(ks.textures[i].width * ks.textures[i].height * 12 for i in range(ks.numTextures))
+    return scene.num_slots * 64 + scene.num_nodes * 24 + ks.numMaterials * 24 + tex
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import crt_b200 as crt
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    L = crt.device_lib()  # raises when the CUDA library is missing: no fallback
+    pk = peaks()
+    spheres = args.workload == "rtiow"
+    depth = 50 if spheres else args.depth
+    scene = crt.rtiow_scene(1) if spheres else crt.Scene.staircase(args.detail, args.tex, 5)
+    nx, ny, ns = args.nx, args.ny, args.spp
+    ns_total = ns * world
+    h2d = (488 * 40) if spheres else scene_bytes(scene)
+    d2h = nx * ny * 12
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allsum(x):
+        if not dist:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return float(t.item())
+
+    def allmax(x):
+        if not dist:
+            return x
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    acc = torch.zeros(ny * nx, 4, device="cuda") if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def open_frame():
+        crt.set_options(device=local_rank, sample_stream=rank, defer_finalize=1 if world > 1 else 0, slots_per_pixel=args.slots)
+        fr = crt.Frame(scene, nx, ny, depth)
+        if world > 1:
+            L.setRendererAccumDevice(acc.data_ptr())
+        return fr
+
+    def step(fr):
+        """One frame. Returns (device ms incl. the reduce, rays, launches)."""
+        L.runRenderer(ns, 8, 8)
+        st = crt.stats()
+        ms = st.msTotal
+        launches = st.kernelLaunches
+        if world > 1:
+            ev0.record()
+            dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms += ev0.elapsed_time(ev1)
+            if rank == 0:
+                L.finalizeFrame(ns_total)
+                launches += 1
+        return ms, st.raysExtend + st.raysShadow, launches
+
+    fr = open_frame()
+    for _ in range(args.warmup):
+        step(fr)
+    barrier()
+    dev_ms, rays_step, launches = 0.0, 0, 0
+    with ClockSampler(local_rank) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            ms, rays_step, l = step(fr)
+            dev_ms += ms
+            launches += l
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+    ms_per_step = allmax(dev_ms / args.steps)
+    total_rays = allsum(rays_step)
+    launches = int(allsum(launches))
+    value = total_rays / (ms_per_step * 1e3)
+    clocks = clk.summary()
+
+    # ---- roofline of the dominant kernel (extendKernel): one extra profiled step + one counting step, untimed
+    roof, extra = None, {}
+    if rank == 0 and not spheres:
+        L.setRendererProfiling(1)
+        L.runRenderer(ns, 8, 8)
+        L.setRendererProfiling(0)
+        ps = crt.stats()
+        L.setRendererCounting(1)
+        L.runRenderer(ns, 8, 8)
+        L.setRendererCounting(0)
+        import ctypes as C
+        nv, tt = C.c_ulonglong(), C.c_ulonglong()
+        L.getRendererTraversalCounts(C.byref(nv), C.byref(tt))
+        iters = max(int(ps.iterations), 1)
+        avg_ms = ps.msExtend / iters
+        bytes_per_launch = EXTEND_BYTES_PER_RAY * ps.raysExtend / iters
+        achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+        flops = 3.0 * (ps.raysExtend + ps.raysShadow) + 36.0 * nv.value + 48.0 * tt.value
+        trav_ms = ps.msExtend + ps.msShadow
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        fp32_peak = sms * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+        roof = dict(bound="hbm", kernel="extendKernel<false>", achieved=achieved, peak=pk["hbm_gbs"], unit="GB/s", frac=achieved / pk["hbm_gbs"],
+                    traffic=None, peak_source=pk["src"], avg_launch_ms=avg_ms, launches=iters, bytes_per_ray=EXTEND_BYTES_PER_RAY,
+                    note="scene (19 MB) is L2-resident by design: the kernel is bound by L2 latency and FP32 issue, not HBM; see fp32",
+                    fp32=dict(achieved=flops / (trav_ms * 1e-3) / 1e12, peak=fp32_peak, unit="TFLOP/s",
+                              frac=flops / (trav_ms * 1e-3) / 1e12 / fp32_peak, kernels="extendKernel + shadowKernel",
+                              node_visits_per_ray=nv.value / max(ps.raysExtend + ps.raysShadow, 1),
+                              tri_tests_per_ray=tt.value / max(ps.raysExtend + ps.raysShadow, 1),
+                              formula="3*rays + 36*dual-node visits + 48*triangle tests (SURVEY.md 8d)"))
+        extra = dict(kernel_ms_profiled=dict(extend=ps.msExtend, shade=ps.msShade, shadow=ps.msShadow, raygen_advance=ps.msOther,
+                                             note="per-family CUDA events, one sync per iteration (serialised)"),
+                     wavefront_iterations=iters)
+    fr.close()
+
+    # ---- e2e: host buffers -> frame on the host, through the reference-facing entry points, every step
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        fr = open_frame()                 # H2D: triangles, nodes, materials, textures (caller-owned pageable memory, as the ABI hands it over)
+        step(fr)
+        if rank == 0:
+            host = fr.frame(copy=True)    # D2H: the managed frame buffer read on the host
+        fr.close()
+    barrier()
+    e2e_ms = allmax((time.perf_counter() - t0) * 1e3 / e2e_steps)
+    e2e_value = total_rays / (e2e_ms * 1e3)
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline: the oracle port on the host cores, row-strided sample of the same frame
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    cpu = None
+    if world == 1:
+        stride, cpu_ns = 40, min(ns, 25)
+        t0 = time.perf_counter()
+        if spheres:
+            _, cnt = oracle.render_spheres(scene, nx, ny, cpu_ns, depth, count=True, row_stride=stride)
+            cr = cnt["primary"] + cnt["secondary"]
+        else:
+            _, cnt = oracle.render(scene, nx, ny, cpu_ns, depth, count=True, row_stride=stride)
+            cr = cnt["primary"] + cnt["secondary"] + cnt["shadow"]
+        sec = time.perf_counter() - t0
+        cpu = dict(value=cr / sec / 1e6, unit="Mrays/s", cores=oracle.lib().oracleNumThreads(), kind="port",
+                   sample="every %dth row of the %dx%d frame at %d spp (%d rays, %.1f s), OpenMP over rows, -O3 -ffp-contract=off" %
+                          (stride, nx, ny, cpu_ns, cr, sec))
+
+    cfg = dict(workload_params(args), parallelism="sample-sharded x%d, 1 NCCL reduce/frame" % world if world > 1 else "single GPU",
+               total_spp=ns_total, rng="reference seeding (stream = rank), %d slot(s)/pixel" % max(args.slots, 1),
+               l2="256 MB written between timed steps; path state + textures (>230 MB) exceed the 126 MB L2")
+    line = dict(metric="Mrays/s", value=value, unit="Mrays/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=cfg,
+                rays_per_step=int(total_rays), msamples_per_s=nx * ny * ns_total / (ms_per_step * 1e3), wall_ms_per_step=wall_ms / args.steps,
+                clocks=clocks, e2e=dict(value=e2e_value, unit="Mrays/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                                        ms_per_step=e2e_ms, steps=e2e_steps,
+                                        note="initRenderer (scene upload from caller-owned host memory) + runRenderer + frame read, per step"),
+                gpu_launches=launches, roofline=roof, cpu_baseline=cpu, **extra)
+    print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+def run_raybatch(args, rank, world, local_rank):
+    """BASELINE config 5: closest-hit queries on a device-resident ray batch (weak scaling: every rank its own batch)."""
+    import torch
+    import crt_b200 as crt
+    torch.cuda.set_device(local_rank)
+    L = crt.device_lib()
+    pk = peaks()
+    n = args.rays
+    scene = crt.Scene.staircase(args.detail, 64, 5)
+    crt.set_options(device=local_rank)
+    with crt.Frame(scene, 64, 64, 1):
+        dO, dD, dH, dM = (L.rendererDeviceAlloc(16 * n), L.rendererDeviceAlloc(16 * n), L.rendererDeviceAlloc(16 * n), L.rendererDeviceAlloc(4 * n))
+        L.generateRayBatchDevice(dO, dD, n, 8192, 4096, 0.01, FLT_MAX)
+        for _ in range(args.warmup):
+            L.intersectBatchDevice(dO, dD, n, dH, dM)
+        with ClockSampler(local_rank) as clk:
+            ms = [L.intersectBatchDevice(dO, dD, n, dH, dM) for _ in range(args.steps)]
+        L.setRendererCounting(1)
+        L.intersectBatchDevice(dO, dD, n, dH, dM)
+        L.setRendererCounting(0)
+        import ctypes as C
+        nv, tt = C.c_ulonglong(), C.c_ulonglong()
+        L.getRendererTraversalCounts(C.byref(nv), C.byref(tt))
+        # e2e: host rays in, host hits out
+        ro, rd = np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32)
+        L.rendererCopyToHost(ro.ctypes.data, dO, 16 * n)
+        L.rendererCopyToHost(rd.ctypes.data, dD, 16 * n)
+        hit, mesh = np.zeros((n, 4), np.float32), np.zeros(n, np.int32)
+        t0 = time.perf_counter()
+        L.rendererCopyToDevice(dO, ro.ctypes.data, 16 * n)
+        L.rendererCopyToDevice(dD, rd.ctypes.data, 16 * n)
+        L.intersectBatchDevice(dO, dD, n, dH, dM)
+        L.rendererCopyToHost(hit.ctypes.data, dH, 16 * n)
+        L.rendererCopyToHost(mesh.ctypes.data, dM, 4 * n)
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        for p in (dO, dD, dH, dM):
+            L.rendererDeviceFree(p)
+    if rank != 0:
+        return
+    avg = sum(ms) / len(ms)
+    achieved = BATCH_BYTES_PER_RAY * n / (avg * 1e-3) / 1e9
+    flops = 3.0 * n + 36.0 * nv.value + 48.0 * tt.value
+    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    fp32_peak = sms * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+    line = dict(metric="Mrays/s", value=n * world / (avg * 1e3), unit="Mrays/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=avg,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload_params(args), l2="ray batch (%d MB) exceeds L2" % (52 * n >> 20)), clocks=clk.summary(),
+                e2e=dict(value=n / (e2e_ms * 1e3), unit="Mrays/s", h2d_bytes_per_step=32 * n, d2h_bytes_per_step=20 * n, ms_per_step=e2e_ms),
+                gpu_launches=args.steps,
+                roofline=dict(bound="hbm", kernel="intersectBatchKernel<false>", achieved=achieved, peak=pk["hbm_gbs"], unit="GB/s",
+                              frac=achieved / pk["hbm_gbs"], traffic=None, peak_source=pk["src"],
+                              fp32=dict(achieved=flops / (avg * 1e-3) / 1e12, peak=fp32_peak, unit="TFLOP/s", frac=flops / (avg * 1e-3) / 1e12 / fp32_peak,
+                                        node_visits_per_ray=nv.value / n, tri_tests_per_ray=tt.value / n)),
+                cpu_baseline=None)
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="staircase", choices=["staircase", "rtiow", "raybatch"])
+    ap.add_argument("--nx", type=int, default=1200)
+    ap.add_argument("--ny", type=int, default=800)
+    ap.add_argument("--spp", type=int, default=100)
+    ap.add_argument("--depth", type=int, default=64)
+    ap.add_argument("--detail", type=float, default=1.0)
+    ap.add_argument("--tex", type=int, default=1024)
+    ap.add_argument("--rays", type=int, default=1 << 26)
+    ap.add_argument("--slots", type=int, default=0, help="path slots per pixel (0/1 = reference RNG streams)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1:  # python bench.py --gpus N without torchrun: re-launch under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(29400 + os.getpid() % 500)] + sys.argv
+        sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    elif args.workload == "raybatch":
+        run_raybatch(args, rank, world, local_rank)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -495,16 +495,16 @@ Ctx makeCtx(const kernel_scene* sc, const camera* cam, int nx, int ny, int ns, i
 
 extern "C" {
 
-// render(), kernels.cu:535-569, for rows [rowBegin, rowEnd). counters (may be NULL): primary, secondary, shadow, nodeVisits, triTests.
+// render(), kernels.cu:535-569, for rows rowBegin, rowBegin+rowStride, ... < rowEnd (other rows of fb are left untouched). counters (may be NULL): primary, secondary, shadow, nodeVisits, triTests.
 void oracleRender(const kernel_scene* sc, const camera* cam, int nx, int ny, int ns, int maxDepth, unsigned int sampleStream,
-                  int rowBegin, int rowEnd, vec3* fb, unsigned long long* counters) {
+                  int rowBegin, int rowEnd, int rowStride, vec3* fb, unsigned long long* counters) {
     const Ctx c = makeCtx(sc, cam, nx, ny, ns, maxDepth);
     Counters total;
 #pragma omp parallel
     {
         Counters local;
 #pragma omp for schedule(dynamic, 1)
-        for (int j = rowBegin; j < rowEnd; j++)
+        for (int j = rowBegin; j < rowEnd; j += rowStride)
             for (int i = 0; i < nx; i++) {
                 Path p;
                 uint32_t pixelId = (uint32_t)(j * nx + i);
@@ -537,13 +537,13 @@ void oracleRender(const kernel_scene* sc, const camera* cam, int nx, int ny, int
 }
 
 void oracleRenderSpheres(const sphere* sph, const material* mats, int n, const camera* cam, int nx, int ny, int ns, int maxDepth,
-                         unsigned int sampleStream, int rowBegin, int rowEnd, vec3* fb, unsigned long long* counters) {
+                         unsigned int sampleStream, int rowBegin, int rowEnd, int rowStride, vec3* fb, unsigned long long* counters) {
     Counters total;
 #pragma omp parallel
     {
         Counters local;
 #pragma omp for schedule(dynamic, 1)
-        for (int j = rowBegin; j < rowEnd; j++)
+        for (int j = rowBegin; j < rowEnd; j += rowStride)
             for (int i = 0; i < nx; i++) {
                 Path p;
                 uint32_t pixelId = (uint32_t)(j * nx + i);

@@ -25,9 +25,9 @@ def lib():
             subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "cpu"], stdout=subprocess.DEVNULL)
         L = C.CDLL(path)
         L.oracleRender.argtypes = [C.POINTER(crt.KernelScene), C.POINTER(crt.Camera), C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint,
-                                   C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_ulonglong)]
+                                   C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_ulonglong)]
         L.oracleRenderSpheres.argtypes = [C.POINTER(crt.Sphere), C.POINTER(crt.Material), C.c_int, C.POINTER(crt.Camera), C.c_int,
-                                          C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_ulonglong)]
+                                          C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_ulonglong)]
         L.oracleIntersectBatch.argtypes = [C.POINTER(crt.KernelScene), C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p,
                                            C.c_void_p, C.POINTER(C.c_ulonglong)]
         L.oracleWangHash.restype = C.c_uint
@@ -53,23 +53,23 @@ def lib():
     return _lib
 
 
-def render(scene, nx, ny, ns, max_depth, cam=None, stream=0, rows=None, count=False):
+def render(scene, nx, ny, ns, max_depth, cam=None, stream=0, rows=None, count=False, row_stride=1):
     """CPU restatement of render() (kernels.cu:535). Returns (frame (ny,nx,3), counters dict or None)."""
     cam = cam or crt.staircase_camera(nx, ny)
     fb = np.zeros((ny, nx, 3), dtype=np.float32)
     r0, r1 = rows if rows else (0, ny)
     cnt = (C.c_ulonglong * 5)() if count else None
-    lib().oracleRender(C.byref(scene.ks), C.byref(cam), nx, ny, ns, max_depth, stream, r0, r1, fb.ctypes.data, cnt)
+    lib().oracleRender(C.byref(scene.ks), C.byref(cam), nx, ny, ns, max_depth, stream, r0, r1, row_stride, fb.ctypes.data, cnt)
     return fb, (dict(primary=cnt[0], secondary=cnt[1], shadow=cnt[2], nodeVisits=cnt[3], triTests=cnt[4]) if count else None)
 
 
-def render_spheres(spheres, nx, ny, ns, max_depth, cam=None, stream=0, rows=None, count=False):
+def render_spheres(spheres, nx, ny, ns, max_depth, cam=None, stream=0, rows=None, count=False, row_stride=1):
     sph, mats, n = spheres
     cam = cam or crt.rtiow_camera(nx, ny)
     fb = np.zeros((ny, nx, 3), dtype=np.float32)
     r0, r1 = rows if rows else (0, ny)
     cnt = (C.c_ulonglong * 5)() if count else None
-    lib().oracleRenderSpheres(sph, mats, n, C.byref(cam), nx, ny, ns, max_depth, stream, r0, r1, fb.ctypes.data, cnt)
+    lib().oracleRenderSpheres(sph, mats, n, C.byref(cam), nx, ny, ns, max_depth, stream, r0, r1, row_stride, fb.ctypes.data, cnt)
     return fb, (dict(primary=cnt[0], secondary=cnt[1]) if count else None)
 
 

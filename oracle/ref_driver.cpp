@@ -40,6 +40,7 @@ static double now() { return std::chrono::duration<double>(std::chrono::steady_c
 static int usage() {
     std::fprintf(stderr,
                  "usage:\n"
+                 "  render_e2e <same arguments as render>   every step = initRenderer + runRenderer + frame read\n"
                  "  render  <detail|file.bvh> <texSize> <primsPerLeaf> <nx> <ny> <ns> <maxDepth> <warmup> <steps> <out.ref|->\n"
                  "  spheres <seed> <nx> <ny> <ns> <maxDepth> <warmup> <steps> <out.ref|->      (shim build only)\n"
                  "  batch   <detail|file.bvh> <texSize> <primsPerLeaf> <rays.bin> <isShadow> <hits.bin> (shim build only)\n");
@@ -55,6 +56,34 @@ static void* makeScene(const char* spec, int texSize, int ppl) {
 int main(int argc, char** argv) {
     if (argc < 2) return usage();
     const std::string mode = argv[1];
+    if (mode == "render_e2e" && argc == 12) {
+        // every step = what a caller of the 3 entry points pays from host buffers to a host-readable frame:
+        // initRenderer (scene upload) + runRenderer + reading the frame; cleanupRenderer (a cudaDeviceReset in the
+        // reference, kernels.cu:679) is left outside the timed region for both libraries.
+        const int texSize = std::atoi(argv[3]), ppl = std::atoi(argv[4]);
+        const int nx = std::atoi(argv[5]), ny = std::atoi(argv[6]), ns = std::atoi(argv[7]), maxDepth = std::atoi(argv[8]);
+        const int warmup = std::atoi(argv[9]), steps = std::atoi(argv[10]);
+        void* scene = makeScene(argv[2], texSize, ppl);
+        if (!scene) { std::fprintf(stderr, "scene creation failed\n"); return 1; }
+        const kernel_scene ksc = *crtSceneKernelScene(scene);
+        camera cam;
+        crtStaircaseCamera(nx, ny, &cam);
+        std::vector<vec3> host((size_t)nx * ny);
+        std::printf("{\"mode\": \"render_e2e\", \"nx\": %d, \"ny\": %d, \"ns\": %d, \"maxDepth\": %d, \"ms\": [", nx, ny, ns, maxDepth);
+        for (int i = 0; i < warmup + steps; i++) {
+            vec3* fb = nullptr;
+            const double t0 = now();
+            initRenderer(ksc, cam, &fb, nx, ny, maxDepth);
+            runRenderer(ns, 8, 8);
+            std::memcpy(host.data(), fb, host.size() * sizeof(vec3));
+            const double t1 = now();
+            if (i >= warmup) std::printf("%s%.4f", i > warmup ? ", " : "", (t1 - t0) * 1e3);
+            if (i == warmup + steps - 1 && std::strcmp(argv[11], "-") != 0) crtWriteRef(argv[11], nx, ny, host.data());
+            cleanupRenderer();
+        }
+        std::printf("]}\n");
+        return 0;
+    }
     if (mode == "render" && argc == 12) {
         const int texSize = std::atoi(argv[3]), ppl = std::atoi(argv[4]);
         const int nx = std::atoi(argv[5]), ny = std::atoi(argv[6]), ns = std::atoi(argv[7]), maxDepth = std::atoi(argv[8]);
