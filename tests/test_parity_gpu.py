@@ -137,7 +137,7 @@ def test_edge_cases(crt, oracle):
 
     t = np.zeros((1, 16), np.float32)
     t[0, :9] = [-300, 0, 300, 300, 0, 300, 0, 400, 300]
-    t.view(np.uint8).reshape(-1, 64)[0, 60] = 3  # white diffuse
+    t.view(np.uint8).reshape(-1, 64)[0, 60] = 4  # ChairSeat: a dark diffuse albedo, so hit pixels differ from the sky
     one = crt.Scene.from_triangles(t, 5, 4)
     ref, _ = oracle.render(one, 33, 17, 3, 4)
     with crt.Frame(one, 33, 17, 4) as fr:
