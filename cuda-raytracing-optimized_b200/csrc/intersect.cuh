@@ -64,21 +64,21 @@ __device__ __forceinline__ bool boxHit(const f3& bmin, const f3& bmax, const Ray
     return !(tMax < tMin);
 }
 
-// triangleHit on a prepared tile. Returns FLT_MAX or t in (tMin, tMax).
+// triangleHit on a prepared tile. Returns FLT_MAX or t in (tMin, tMax). Every operation is pinned (see vecmath.cuh).
 __device__ __forceinline__ float triHit(const f3& v0, const f3& edge1, const f3& edge2, const RayPrep& r, float tMin, float tMax,
                                         float& hitU, float& hitV) {
     const float EPS = 0.0000001f;
-    f3 h = cross(r.d, edge2);
-    float a = dot(edge1, h);
+    const f3 h = cross(r.d, edge2);
+    const float a = dot(edge1, h);
     if (a > -EPS && a < EPS) return FLT_MAX;
-    float f = 1.0f / a;
-    f3 s = r.o - v0;
-    float u = f * dot(s, h);
+    const float f = __fdiv_rn(1.0f, a);
+    const f3 s = subPinned(r.o, v0);
+    const float u = __fmul_rn(f, dot(s, h));
     if (u < 0.0f || u > 1.0f) return FLT_MAX;
-    f3 q = cross(s, edge1);
-    float v = f * dot(r.d, q);
-    if (v < 0.0f || u + v > 1.0f) return FLT_MAX;
-    float t = f * dot(edge2, q);
+    const f3 q = cross(s, edge1);
+    const float v = __fmul_rn(f, dot(r.d, q));
+    if (v < 0.0f || __fadd_rn(u, v) > 1.0f) return FLT_MAX;
+    const float t = __fmul_rn(f, dot(edge2, q));
     if (t > tMin && t < tMax) {
         hitU = u;
         hitV = v;
@@ -88,11 +88,11 @@ __device__ __forceinline__ float triHit(const f3& v0, const f3& edge1, const f3&
 }
 
 __device__ __forceinline__ float sphereHitT(const f3& center, float radius, const f3& o, const f3& d, float tMin, float tMax) {
-    f3 oc = o - center;
-    float a = dot(d, d);
-    float b = dot(oc, d);
-    float c = dot(oc, oc) - radius * radius;
-    float discriminant = b * b - a * c;
+    const f3 oc = o - center;
+    const float a = dot(d, d);
+    const float b = dot(oc, d);
+    const float c = __fsub_rn(dot(oc, oc), __fmul_rn(radius, radius)); // compiled as a separate multiply and subtract
+    const float discriminant = __fmaf_rn(b, b, -__fmul_rn(a, c));
     if (discriminant > 0) {
         float temp = (-b - sqrtf(discriminant)) / a;
         if (temp < tMax && temp > tMin) return temp;

@@ -1,0 +1,416 @@
+// mesh_pipeline.cuh -- the triangle-mesh render path as a two-launch wavefront iteration.
+//
+//   traceKernel   every ray of the iteration, closest-hit (extend) and any-hit (shadow) alike, traversed by
+//                 persistent warps that refill idle lanes one by one from the trace queue; a ray that exceeds its
+//                 step budget parks its 24-byte state and is re-queued for the next launch (traverse.cuh)
+//   shadeKernel   everything between two hit() calls of the reference's color() loop (kernels.cu:402-531): miss / light /
+//                 albedo / scatter / next-event sample / Russian roulette, plus -- when the path ends -- retiring the
+//                 sample into the pixel's sum (kernels.cu:558) and generating the next camera ray (kernels.cu:549-555)
+//   startKernel   seeds the slots and generates sample 0 (kernels.cu:541-555)
+//
+// Ordering rules that keep the float sums bit-identical to the reference's sequential thread:
+//   * a slot has at most ONE shadow ray in flight (`pending`); shadeKernel does not touch a slot whose shadow ray is
+//     still pending, it re-queues the entry for the next iteration; so p.color receives light contributions and the
+//     sky term in bounce order (kernels.cu:424,508);
+//   * the shadow ray of a path's last bounce is FINAL: it carries the finished sample's colour and adds
+//     colour (+ contribution when unoccluded) to the pixel sum itself, while the slot already traces its next sample;
+//     the next sample cannot retire before `pending` clears, so samples reach `col` in sample order (kernels.cu:558).
+//
+// Queue entries are 32-bit: slot index | ENTRY_SHADOW | ENTRY_RESUME. Appends use one atomic per warp (ballot + popc).
+#pragma once
+
+#include "bsdf.cuh"
+#include "device_scene.cuh"
+#include "traverse.cuh"
+#include "wavefront_kernels.cuh"
+
+#define ENTRY_RESUME 0x80000000u
+#define ENTRY_SHADOW 0x40000000u
+#define ENTRY_SLOT_MASK 0x3FFFFFFFu
+
+#define SHADOW_FLAG_FINAL 1u
+
+struct MeshControl {
+    unsigned int traceCount[2];  // entries in traceQ[k]
+    unsigned int shadeCount[2];  // entries in shadeQ[k]
+    unsigned int traceCursor;    // dynamic fetch cursor of the running traceKernel
+    unsigned int blocksDone;     // shadeKernel's last block resets the consumed queues
+    unsigned int pad0, pad1;
+    unsigned long long raysExtend;  // finished closest-hit rays
+    unsigned long long raysShadow;  // finished any-hit rays
+    unsigned long long resumes;     // rays parked and continued in a later launch
+    unsigned long long deferred;    // shade entries postponed because a shadow ray was pending
+    unsigned long long iterations;
+    unsigned long long nodeVisits;
+    unsigned long long triTests;
+};
+
+struct MeshState {
+    // path state, one entry per slot
+    float4* rayO;   // {origin, rng}
+    float4* rayD;   // {rayDir, flags}
+    float4* atten;  // {attenuation, sample index}
+    float4* pcol;   // {p.color, -}
+    float4* hit;    // {t/closest, u, v, triId}
+    uint2* travE;   // parked closest-hit traversal {idx, bitStack}
+    // the slot's shadow ray
+    float4* shO;    // {origin, -}
+    float4* shD;    // {shadowDir, lightDist}
+    float4* shL;    // {lightContribution, flags}
+    float4* shC;    // FINAL only: {finished sample's colour, -}
+    uint2* travS;   // parked any-hit traversal
+    unsigned char* pending;
+    unsigned int* traceQ[2];
+    unsigned int* shadeQ[2];
+    float4* accum;
+    MeshControl* ctl;
+    unsigned int numSlots;
+    unsigned int npix;
+    int nx, ny;
+    int samplesPerSlot;
+    int slotsPerPixel;
+    unsigned int streamBase;
+    int traceBudget;    // steps per ray per launch before it is parked
+    int traceMinActive; // refill a warp when fewer lanes than this still traverse
+};
+
+__device__ __forceinline__ void accumulatePixel(const MeshState& st, unsigned int pixel, float r, float g, float b) {
+    if (st.slotsPerPixel == 1) { // one slot per pixel: plain read-modify-write, in sample order
+        float4 a = st.accum[pixel];
+        a.x += r; a.y += g; a.z += b;
+        st.accum[pixel] = a;
+    } else {
+        atomicAdd(&st.accum[pixel].x, r);
+        atomicAdd(&st.accum[pixel].y, g);
+        atomicAdd(&st.accum[pixel].z, b);
+    }
+}
+
+// Starts sample `sample` of `slot`: kernels.cu:549-555.
+__device__ __forceinline__ void startSample(const MeshState& st, const CameraDev& cam, unsigned int slot, unsigned int rng, int sample) {
+    const unsigned int pixel = slot % st.npix;
+    const int px = (int)(pixel % (unsigned int)st.nx), py = (int)(pixel / (unsigned int)st.nx);
+    const float u = float(px + rnd(rng)) / float(st.nx);
+    const float v = float(py + rnd(rng)) / float(st.ny);
+    f3 o, d;
+    cameraRay(cam, u, v, rng, o, d);
+    st.rayO[slot] = mk4(o, __uint_as_float(rng));
+    st.rayD[slot] = mk4(d, __uint_as_float(0u));
+    st.atten[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(sample));
+    st.pcol[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+__global__ void __launch_bounds__(WF_BLOCK) meshStartKernel(MeshState st, CameraDev cam) {
+    const unsigned int stride = gridDim.x * blockDim.x;
+    for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < st.numSlots; base += stride) {
+        const unsigned int slot = base + laneId();
+        const bool alive = slot < st.numSlots;
+        if (alive) {
+            const unsigned int pixel = slot % st.npix;
+            const unsigned int stream = st.streamBase * (unsigned int)st.slotsPerPixel + slot / st.npix;
+            st.pending[slot] = 0;
+            startSample(st, cam, slot, pathSeed(pixel + stream * st.npix), 0); // kernels.cu:541-542 is stream 0
+        }
+        const unsigned int pos = warpAppend(alive, &st.ctl->traceCount[0]);
+        if (alive) st.traceQ[0][pos] = slot;
+    }
+}
+
+// ------------------------------------------------------------------- trace --
+#define TRACE_BUDGET 96      // default steps per ray per launch before it is parked
+#define TRACE_MIN_ACTIVE 20  // default: refill when fewer lanes than this still traverse
+
+template <bool COUNT>
+__global__ void __launch_bounds__(WF_BLOCK) traceKernel(MeshState st, MeshView mesh, int cur) {
+    MeshControl* ctl = st.ctl;
+    const unsigned int n = ctl->traceCount[cur];
+    const unsigned int* __restrict__ queue = st.traceQ[cur];
+    unsigned int* __restrict__ nextTrace = st.traceQ[cur ^ 1];
+    unsigned int* __restrict__ shadeQ = st.shadeQ[cur];
+    const unsigned int lane = laneId();
+
+    bool live = false;       // this lane holds a ray
+    bool exhausted = false;  // the queue has no more entries for this warp
+    unsigned int entry = 0;
+    RayPrep r;
+    TravState s;
+    float tMax = 0.0f;
+    int steps = 0;
+    unsigned int nodeVisits = 0, triTests = 0, doneExtend = 0, doneShadow = 0, parked = 0;
+    r.o = r.d = r.inv = mk3(0.0f, 0.0f, 0.0f);
+    travInit(s, 0.0f);
+    s.idx = 0;
+
+    while (true) {
+        // ---- refill idle lanes, one atomic per warp
+        if (!exhausted) {
+            const bool want = !live;
+            const unsigned int mask = __ballot_sync(0xFFFFFFFFu, want);
+            if (mask) {
+                unsigned int base = 0;
+                const unsigned int leader = __ffs(mask) - 1;
+                if (lane == leader) base = atomicAdd(&ctl->traceCursor, __popc(mask));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (base + __popc(mask) >= n) exhausted = true; // warp-uniform: the tail of the queue has been handed out
+                const unsigned int i = base + __popc(mask & ((1u << lane) - 1u));
+                if (want && i < n) {
+                    entry = queue[i];
+                    const unsigned int slot = entry & ENTRY_SLOT_MASK;
+                    const bool isShadow = (entry & ENTRY_SHADOW) != 0u;
+                    const float4 ro = isShadow ? st.shO[slot] : st.rayO[slot];
+                    const float4 rd = isShadow ? st.shD[slot] : st.rayD[slot];
+                    r = prepRay(xyz(ro), unit(xyz(rd))); // hit(): ray(p.origin, dir) normalises again (kernels.cu:326)
+                    tMax = isShadow ? rd.w : FLT_MAX;
+                    steps = 0;
+                    live = true;
+                    if (entry & ENTRY_RESUME) {
+                        const uint2 t = isShadow ? st.travS[slot] : st.travE[slot];
+                        s.idx = t.x;
+                        s.bitStack = t.y;
+                        if (isShadow) {
+                            s.closest = tMax;
+                        } else {
+                            const float4 h = st.hit[slot];
+                            s.closest = h.x; s.u = h.y; s.v = h.z; s.triId = __float_as_uint(h.w);
+                        }
+                    } else {
+                        travInit(s, tMax);
+                        if (!boxHit(mesh.boundsMin, mesh.boundsMax, r, tMax)) { // hitMesh: scene bounds first (kernels.cu:297)
+                            s.idx = 0;
+                            s.closest = FLT_MAX;
+                        }
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, live)) break;
+
+        // ---- traverse
+        const bool isShadow = (entry & ENTRY_SHADOW) != 0u;
+        travRun(mesh, r, RT_EPSILON, isShadow, live, s, steps, st.traceBudget, exhausted ? 1 : st.traceMinActive, nodeVisits, triTests);
+
+        // ---- retire finished rays, park the ones that ran out of budget
+        const unsigned int slot = entry & ENTRY_SLOT_MASK;
+        const bool finished = live && s.idx == 0u;
+        const bool park = live && !finished && steps >= st.traceBudget;
+        const bool toShade = finished && !isShadow;
+        if (finished) {
+            if (!isShadow) {
+                // hitMesh returns `closest` (== t_max when nothing was hit) or FLT_MAX; hit() tests `< t_max` (kernels.cu:330)
+                st.hit[slot] = make_float4(s.closest, s.u, s.v, __uint_as_float(s.triId));
+                doneExtend++;
+            } else {
+                const float4 l = st.shL[slot];
+                const bool unoccluded = !(s.closest < tMax); // hit(...) false: p.color += p.lightContribution (kernels.cu:500-508)
+                if (__float_as_uint(l.w) & SHADOW_FLAG_FINAL) {
+                    float4 c = st.shC[slot];
+                    if (unoccluded) { c.x += l.x; c.y += l.y; c.z += l.z; }
+                    accumulatePixel(st, slot % st.npix, c.x, c.y, c.z); // col += p.color (kernels.cu:558)
+                } else if (unoccluded) {
+                    float4 c = st.pcol[slot];
+                    c.x += l.x; c.y += l.y; c.z += l.z;
+                    st.pcol[slot] = c;
+                }
+                st.pending[slot] = 0;
+                doneShadow++;
+            }
+            live = false;
+        }
+        if (park) {
+            if (isShadow) {
+                st.travS[slot] = make_uint2(s.idx, s.bitStack);
+            } else {
+                st.travE[slot] = make_uint2(s.idx, s.bitStack);
+                st.hit[slot] = make_float4(s.closest, s.u, s.v, __uint_as_float(s.triId));
+            }
+            parked++;
+            live = false;
+        }
+        const unsigned int posShade = warpAppend(toShade, &ctl->shadeCount[cur]);
+        if (toShade) shadeQ[posShade] = slot;
+        const unsigned int posPark = warpAppend(park, &ctl->traceCount[cur ^ 1]);
+        if (park) nextTrace[posPark] = entry | ENTRY_RESUME;
+    }
+
+    // per-warp statistics: one atomic per counter per warp
+    for (int o = 16; o > 0; o >>= 1) {
+        doneExtend += __shfl_xor_sync(0xFFFFFFFFu, doneExtend, o);
+        doneShadow += __shfl_xor_sync(0xFFFFFFFFu, doneShadow, o);
+        parked += __shfl_xor_sync(0xFFFFFFFFu, parked, o);
+        if (COUNT) {
+            nodeVisits += __shfl_xor_sync(0xFFFFFFFFu, nodeVisits, o);
+            triTests += __shfl_xor_sync(0xFFFFFFFFu, triTests, o);
+        }
+    }
+    if (lane == 0) {
+        if (doneExtend) atomicAdd(&ctl->raysExtend, (unsigned long long)doneExtend);
+        if (doneShadow) atomicAdd(&ctl->raysShadow, (unsigned long long)doneShadow);
+        if (parked) atomicAdd(&ctl->resumes, (unsigned long long)parked);
+        if (COUNT) {
+            atomicAdd(&ctl->nodeVisits, (unsigned long long)nodeVisits);
+            atomicAdd(&ctl->triTests, (unsigned long long)triTests);
+        }
+    }
+}
+
+// ------------------------------------------------------------------- shade --
+__global__ void __launch_bounds__(WF_BLOCK) meshShadeKernel(MeshState st, ShadeScene sc, CameraDev cam, int cur) {
+    MeshControl* ctl = st.ctl;
+    const unsigned int n = ctl->shadeCount[cur];
+    const unsigned int* __restrict__ queue = st.shadeQ[cur];
+    unsigned int* __restrict__ nextTrace = st.traceQ[cur ^ 1];
+    unsigned int* __restrict__ nextShade = st.shadeQ[cur ^ 1];
+    const unsigned int stride = gridDim.x * blockDim.x;
+    unsigned int deferredCount = 0;
+    for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        const unsigned int i = base + laneId();
+        bool traceNext = false, castsShadow = false, defer = false;
+        unsigned int slot = 0;
+        if (i < n) {
+            slot = queue[i];
+            if (st.pending[slot]) {
+                defer = true; // its shadow ray is still in flight: keep bounce order, come back next iteration
+            } else {
+                const float4 h = st.hit[slot];
+                const float4 ro = st.rayO[slot];
+                const float4 rd = st.rayD[slot];
+                const float4 att4 = st.atten[slot];
+                f3 origin = xyz(ro), dir = xyz(rd), att = xyz(att4);
+                unsigned int rng = __float_as_uint(ro.w);
+                unsigned int flags = __float_as_uint(rd.w);
+                const bool specularIn = (flags & PATH_FLAG_SPECULAR) != 0u;
+                bool inside = (flags & PATH_FLAG_INSIDE) != 0u;
+                unsigned int bounce = flags & PATH_BOUNCE_MASK;
+                const f3 rdir = unit(dir); // direction of the ray hit() traced
+                float4 pc = st.pcol[slot];
+                bool continues = false;
+                f3 shDir = mk3(0.0f, 0.0f, 0.0f), shL = mk3(0.0f, 0.0f, 0.0f);
+                float lightDist = 0.0f;
+
+                if (!(h.x < FLT_MAX)) {
+                    // no mesh hit. Specular paths may still see the light sphere (kernels.cu:346-349); it ends the path
+                    // without adding emission because SHADOW is defined (:440-446). Otherwise: constant grey sky (:424).
+                    const bool hitsLight = specularIn && sphereHitT(sc.light.center, sc.light.radius, origin, rdir, RT_EPSILON, FLT_MAX) < FLT_MAX;
+                    if (!hitsLight) {
+                        const f3 add = att * mk3(0.5f, 0.5f, 0.5f);
+                        pc.x += add.x; pc.y += add.y; pc.z += add.z;
+                    }
+                } else {
+                    const unsigned int triId = __float_as_uint(h.w);
+                    const float4 s0 = __ldg(sc.triShade + 3 * triId);
+                    const float4 s1 = __ldg(sc.triShade + 3 * triId + 1);
+                    const float4 s2 = __ldg(sc.triShade + 3 * triId + 2);
+                    const int meshID = __float_as_int(s0.w);
+                    SurfacePoint sp;
+                    sp.normal = xyz(s0);
+                    sp.t = h.x;
+                    sp.inside = inside;
+                    const float hu = h.y, hv = h.z;
+                    // texCoords: u weights vertex 1, v weights vertex 2 (kernels.cu:337-338)
+                    const float hw = (1 - hu - hv);
+                    float tu = __fmaf_rn(hw, s1.x, mad2(hu, s1.z, hv, s2.x)); // hu*tc[2] + hv*tc[4] + (1-hu-hv)*tc[0]
+                    float tv = __fmaf_rn(hw, s1.y, mad2(hu, s1.w, hv, s2.y));
+                    if (dot(rdir, sp.normal) > 0.0f) sp.normal = -sp.normal;
+
+                    const float4 m0 = __ldg(sc.mats.mats + 2 * meshID);
+                    const float4 m1 = __ldg(sc.mats.mats + 2 * meshID + 1);
+                    const int texId = __float_as_int(m1.y);
+                    f3 albedo;
+                    if (texId != -1) { // kernels.cu:457-471: nearest texel, frac() wrap
+                        const int width = sc.mats.texWidth[texId];
+                        const int height = sc.mats.texHeight[texId];
+                        tu = tu - floorf(tu);
+                        tv = tv - floorf(tv);
+                        const int tx = (width - 1) * tu;
+                        const int ty = (height - 1) * tv;
+                        const int tIdx = ty * width + tx;
+                        const float* td = sc.mats.texData[texId];
+                        albedo = mk3(__ldg(td + tIdx * 3 + 0), __ldg(td + tIdx * 3 + 1), __ldg(td + tIdx * 3 + 2));
+                    } else {
+                        albedo = xyz(m0);
+                    }
+
+                    Scatter scat;
+                    scat.specular = false;
+                    scat.throughput = mk3(1.0f, 1.0f, 1.0f);
+                    scat.refracted = false;
+                    scat.t = h.x;
+                    scat.wi = mk3(0.0f, 0.0f, 0.0f);
+                    materialScatter(scat, sp, dir, __float_as_int(m1.x), m0.w, albedo, rng);
+
+                    origin = origin + scat.t * dir; // kernels.cu:485 (not inters.p)
+                    dir = scat.wi;
+                    att = att * scat.throughput;
+                    const bool specular = scat.specular;
+                    inside = scat.refracted ? !inside : inside;
+
+                    if (!specular && sampleLight(sc.light, origin, sp.normal, att, rng, shDir, shL, lightDist)) castsShadow = true;
+
+                    continues = true;
+                    if (bounce > 3u) { // Russian roulette, kernels.cu:514-526
+                        const float m = maxcomp(att);
+                        if (rnd(rng) > m) continues = false;
+                        else att = att * (1 / m);
+                    }
+                    if (continues) {
+                        bounce = (bounce + 1u) & PATH_BOUNCE_MASK; // p.bounce is a uint8_t (helper_structs.h:58)
+                        if (!((int)bounce < sc.maxDepth)) continues = false;
+                    }
+                    flags = bounce | (specular ? PATH_FLAG_SPECULAR : 0u) | (inside ? PATH_FLAG_INSIDE : 0u);
+                }
+
+                if (castsShadow) {
+                    st.shO[slot] = mk4(origin, 0.0f);
+                    st.shD[slot] = mk4(shDir, lightDist);
+                    st.shL[slot] = mk4(shL, __uint_as_float(continues ? 0u : SHADOW_FLAG_FINAL));
+                    st.pending[slot] = 1;
+                }
+                if (continues) {
+                    st.rayO[slot] = mk4(origin, __uint_as_float(rng));
+                    st.rayD[slot] = mk4(dir, __uint_as_float(flags));
+                    st.atten[slot] = mk4(att, att4.w);
+                    traceNext = true;
+                } else {
+                    // the sample is finished: retire its colour (now, or by its FINAL shadow ray) and start the next one
+                    if (castsShadow) st.shC[slot] = pc;
+                    else accumulatePixel(st, slot % st.npix, pc.x, pc.y, pc.z);
+                    const int sample = __float_as_int(att4.w) + 1;
+                    if (sample < st.samplesPerSlot) {
+                        startSample(st, cam, slot, rng, sample);
+                        traceNext = true;
+                    }
+                }
+            }
+        }
+        const unsigned int posDefer = warpAppend(defer, &ctl->shadeCount[cur ^ 1]);
+        if (defer) { nextShade[posDefer] = slot; deferredCount++; }
+        // extend and shadow entries of a warp go out with one atomic
+        const unsigned int mE = __ballot_sync(0xFFFFFFFFu, traceNext), mS = __ballot_sync(0xFFFFFFFFu, castsShadow);
+        const unsigned int total = __popc(mE) + __popc(mS);
+        if (total) {
+            unsigned int basePos = 0;
+            if (laneId() == 0) basePos = atomicAdd(&ctl->traceCount[cur ^ 1], total);
+            basePos = __shfl_sync(0xFFFFFFFFu, basePos, 0);
+            const unsigned int below = (1u << laneId()) - 1u;
+            if (castsShadow) nextTrace[basePos + __popc(mS & below)] = slot | ENTRY_SHADOW; // shadow rays first: they unblock the slot
+            if (traceNext) nextTrace[basePos + __popc(mS) + __popc(mE & below)] = slot;
+        }
+    }
+    if (deferredCount) atomicAdd(&ctl->deferred, (unsigned long long)deferredCount);
+
+    // the last block to finish recycles the queues this iteration consumed
+    __shared__ bool isLast;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        isLast = atomicAdd(&ctl->blocksDone, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (isLast && threadIdx.x == 0) {
+        if (ctl->traceCount[cur] | ctl->shadeCount[cur]) ctl->iterations += 1;
+        ctl->traceCount[cur] = 0;
+        ctl->shadeCount[cur] = 0;
+        ctl->traceCursor = 0;
+        ctl->blocksDone = 0;
+    }
+}

@@ -7,42 +7,74 @@
 
 #include "device_scene.cuh"
 #include "rng.cuh"
+#include "traverse.cuh"
 
 template <bool COUNT>
-__global__ void __launch_bounds__(256) intersectBatchKernel(MeshView mesh, const float4* __restrict__ triShade,
+__global__ void __launch_bounds__(256, 4) intersectBatchKernel(MeshView mesh, const float4* __restrict__ triShade,
                                                             const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                             unsigned long long n, float4* __restrict__ outHit, int* __restrict__ outMesh,
-                                                            unsigned int* cursor, unsigned long long* counts) {
-    TravCounters cnt = {0u, 0u};
+                                                            unsigned long long* cursor, unsigned long long* counts) {
     const unsigned int lane = threadIdx.x & 31u;
+    bool live = false, exhausted = false;
+    unsigned long long index = 0;
+    RayPrep r;
+    TravState s;
+    float tMin = 0.0f, tMax = 0.0f;
+    int steps = 0;
+    unsigned int nodeVisits = 0, triTests = 0;
+    r.o = r.d = r.inv = mk3(0.0f, 0.0f, 0.0f);
+    travInit(s, 0.0f);
+    s.idx = 0;
     while (true) {
-        unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(cursor, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if ((unsigned long long)base >= n) break;
-        const unsigned long long i = (unsigned long long)base + lane;
-        if (i < n) {
-            const float4 ro = __ldg(rayO + i);
-            const float4 rd = __ldg(rayD + i);
-            const RayPrep r = prepRay(xyz(ro), unit(xyz(rd)));
-            unsigned int triId = 0xFFFFFFFFu;
-            float u = 0.0f, v = 0.0f;
-            float t = traverseRefOrder<false, COUNT>(mesh, r, ro.w, rd.w, triId, u, v, &cnt);
+        if (!exhausted) { // refill idle lanes, one atomic per warp
+            const bool want = !live;
+            const unsigned int mask = __ballot_sync(0xFFFFFFFFu, want);
+            if (mask) {
+                unsigned long long base = 0;
+                const unsigned int leader = __ffs(mask) - 1;
+                if (lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(mask));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (base + __popc(mask) >= n) exhausted = true;
+                const unsigned long long i = base + __popc(mask & ((1u << lane) - 1u));
+                if (want && i < n) {
+                    index = i;
+                    const float4 ro = __ldg(rayO + i);
+                    const float4 rd = __ldg(rayD + i);
+                    r = prepRay(xyz(ro), unit(xyz(rd)));
+                    tMin = ro.w;
+                    tMax = rd.w;
+                    steps = 0;
+                    live = true;
+                    travInit(s, tMax);
+                    if (!boxHit(mesh.boundsMin, mesh.boundsMax, r, tMax)) {
+                        s.idx = 0;
+                        s.closest = FLT_MAX;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, live)) break;
+        travRun(mesh, r, tMin, false, live, s, steps, 0x7FFFFFFF, exhausted ? 1 : 20, nodeVisits, triTests);
+        if (live && s.idx == 0u) {
+            float t = s.closest;
+            unsigned int triId = s.triId;
+            float u = s.u, v = s.v;
             int meshID = -1;
-            if (t < rd.w) {
+            if (t < tMax) {
                 meshID = __float_as_int(__ldg(triShade + 3 * triId).w);
             } else {
                 t = FLT_MAX;
                 triId = 0xFFFFFFFFu;
                 u = v = 0.0f;
             }
-            outHit[i] = make_float4(t, u, v, __uint_as_float(triId));
-            outMesh[i] = meshID;
+            outHit[index] = make_float4(t, u, v, __uint_as_float(triId));
+            outMesh[index] = meshID;
+            live = false;
         }
     }
     if (COUNT) {
-        atomicAdd(&counts[0], (unsigned long long)cnt.nodeVisits);
-        atomicAdd(&counts[1], (unsigned long long)cnt.triTests);
+        atomicAdd(&counts[0], (unsigned long long)nodeVisits);
+        atomicAdd(&counts[1], (unsigned long long)triTests);
     }
 }
 

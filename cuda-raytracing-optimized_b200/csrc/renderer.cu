@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "kernels.h"
@@ -69,6 +70,41 @@ static void allocWavefront(RendererContext& c, unsigned int numSlots) {
     s.ctl = devAlloc<WfControl>(1);
 }
 
+static void freeMeshPipeline(RendererContext& c) {
+    MeshState& s = c.mp;
+    cudaFree(s.rayO); cudaFree(s.rayD); cudaFree(s.atten); cudaFree(s.pcol); cudaFree(s.hit); cudaFree(s.travE);
+    cudaFree(s.shO); cudaFree(s.shD); cudaFree(s.shL); cudaFree(s.shC); cudaFree(s.travS); cudaFree(s.pending);
+    cudaFree(s.traceQ[0]); cudaFree(s.traceQ[1]); cudaFree(s.shadeQ[0]); cudaFree(s.shadeQ[1]);
+    cudaFree(s.ctl);
+    std::memset(&s, 0, sizeof(s));
+    if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
+    c.graphKey = -1;
+}
+
+static void allocMeshPipeline(RendererContext& c, unsigned int numSlots) {
+    if (c.mp.numSlots == numSlots && c.mp.rayO) return;
+    freeMeshPipeline(c);
+    MeshState& s = c.mp;
+    s.numSlots = numSlots;
+    s.rayO = devAlloc<float4>(numSlots);
+    s.rayD = devAlloc<float4>(numSlots);
+    s.atten = devAlloc<float4>(numSlots);
+    s.pcol = devAlloc<float4>(numSlots);
+    s.hit = devAlloc<float4>(numSlots);
+    s.travE = devAlloc<uint2>(numSlots);
+    s.shO = devAlloc<float4>(numSlots);
+    s.shD = devAlloc<float4>(numSlots);
+    s.shL = devAlloc<float4>(numSlots);
+    s.shC = devAlloc<float4>(numSlots);
+    s.travS = devAlloc<uint2>(numSlots);
+    s.pending = devAlloc<unsigned char>(numSlots);
+    for (int k = 0; k < 2; k++) {
+        s.traceQ[k] = devAlloc<unsigned int>(2 * (size_t)numSlots); // at most one extend and one shadow entry per slot
+        s.shadeQ[k] = devAlloc<unsigned int>(numSlots);
+    }
+    s.ctl = devAlloc<MeshControl>(1);
+}
+
 extern "C" void setRendererOptions(const renderer_options* opt) {
     if (opt) g_opts = *opt;
     else g_opts = renderer_options{-1, 0u, 0, 0, 0, {0, 0, 0}};
@@ -103,7 +139,7 @@ static void initCommon(RendererContext& c, const camera& cam, vec3** fb, int nx,
     if (fb) *fb = c.fb;
     c.wf.accum = devAlloc<float4>(npix);
     c.ownsAccum = true;
-    CRT_CHECK(cudaMallocHost((void**)&c.hostCtl, sizeof(WfControl)));
+    CRT_CHECK(cudaMallocHost((void**)&c.hostCtl, sizeof(WfControl) > sizeof(MeshControl) ? sizeof(WfControl) : sizeof(MeshControl)));
     std::memset(&c.stats, 0, sizeof(c.stats));
     c.initialised = true;
 }
@@ -196,85 +232,82 @@ static ShadeScene shadeScene(const RendererContext& c) {
     return s;
 }
 
-// One wavefront iteration on `stream`: extend -> shade -> shadow -> raygen -> advance.
-static void launchIteration(RendererContext& c, cudaStream_t stream, unsigned int* qCur, unsigned int* qNext, int samplesPerSlot,
-                            int slotsPerPixel, cudaEvent_t* ev) {
-    const int persistent = c.numSMs * 8;
-    const int wide = c.numSMs * 8;
+// One wavefront iteration on `stream`: trace (extend + shadow rays) -> shade (+ retire sample, + next camera ray).
+static void launchMeshIteration(RendererContext& c, cudaStream_t stream, int cur, cudaEvent_t* ev) {
     if (ev) cudaEventRecord(ev[0], stream);
-    if (c.counting) extendKernel<true><<<persistent, WF_BLOCK, 0, stream>>>(c.wf, c.mesh, qCur);
-    else extendKernel<false><<<persistent, WF_BLOCK, 0, stream>>>(c.wf, c.mesh, qCur);
+    if (c.counting) traceKernel<true><<<c.traceBlocks, WF_BLOCK, 0, stream>>>(c.mp, c.mesh, cur);
+    else traceKernel<false><<<c.traceBlocks, WF_BLOCK, 0, stream>>>(c.mp, c.mesh, cur);
     if (ev) cudaEventRecord(ev[1], stream);
-    shadeKernel<<<wide, WF_BLOCK, 0, stream>>>(c.wf, shadeScene(c), qCur, qNext);
+    meshShadeKernel<<<c.numSMs * 4, WF_BLOCK, 0, stream>>>(c.mp, shadeScene(c), c.cam, cur);
     if (ev) cudaEventRecord(ev[2], stream);
-    if (c.counting) shadowKernel<true><<<persistent, WF_BLOCK, 0, stream>>>(c.wf, c.mesh);
-    else shadowKernel<false><<<persistent, WF_BLOCK, 0, stream>>>(c.wf, c.mesh);
-    if (ev) cudaEventRecord(ev[3], stream);
-    raygenKernel<false><<<wide, WF_BLOCK, 0, stream>>>(c.wf, c.cam, qNext, c.nx, c.ny, samplesPerSlot, slotsPerPixel, c.opts.sampleStream);
-    advanceKernel<<<1, 1, 0, stream>>>(c.wf.ctl);
-    if (ev) cudaEventRecord(ev[4], stream);
 }
 
-#define KERNELS_PER_ITERATION 5
+#define MESH_KERNELS_PER_ITERATION 2
 
 void crtRunMesh(RendererContext& c, int ns) {
     const unsigned int npix = (unsigned int)c.nx * (unsigned int)c.ny;
     int slotsPerPixel = c.opts.reserved[0] > 0 ? c.opts.reserved[0] : 1;
     if (ns % slotsPerPixel != 0) slotsPerPixel = 1;
-    const int samplesPerSlot = ns / slotsPerPixel;
-    allocWavefront(c, npix * (unsigned int)slotsPerPixel);
+    allocMeshPipeline(c, npix * (unsigned int)slotsPerPixel);
+    MeshState& mp = c.mp;
+    mp.accum = c.wf.accum;
+    mp.npix = npix;
+    mp.nx = c.nx;
+    mp.ny = c.ny;
+    mp.samplesPerSlot = ns / slotsPerPixel;
+    mp.slotsPerPixel = slotsPerPixel;
+    mp.streamBase = c.opts.sampleStream;
+    mp.traceBudget = c.opts.reserved[1] > 0 ? c.opts.reserved[1] : TRACE_BUDGET;
+    mp.traceMinActive = c.opts.reserved[2] > 0 ? c.opts.reserved[2] : TRACE_MIN_ACTIVE;
+    if (!c.traceBlocks) {
+        int perSM = 0;
+        CRT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, traceKernel<false>, WF_BLOCK, 0));
+        c.traceBlocks = c.numSMs * (perSM > 0 ? perSM : 1); // persistent: exactly one resident wave
+    }
     cudaStream_t stream = c.stream;
 
     std::memset(&c.stats, 0, sizeof(c.stats));
     c.stats.samples = (unsigned long long)npix * (unsigned long long)(ns > 0 ? ns : 0);
     CRT_CHECK(cudaEventRecord(c.evStart, stream));
-    CRT_CHECK(cudaMemsetAsync(c.wf.accum, 0, (size_t)npix * sizeof(float4), stream));
-    CRT_CHECK(cudaMemsetAsync(c.wf.ctl, 0, sizeof(WfControl), stream));
+    CRT_CHECK(cudaMemsetAsync(mp.accum, 0, (size_t)npix * sizeof(float4), stream));
+    CRT_CHECK(cudaMemsetAsync(mp.ctl, 0, sizeof(MeshControl), stream));
     unsigned long long launches = 0;
+    MeshControl* host = (MeshControl*)c.hostCtl;
 
     if (npix > 0 && ns > 0 && c.maxDepth > 0) {
-        const int wide = c.numSMs * 8;
-        raygenKernel<true><<<wide, WF_BLOCK, 0, stream>>>(c.wf, c.cam, c.wf.queueA, c.nx, c.ny, samplesPerSlot, slotsPerPixel,
-                                                          c.opts.sampleStream);
-        advanceKernel<<<1, 1, 0, stream>>>(c.wf.ctl);
-        launches += 2;
+        meshStartKernel<<<c.numSMs * 4, WF_BLOCK, 0, stream>>>(mp, c.cam);
+        launches += 1;
         CRT_CHECK(cudaGetLastError());
 
         int batch = c.opts.megaBatch > 0 ? c.opts.megaBatch : 16;
-        batch = (batch + 1) & ~1; // even: the two queues swap roles every iteration
+        batch = (batch + 1) & ~1; // even: the two queue sets swap roles every iteration
         if (g_profiling) {
-            cudaEvent_t ev[5];
+            cudaEvent_t ev[3];
             for (auto& e : ev) CRT_CHECK(cudaEventCreate(&e));
             c.stats.profiled = 1;
-            bool flip = false;
             while (true) {
-                launchIteration(c, stream, flip ? c.wf.queueB : c.wf.queueA, flip ? c.wf.queueA : c.wf.queueB, samplesPerSlot,
-                                slotsPerPixel, ev);
-                flip = !flip;
-                launches += KERNELS_PER_ITERATION;
-                CRT_CHECK(cudaMemcpyAsync(c.hostCtl, c.wf.ctl, sizeof(WfControl), cudaMemcpyDeviceToHost, stream));
+                for (int cur = 0; cur < 2; cur++) {
+                    launchMeshIteration(c, stream, cur, ev);
+                    launches += MESH_KERNELS_PER_ITERATION;
+                    CRT_CHECK(cudaStreamSynchronize(stream));
+                    float ms;
+                    cudaEventElapsedTime(&ms, ev[0], ev[1]); c.stats.msTrace += ms;
+                    cudaEventElapsedTime(&ms, ev[1], ev[2]); c.stats.msShade += ms;
+                }
+                CRT_CHECK(cudaMemcpyAsync(host, mp.ctl, sizeof(MeshControl), cudaMemcpyDeviceToHost, stream));
                 CRT_CHECK(cudaStreamSynchronize(stream));
-                float ms;
-                cudaEventElapsedTime(&ms, ev[0], ev[1]); c.stats.msExtend += ms;
-                cudaEventElapsedTime(&ms, ev[1], ev[2]); c.stats.msShade += ms;
-                cudaEventElapsedTime(&ms, ev[2], ev[3]); c.stats.msShadow += ms;
-                cudaEventElapsedTime(&ms, ev[3], ev[4]); c.stats.msOther += ms;
-                if (c.hostCtl->countActive == 0) break;
+                if (host->traceCount[0] == 0 && host->shadeCount[0] == 0) break;
             }
-            if (flip) { /* an odd number of iterations ran: harmless, queues are scratch */ }
             for (auto& e : ev) cudaEventDestroy(e);
         } else {
-            const long long key = ((long long)samplesPerSlot << 24) ^ ((long long)slotsPerPixel << 8) ^ batch ^
-                                  ((long long)c.counting << 60) ^ ((long long)c.maxDepth << 40);
+            const long long key = ((long long)mp.samplesPerSlot << 24) ^ ((long long)slotsPerPixel << 8) ^ batch ^
+                                  ((long long)c.counting << 60) ^ ((long long)c.maxDepth << 40) ^ ((long long)mp.streamBase << 48) ^ ((long long)mp.traceBudget << 12) ^
+                                  ((long long)mp.traceMinActive << 4);
             if (!c.graphExec || c.graphKey != key) {
                 if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
                 cudaGraph_t graph;
                 CRT_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-                for (int k = 0; k < batch; k++) {
-                    const bool flip = (k & 1) != 0;
-                    launchIteration(c, stream, flip ? c.wf.queueB : c.wf.queueA, flip ? c.wf.queueA : c.wf.queueB, samplesPerSlot,
-                                    slotsPerPixel, nullptr);
-                }
+                for (int k = 0; k < batch; k++) launchMeshIteration(c, stream, k & 1, nullptr);
                 CRT_CHECK(cudaStreamEndCapture(stream, &graph));
                 CRT_CHECK(cudaGraphInstantiate(&c.graphExec, graph, 0));
                 CRT_CHECK(cudaGraphDestroy(graph));
@@ -282,30 +315,32 @@ void crtRunMesh(RendererContext& c, int ns) {
             }
             while (true) {
                 CRT_CHECK(cudaGraphLaunch(c.graphExec, stream));
-                launches += (unsigned long long)batch * KERNELS_PER_ITERATION;
-                CRT_CHECK(cudaMemcpyAsync(c.hostCtl, c.wf.ctl, sizeof(WfControl), cudaMemcpyDeviceToHost, stream));
+                launches += (unsigned long long)batch * MESH_KERNELS_PER_ITERATION;
+                CRT_CHECK(cudaMemcpyAsync(host, mp.ctl, sizeof(MeshControl), cudaMemcpyDeviceToHost, stream));
                 CRT_CHECK(cudaStreamSynchronize(stream));
-                if (c.hostCtl->countActive == 0) break;
+                if (host->traceCount[0] == 0 && host->shadeCount[0] == 0) break;
             }
         }
     } else {
-        CRT_CHECK(cudaMemcpyAsync(c.hostCtl, c.wf.ctl, sizeof(WfControl), cudaMemcpyDeviceToHost, stream));
+        CRT_CHECK(cudaMemcpyAsync(host, mp.ctl, sizeof(MeshControl), cudaMemcpyDeviceToHost, stream));
     }
 
     if (!c.opts.deferFinalize) {
-        if (npix) finalizeKernel<<<(npix + 255) / 256, 256, 0, stream>>>(c.wf.accum, (float*)c.fb, npix, float(ns));
+        if (npix) finalizeKernel<<<(npix + 255) / 256, 256, 0, stream>>>(mp.accum, (float*)c.fb, npix, float(ns));
         launches += 1;
     }
     CRT_CHECK(cudaEventRecord(c.evStop, stream));
     CRT_CHECK(cudaStreamSynchronize(stream));
     CRT_CHECK(cudaGetLastError());
     CRT_CHECK(cudaEventElapsedTime(&c.stats.msTotal, c.evStart, c.evStop));
-    c.stats.raysExtend = c.hostCtl->raysExtend;
-    c.stats.raysShadow = c.hostCtl->raysShadow;
-    c.stats.iterations = c.hostCtl->iterations;
+    c.stats.raysExtend = host->raysExtend;
+    c.stats.raysShadow = host->raysShadow;
+    c.stats.iterations = host->iterations;
+    c.stats.resumes = host->resumes;
+    c.stats.deferred = host->deferred;
     c.stats.kernelLaunches = launches;
-    c.lastNodeVisits = c.hostCtl->nodeVisits;
-    c.lastTriTests = c.hostCtl->triTests;
+    c.lastNodeVisits = host->nodeVisits;
+    c.lastTriTests = host->triTests;
 }
 
 extern "C" void runRenderer(int ns, int tx, int ty) {
@@ -342,6 +377,24 @@ extern "C" void getRendererStats(renderer_stats* out) {
     if (out) *out = g_ctx.stats;
 }
 
+// Test/diagnostic hook: copies one of the mesh pipeline's per-slot arrays to the host (returns bytes copied, 0 if unknown).
+extern "C" size_t rendererDebugRead(const char* name, void* dst, size_t maxBytes) {
+    RendererContext& c = g_ctx;
+    if (!c.initialised || !c.mp.rayO) return 0;
+    const MeshState& m = c.mp;
+    const void* src = nullptr;
+    size_t bytes = (size_t)m.numSlots * sizeof(float4);
+    const std::string n(name);
+    if (n == "rayO") src = m.rayO; else if (n == "rayD") src = m.rayD; else if (n == "atten") src = m.atten;
+    else if (n == "pcol") src = m.pcol; else if (n == "hit") src = m.hit; else if (n == "shO") src = m.shO;
+    else if (n == "shD") src = m.shD; else if (n == "shL") src = m.shL; else if (n == "shC") src = m.shC;
+    else if (n == "accum") { src = m.accum; bytes = (size_t)m.npix * sizeof(float4); }
+    if (!src) return 0;
+    if (bytes > maxBytes) bytes = maxBytes;
+    CRT_CHECK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return bytes;
+}
+
 extern "C" void setRendererCounting(int on) {
     g_ctx.counting = on != 0;
 }
@@ -356,6 +409,7 @@ extern "C" void cleanupRenderer() {
     if (!c.initialised) return;
     CRT_CHECK(cudaDeviceSynchronize());
     freeWavefront(c);
+    freeMeshPipeline(c);
     if (c.ownsAccum) cudaFree(c.wf.accum);
     c.wf.accum = nullptr;
     cudaFree(c.fb);
@@ -378,9 +432,9 @@ extern "C" float intersectBatchDevice(const void* dRayO, const void* dRayD, long
         std::fprintf(stderr, "intersectBatchDevice needs a mesh scene (initRenderer)\n");
         std::exit(99);
     }
-    unsigned int* cursor = devAlloc<unsigned int>(2);
+    unsigned long long* cursor = devAlloc<unsigned long long>(2);
     unsigned long long* counts = devAlloc<unsigned long long>(2);
-    CRT_CHECK(cudaMemsetAsync(cursor, 0, 2 * sizeof(unsigned int), c.stream));
+    CRT_CHECK(cudaMemsetAsync(cursor, 0, 2 * sizeof(unsigned long long), c.stream));
     CRT_CHECK(cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), c.stream));
     const int blocks = c.numSMs * 8;
     CRT_CHECK(cudaEventRecord(c.evStart, c.stream));

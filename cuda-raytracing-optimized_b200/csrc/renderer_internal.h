@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "device_scene.cuh"
+#include "mesh_pipeline.cuh"
 #include "kernels.h"
 
 #define CRT_CHECK(val) crtCheckCuda((val), #val, __FILE__, __LINE__)
@@ -42,7 +43,8 @@ struct RendererContext {
     int numSpheres = 0;
     int skyMode = 0;
 
-    // wavefront state
+    // wavefront state: `mp` = mesh pipeline, `wf` = sphere pipeline (accum lives in wf.accum for both)
+    MeshState mp = {};
     WfState wf = {};
     bool ownsAccum = false;
     WfControl* hostCtl = nullptr; // pinned
@@ -51,6 +53,7 @@ struct RendererContext {
     cudaGraphExec_t graphExec = nullptr;
     long long graphKey = -1;
 
+    int traceBlocks = 0; // persistent grid of traceKernel: one resident wave
     bool counting = false;
     unsigned long long lastNodeVisits = 0, lastTriTests = 0;
     renderer_stats stats = {};

@@ -26,14 +26,28 @@ __device__ __forceinline__ f3 operator*(const f3& a, const f3& b) { return mk3(a
 __device__ __forceinline__ f3 operator*(float t, const f3& v) { return mk3(t * v.x, t * v.y, t * v.z); }
 __device__ __forceinline__ f3 operator*(const f3& v, float t) { return mk3(t * v.x, t * v.y, t * v.z); }
 __device__ __forceinline__ f3 operator/(const f3& v, float t) { return mk3(v.x / t, v.y / t, v.z / t); }
-__device__ __forceinline__ float dot(const f3& a, const f3& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ f3 cross(const f3& a, const f3& b) {
-    return mk3((a.y * b.z - a.z * b.y), (-(a.x * b.z - a.z * b.x)), (a.x * b.y - a.y * b.x));
+// dot / cross / squared length are PINNED with intrinsics. For `a*b + c*d` and `a*b - c*d` C++ does not say which
+// product is fused: nvcc decides per context (we saw length() contract as fma(y,y,x*x) in one kernel and fma(x,x,y*y) in
+// another) and leaves `a*b - c*d` to ptxas, which decides per kernel. The forms below are the ones in the reference's
+// compiled render kernel (read from SASS): second product rounded on its own, first product fused onto it, further terms
+// fused on top. Intrinsics are never re-fused or re-associated by either compiler stage.
+__device__ __forceinline__ float dot(const f3& a, const f3& b) {
+    return __fmaf_rn(a.z, b.z, __fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y)));
 }
-__device__ __forceinline__ float sqlen(const f3& a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
-__device__ __forceinline__ float length(const f3& a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }
+__device__ __forceinline__ f3 cross(const f3& a, const f3& b) {
+    return mk3(__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), -__fmaf_rn(a.x, b.z, -__fmul_rn(a.z, b.x)),
+               __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x)));
+}
+__device__ __forceinline__ float sqlen(const f3& a) { return dot(a, a); }
+__device__ __forceinline__ float length(const f3& a) { return sqrtf(dot(a, a)); }
 __device__ __forceinline__ f3 unit(const f3& v) { return v / length(v); }
 __device__ __forceinline__ float maxcomp(const f3& v) { return fmaxf(v.x, fmaxf(v.y, v.z)); }
 
 __device__ __forceinline__ f3 xyz(const float4& v) { return mk3(v.x, v.y, v.z); }
 __device__ __forceinline__ float4 mk4(const f3& v, float w) { return make_float4(v.x, v.y, v.z, w); }
+
+__device__ __forceinline__ f3 subPinned(const f3& a, const f3& b) {
+    return mk3(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z));
+}
+// a*p + b*q with the second product rounded on its own (the reference's compiled form)
+__device__ __forceinline__ float mad2(float a, float p, float b, float q) { return __fmaf_rn(a, p, __fmul_rn(b, q)); }

@@ -70,9 +70,9 @@ class RendererOptions(C.Structure):
 
 class RendererStats(C.Structure):
     _fields_ = [("raysExtend", C.c_ulonglong), ("raysShadow", C.c_ulonglong), ("samples", C.c_ulonglong),
-                ("kernelLaunches", C.c_ulonglong), ("iterations", C.c_ulonglong), ("msTotal", C.c_float),
-                ("msExtend", C.c_float), ("msShade", C.c_float), ("msShadow", C.c_float), ("msOther", C.c_float),
-                ("profiled", C.c_int)]
+                ("kernelLaunches", C.c_ulonglong), ("iterations", C.c_ulonglong), ("resumes", C.c_ulonglong),
+                ("deferred", C.c_ulonglong), ("msTotal", C.c_float), ("msTrace", C.c_float), ("msShade", C.c_float),
+                ("msOther", C.c_float), ("profiled", C.c_int)]
 
 
 assert C.sizeof(Vec3) == 12 and C.sizeof(Triangle) == 64 and C.sizeof(BvhNode) == 24 and C.sizeof(Mesh) == 56
@@ -122,7 +122,7 @@ DEVICE_SYMBOLS = [
     "initRenderer", "runRenderer", "cleanupRenderer", "setRendererOptions", "initRendererSpheres", "intersectBatch",
     "intersectBatchDevice", "generateRayBatchDevice", "rendererDeviceAlloc", "rendererDeviceFree", "rendererCopyToHost",
     "rendererCopyToDevice", "getRendererStats", "setRendererProfiling", "getRendererAccumDevice", "setRendererAccumDevice",
-    "finalizeFrame", "setRendererCounting", "getRendererTraversalCounts",
+    "finalizeFrame", "setRendererCounting", "getRendererTraversalCounts", "rendererDebugRead",
 ]
 
 
@@ -157,6 +157,8 @@ def device_lib():
         L.getRendererAccumDevice.restype = C.c_void_p
         L.setRendererAccumDevice.argtypes = [C.c_void_p]
         L.finalizeFrame.argtypes = [C.c_int]
+        L.rendererDebugRead.restype = C.c_size_t
+        L.rendererDebugRead.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t]
         L.setRendererCounting.argtypes = [C.c_int]
         L.getRendererTraversalCounts.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
         _dev = L
@@ -253,8 +255,10 @@ def rtiow_camera(nx, ny):
     return cam
 
 
-def set_options(device=-1, sample_stream=0, defer_finalize=0, reset_on_cleanup=0, mega_batch=0, slots_per_pixel=0):
-    o = RendererOptions(device, sample_stream, defer_finalize, reset_on_cleanup, mega_batch, (C.c_int * 3)(slots_per_pixel, 0, 0))
+def set_options(device=-1, sample_stream=0, defer_finalize=0, reset_on_cleanup=0, mega_batch=0, slots_per_pixel=0, trace_budget=0,
+                trace_min_active=0):
+    o = RendererOptions(device, sample_stream, defer_finalize, reset_on_cleanup, mega_batch,
+                        (C.c_int * 3)(slots_per_pixel, trace_budget, trace_min_active))
     device_lib().setRendererOptions(C.byref(o))
 
 

@@ -90,13 +90,15 @@ void rendererCopyToHost(void* dst, const void* dSrc, size_t bytes);
 void rendererCopyToDevice(void* dDst, const void* src, size_t bytes);
 
 typedef struct renderer_stats {
-    unsigned long long raysExtend;  // closest-hit rays traced by the last runRenderer (primary + secondary)
-    unsigned long long raysShadow;  // any-hit rays traced by the last runRenderer
+    unsigned long long raysExtend;  // closest-hit rays traced by the last runRenderer (primary + secondary) = calls of hit(.., false)
+    unsigned long long raysShadow;  // any-hit rays traced by the last runRenderer = calls of hit(.., true)
     unsigned long long samples;     // nx*ny*ns
     unsigned long long kernelLaunches; // kernels launched by the last runRenderer
-    unsigned long long iterations;  // wavefront iterations
+    unsigned long long iterations;  // wavefront iterations that had work
+    unsigned long long resumes;     // rays that ran out of their per-launch step budget and continued in a later launch
+    unsigned long long deferred;    // shade entries postponed one iteration because the slot's shadow ray was pending
     float msTotal;                  // device time of the last runRenderer (CUDA events on the render stream)
-    float msExtend, msShade, msShadow, msOther; // per-kernel-family device time (only when profiling is on)
+    float msTrace, msShade, msOther; // per-kernel-family device time (only when profiling is on)
     int profiled;
 } renderer_stats;
 
@@ -110,6 +112,10 @@ void setRendererProfiling(int on);
 void* getRendererAccumDevice();   // device pointer, nx*ny float4
 void setRendererAccumDevice(void* dAccum); // render into a caller-owned device buffer (e.g. a torch tensor) instead
 void finalizeFrame(int nsTotal);  // fb = accum / nsTotal (blocking)
+
+// Diagnostic hook for tests: copy one per-slot array of the mesh pipeline ("rayO","rayD","atten","pcol","hit","shO","shD",
+// "shL","shC","accum"; float4 per slot / pixel) to the host. Returns the number of bytes copied (0 = unknown name).
+size_t rendererDebugRead(const char* name, void* dst, size_t maxBytes);
 
 // Instrumentation for the flop side of the roofline: when on, the traversal kernels count
 // internal-node visits (two slab tests each) and triangle tests.  Never on in timed runs.
