@@ -31,7 +31,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "cuda-raytracing-optimized_b200", "python"))
 
 FLT_MAX = 3.4028234663852886e38
-EXTEND_BYTES_PER_RAY = 52   # queue index 4 + {origin,rng} 16 + {dir,flags} 16 read, {t,u,v,id} 16 written
+EXTEND_BYTES_PER_RAY = 56   # queue entry 4 + {origin,rng} 16 + {dir,flags} 16 read; {t,u,v,id} 16 + shade-queue entry 4 written
+SHADOW_BYTES_PER_RAY = 85   # entry 4 + {origin} 16 + {dir,dist} 16 + {contribution,flags} 16 read; colour 16 read + 16 written; pending 1
+RESUME_BYTES = 64           # a parked ray: state 8 + hit 16 + entry 4 written, then ray 32 + the same 28 read again
 BATCH_BYTES_PER_RAY = 52    # 32 in, 16 + 4 out
 
 
@@ -280,24 +282,25 @@ def run_ours(args, rank, world, local_rank):
         nv, tt = C.c_ulonglong(), C.c_ulonglong()
         L.getRendererTraversalCounts(C.byref(nv), C.byref(tt))
         iters = max(int(ps.iterations), 1)
-        avg_ms = ps.msExtend / iters
-        bytes_per_launch = EXTEND_BYTES_PER_RAY * ps.raysExtend / iters
+        avg_ms = ps.msTrace / iters
+        rays_all = ps.raysExtend + ps.raysShadow
+        bytes_per_launch = (EXTEND_BYTES_PER_RAY * ps.raysExtend + SHADOW_BYTES_PER_RAY * ps.raysShadow + RESUME_BYTES * ps.resumes) / iters
         achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
-        flops = 3.0 * (ps.raysExtend + ps.raysShadow) + 36.0 * nv.value + 48.0 * tt.value
-        trav_ms = ps.msExtend + ps.msShadow
+        flops = 3.0 * rays_all + 36.0 * nv.value + 48.0 * tt.value
+        trav_ms = ps.msTrace
         sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
         fp32_peak = sms * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
-        roof = dict(bound="hbm", kernel="extendKernel<false>", achieved=achieved, peak=pk["hbm_gbs"], unit="GB/s", frac=achieved / pk["hbm_gbs"],
-                    traffic=None, peak_source=pk["src"], avg_launch_ms=avg_ms, launches=iters, bytes_per_ray=EXTEND_BYTES_PER_RAY,
+        roof = dict(bound="hbm", kernel="traceKernel<false>", achieved=achieved, peak=pk["hbm_gbs"], unit="GB/s", frac=achieved / pk["hbm_gbs"],
+                    traffic=None, peak_source=pk["src"], avg_launch_ms=avg_ms, launches=iters,
+                    bytes_per_ray=dict(extend=EXTEND_BYTES_PER_RAY, shadow=SHADOW_BYTES_PER_RAY, resumed=RESUME_BYTES),
                     note="scene (19 MB) is L2-resident by design: the kernel is bound by L2 latency and FP32 issue, not HBM; see fp32",
                     fp32=dict(achieved=flops / (trav_ms * 1e-3) / 1e12, peak=fp32_peak, unit="TFLOP/s",
-                              frac=flops / (trav_ms * 1e-3) / 1e12 / fp32_peak, kernels="extendKernel + shadowKernel",
-                              node_visits_per_ray=nv.value / max(ps.raysExtend + ps.raysShadow, 1),
-                              tri_tests_per_ray=tt.value / max(ps.raysExtend + ps.raysShadow, 1),
+                              frac=flops / (trav_ms * 1e-3) / 1e12 / fp32_peak, kernels="traceKernel",
+                              node_visits_per_ray=nv.value / max(rays_all, 1), tri_tests_per_ray=tt.value / max(rays_all, 1),
                               formula="3*rays + 36*dual-node visits + 48*triangle tests (SURVEY.md 8d)"))
-        extra = dict(kernel_ms_profiled=dict(extend=ps.msExtend, shade=ps.msShade, shadow=ps.msShadow, raygen_advance=ps.msOther,
+        extra = dict(kernel_ms_profiled=dict(trace=ps.msTrace, shade=ps.msShade,
                                              note="per-family CUDA events, one sync per iteration (serialised)"),
-                     wavefront_iterations=iters)
+                     wavefront_iterations=iters, resumed_rays=int(ps.resumes), deferred_shades=int(ps.deferred))
     fr.close()
 
     # ---- e2e: host buffers -> frame on the host, through the reference-facing entry points, every step

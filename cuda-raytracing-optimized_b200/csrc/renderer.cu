@@ -285,14 +285,20 @@ void crtRunMesh(RendererContext& c, int ns) {
             cudaEvent_t ev[3];
             for (auto& e : ev) CRT_CHECK(cudaEventCreate(&e));
             c.stats.profiled = 1;
+            const bool dump = std::getenv("CRT_DUMP_ITERATIONS") != nullptr; // per-iteration queue sizes and kernel times on stderr
+            unsigned long long iter = 0;
             while (true) {
                 for (int cur = 0; cur < 2; cur++) {
+                    if (dump) CRT_CHECK(cudaMemcpyAsync(host, mp.ctl, sizeof(MeshControl), cudaMemcpyDeviceToHost, stream));
                     launchMeshIteration(c, stream, cur, ev);
                     launches += MESH_KERNELS_PER_ITERATION;
                     CRT_CHECK(cudaStreamSynchronize(stream));
-                    float ms;
-                    cudaEventElapsedTime(&ms, ev[0], ev[1]); c.stats.msTrace += ms;
-                    cudaEventElapsedTime(&ms, ev[1], ev[2]); c.stats.msShade += ms;
+                    float msT, msS;
+                    cudaEventElapsedTime(&msT, ev[0], ev[1]); c.stats.msTrace += msT;
+                    cudaEventElapsedTime(&msS, ev[1], ev[2]); c.stats.msShade += msS;
+                    if (dump) std::fprintf(stderr, "iter %llu trace %u deferred %u  trace_ms %.4f shade_ms %.4f\n", iter, host->traceCount[cur],
+                                           host->shadeCount[cur], msT, msS);
+                    iter++;
                 }
                 CRT_CHECK(cudaMemcpyAsync(host, mp.ctl, sizeof(MeshControl), cudaMemcpyDeviceToHost, stream));
                 CRT_CHECK(cudaStreamSynchronize(stream));
