@@ -33,16 +33,18 @@ __device__ __forceinline__ RayPrep prepRay(const f3& o, const f3& dirNormalised)
     return r;
 }
 
-// One axis of the slab loop (intersections.h:27-36). NaNs (0 * inf) leave tMin/tMax unchanged,
-// exactly like the reference's `t0 > t_min ? t0 : t_min` selects.
+// One axis of the slab loop (intersections.h:27-36):
+//     t0 = (bmin - o) * invD; t1 = (bmax - o) * invD; if (invD < 0) swap(t0, t1);
+//     t_min = t0 > t_min ? t0 : t_min;  t_max = t1 < t_max ? t1 : t_max;
+// The swap is a per-ray constant (sign of invD), so the near/far plane is selected before the multiply: the two products
+// are the same two products. The ternaries keep t_min / t_max when t0 / t1 is NaN (0 * inf); fmaxf / fminf return their
+// non-NaN operand, i.e. the same value, in one min/max instruction instead of a compare plus a select.
 __device__ __forceinline__ void slabAxis(float bmin, float bmax, float o, float inv, float& tMin, float& tMax) {
-    float t0 = (bmin - o) * inv;
-    float t1 = (bmax - o) * inv;
-    if (inv < 0.0f) {
-        float tmp = t0; t0 = t1; t1 = tmp;
-    }
-    tMin = t0 > tMin ? t0 : tMin;
-    tMax = t1 < tMax ? t1 : tMax;
+    const bool neg = inv < 0.0f;
+    const float t0 = ((neg ? bmax : bmin) - o) * inv;
+    const float t1 = ((neg ? bmin : bmax) - o) * inv;
+    tMin = fmaxf(tMin, t0);
+    tMax = fminf(tMax, t1);
 }
 
 // hit_bbox_dist: entry distance, or FLT_MAX. tMin only grows and tMax only shrinks, so testing

@@ -128,6 +128,10 @@ __global__ void __launch_bounds__(WF_BLOCK) traceKernel(MeshState st, MeshView m
     unsigned int* __restrict__ nextTrace = st.traceQ[cur ^ 1];
     unsigned int* __restrict__ shadeQ = st.shadeQ[cur];
     const unsigned int lane = laneId();
+    // Entries a warp takes per refill: 32 when the queue is long; when it is shorter than the grid (the tail of a frame)
+    // the rays are spread one per warp, so that no ray waits in lockstep for a longer one in the same warp.
+    const unsigned int totalWarps = gridDim.x * (WF_BLOCK / 32);
+    const unsigned int take = min(32u, max(1u, (n + totalWarps - 1) / totalWarps));
 
     bool live = false;       // this lane holds a ray
     bool exhausted = false;  // the queue has no more entries for this warp
@@ -144,16 +148,17 @@ __global__ void __launch_bounds__(WF_BLOCK) traceKernel(MeshState st, MeshView m
     while (true) {
         // ---- refill idle lanes, one atomic per warp
         if (!exhausted) {
-            const bool want = !live;
-            const unsigned int mask = __ballot_sync(0xFFFFFFFFu, want);
-            if (mask) {
+            const unsigned int idle = __ballot_sync(0xFFFFFFFFu, !live);
+            const unsigned int busy = 32u - __popc(idle);
+            if (idle != 0u && busy < take) {
+                const unsigned int count = min((unsigned int)__popc(idle), take - busy);
                 unsigned int base = 0;
-                const unsigned int leader = __ffs(mask) - 1;
-                if (lane == leader) base = atomicAdd(&ctl->traceCursor, __popc(mask));
-                base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                if (base + __popc(mask) >= n) exhausted = true; // warp-uniform: the tail of the queue has been handed out
-                const unsigned int i = base + __popc(mask & ((1u << lane) - 1u));
-                if (want && i < n) {
+                if (lane == 0) base = atomicAdd(&ctl->traceCursor, count);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (base + count >= n) exhausted = true; // warp-uniform: the tail of the queue has been handed out
+                const unsigned int rank = __popc(idle & ((1u << lane) - 1u));
+                const unsigned int i = base + rank;
+                if (!live && rank < count && i < n) {
                     entry = queue[i];
                     const unsigned int slot = entry & ENTRY_SLOT_MASK;
                     const bool isShadow = (entry & ENTRY_SHADOW) != 0u;
@@ -187,7 +192,7 @@ __global__ void __launch_bounds__(WF_BLOCK) traceKernel(MeshState st, MeshView m
 
         // ---- traverse
         const bool isShadow = (entry & ENTRY_SHADOW) != 0u;
-        travRun(mesh, r, RT_EPSILON, isShadow, live, s, steps, st.traceBudget, exhausted ? 1 : st.traceMinActive, nodeVisits, triTests);
+        travRun(mesh, r, RT_EPSILON, isShadow, live, s, steps, st.traceBudget, exhausted ? 1 : min((unsigned int)st.traceMinActive, take), nodeVisits, triTests);
 
         // ---- retire finished rays, park the ones that ran out of budget
         const unsigned int slot = entry & ENTRY_SLOT_MASK;

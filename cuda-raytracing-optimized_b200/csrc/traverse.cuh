@@ -62,10 +62,11 @@ __device__ __forceinline__ bool travLeafStep(const MeshView& m, const RayPrep& r
                                              unsigned int& triTests) {
     const unsigned int first = (s.idx - m.firstLeaf) * m.primsPerLeaf;
     for (unsigned int i = 0; i < m.primsPerLeaf; i++) {
+        // all 48 bytes of the tile are requested together (one round trip); unused slots are readable padding
         const float4 t0 = __ldg(m.tris + 3 * (first + i));
-        if (isinf(t0.x)) break;
         const float4 t1 = __ldg(m.tris + 3 * (first + i) + 1);
         const float4 t2 = __ldg(m.tris + 3 * (first + i) + 2);
+        if (isinf(t0.x)) break;
         triTests++;
         float u, v;
         const float hitT = triHit(mk3(t0.x, t0.y, t0.z), mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), r, tMin, s.closest, u, v);
@@ -86,20 +87,34 @@ __device__ __forceinline__ bool travLeafStep(const MeshView& m, const RayPrep& r
 }
 
 // Run one lane's traversal for at most `budget` steps (a node step costs 1, a leaf visit 2); `steps` accumulates.
-// Lanes of a warp call this together: the inner node loop and the leaf body are each entered by the warp as a whole.
-// Returns when the lane is finished (s.idx == 0), out of budget, or when fewer than `minActive` lanes of the warp
-// still have work (the caller then refills the idle lanes and calls again).
+// Lanes of a warp call this together. Scheduling inside the warp (it does not change any lane's own sequence of steps):
+//   * node steps are issued while at least TRAV_NODE_QUORUM lanes stand on internal nodes; lanes that already reached a
+//     leaf wait for that long and no longer -- waiting for ALL lanes to reach a leaf (plain while-while) left 8 of 32
+//     lanes active in the node loop (profiles/r01/b_trace_ncu_summary.txt), a quorum of 16 doubles that in simulation;
+//   * then the leaves are processed for every lane that stands on one.
+// Returns when fewer than `minActive` lanes of the warp still have work (finished, out of budget or idle): the caller
+// retires / refills lanes and calls again.
+#define TRAV_NODE_QUORUM 16
+
 __device__ __forceinline__ void travRun(const MeshView& m, const RayPrep& r, float tMin, bool anyHit, bool live, TravState& s,
                                         int& steps, int budget, int minActive, unsigned int& nodeVisits, unsigned int& triTests) {
     while (true) {
         bool work = live && s.idx != 0u && steps < budget;
         if (__popc(__ballot_sync(0xFFFFFFFFu, work)) < minActive) break;
         // node phase
-        while (work && s.idx < m.firstLeaf) {
-            travNodeStep(m, r, s);
-            nodeVisits++;
-            steps++;
-            work = s.idx != 0u && steps < budget;
+        while (true) {
+            const bool atNode = work && s.idx < m.firstLeaf;
+            const unsigned int nodeMask = __ballot_sync(0xFFFFFFFFu, atNode);
+            if (nodeMask == 0u) break;
+            const unsigned int leafMask = __ballot_sync(0xFFFFFFFFu, work && s.idx >= m.firstLeaf);
+            if (__popc(nodeMask) < TRAV_NODE_QUORUM && leafMask != 0u) break;        // let the waiting lanes test their leaves
+            if (__popc(nodeMask) + __popc(leafMask) < minActive) break;              // too few lanes left: let the caller refill
+            if (atNode) {
+                travNodeStep(m, r, s);
+                nodeVisits++;
+                steps++;
+                work = s.idx != 0u && steps < budget;
+            }
         }
         // leaf phase
         if (work && s.idx >= m.firstLeaf) {

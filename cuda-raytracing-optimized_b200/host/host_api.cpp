@@ -179,23 +179,25 @@ void buildStaircase(MeshGen& g) {
     const float sx0 = -300, sx1 = -40, rise = 22, run = 34, zStart = 150;
     for (int s = 0; s < nSteps; s++) {
         float zs = zStart - run * s;
-        g.box(vec3(sx0, y0, zs - run), vec3(sx1, rise * (s + 1), zs), 26, M_STAIRS, 2.0f);
-        // nosing strip
-        g.box(vec3(sx0, rise * (s + 1), zs - 3), vec3(sx1 + 4, rise * (s + 1) + 2.5f, zs + 3), 26, M_WOODCHAIR, 2.0f);
+        // No two faces of the scene are coplanar AND overlapping (exact ties would make the closest hit depend on the
+        // traversal order): boxes that touch either interpenetrate or keep a 0.2 gap, and nothing ends exactly on the floor.
+        g.box(vec3(sx0, y0 - 0.5f, zs - run + 0.2f), vec3(sx1, rise * (s + 1), zs), 26, M_STAIRS, 2.0f);
+        // nosing strip, sunk one unit into the tread
+        g.box(vec3(sx0 + 0.3f, rise * (s + 1) - 1.0f, zs - 3), vec3(sx1 + 4, rise * (s + 1) + 2.5f, zs + 3), 26, M_WOODCHAIR, 2.0f);
     }
     const float landY = rise * nSteps, landZ1 = zStart - run * nSteps;
     g.box(vec3(sx0, landY - 12, z0 + 2), vec3(x1 - 60, landY, landZ1), 48, M_STAIRS, 4.0f); // landing slab
     // balusters + hand rail along the open side of the flight
     for (int s = 0; s < nSteps; s++) {
         float zs = zStart - run * (s + 0.5f);
-        g.cylinder(vec3(sx1 - 8, rise * (s + 1), zs), 2.2f, 78, 16, 6, (s & 1) ? M_BRASS : M_BLACK);
+        g.cylinder(vec3(sx1 - 8, rise * (s + 1) - 0.5f, zs), 2.2f, 78.5f, 16, 6, (s & 1) ? M_BRASS : M_BLACK);
     }
     g.tube(vec3(sx1 - 8, rise + 80, zStart - run * 0.5f), vec3(sx1 - 8, landY + 80, landZ1 - run * 0.5f + run), 4.5f, 20, 60,
            M_WOODCHAIR);
     // balustrade along the landing edge
     for (int k = 0; k < 18; k++) {
         float x = sx1 + 10 + k * 18.0f;
-        g.cylinder(vec3(x, landY, landZ1 - 6), 2.2f, 78, 16, 6, (k & 1) ? M_GOLD : M_BLACK);
+        g.cylinder(vec3(x, landY - 0.5f, landZ1 - 6), 2.2f, 78.5f, 16, 6, (k & 1) ? M_GOLD : M_BLACK);
     }
     g.tube(vec3(sx1 - 8, landY + 80, landZ1 - 6), vec3(sx1 + 10 + 17 * 18.0f + 10, landY + 80, landZ1 - 6), 4.5f, 20, 40,
            M_WOODCHAIR);
@@ -219,14 +221,14 @@ void buildStaircase(MeshGen& g) {
     for (int c = 0; c < 2; c++) {
         float cx = 150 + 110 * c, cz = -40 + 170 * c;
         g.box(vec3(cx - 24, 44, cz - 24), vec3(cx + 24, 50, cz + 24), 10, M_WOODCHAIR);
-        g.box(vec3(cx - 22, 50, cz - 22), vec3(cx + 22, 56, cz + 22), 10, M_SEAT);
-        g.box(vec3(cx - 24, 50, cz - 28), vec3(cx + 24, 112, cz - 23), 12, M_WOODCHAIR);
+        g.box(vec3(cx - 22, 49.5f, cz - 22), vec3(cx + 22, 56, cz + 22), 10, M_SEAT);
+        g.box(vec3(cx - 23.5f, 49, cz - 28), vec3(cx + 23.5f, 112, cz - 23), 12, M_WOODCHAIR);
         for (int l = 0; l < 4; l++)
-            g.cylinder(vec3(cx + ((l & 1) ? 20.f : -20.f), 0, cz + ((l & 2) ? 20.f : -20.f)), 2.6f, 44, 14, 4, M_WOODCHAIR);
+            g.cylinder(vec3(cx + ((l & 1) ? 20.f : -20.f), -0.5f, cz + ((l & 2) ? 20.f : -20.f)), 2.6f, 45, 14, 4, M_WOODCHAIR);
     }
 
     // side table with glass vase, candles, steel and gold balls
-    g.cylinder(vec3(170, 0, 60), 5, 70, 24, 6, M_ALU);
+    g.cylinder(vec3(170, -0.5f, 60), 5, 71, 24, 6, M_ALU);
     g.cylinder(vec3(170, 70, 60), 46, 4, 64, 1, M_ALU);
     g.lathe(vec3(170, 74.5f, 60), [](float v) { return 7 + 9 * std::sin(2.6f * v) + 3 * v; }, [](float v) { return 58 * v; }, 96, 64,
             M_GLASS); // open vase (single sheet: a thin glass shell)
@@ -240,8 +242,8 @@ void buildStaircase(MeshGen& g) {
     g.torus(vec3(10, 10.5f, 200), 30, 10, 160, 48, M_STEEL);
 
     // floor lamp: wooden pole, fabric shade (open cone frustum), brass finial
-    g.cylinder(vec3(300, 0, -60), 16, 5, 48, 1, M_WOODLAMP);
-    g.cylinder(vec3(300, 5, -60), 3.2f, 290, 24, 24, M_WOODLAMP);
+    g.cylinder(vec3(300, -0.5f, -60), 16, 5.5f, 48, 1, M_WOODLAMP);
+    g.cylinder(vec3(300, 4.5f, -60), 3.2f, 290, 24, 24, M_WOODLAMP);
     g.lathe(vec3(300, 295, -60), [](float v) { return 52 - 22 * v; }, [](float v) { return 70 * v; }, 128, 32, M_SHADE);
     g.sphereMesh(vec3(300, 372, -60), 5, 32, M_BRASS);
 
@@ -249,7 +251,7 @@ void buildStaircase(MeshGen& g) {
     g.torus(vec3(52.5f, 610, -272.6f), 70, 4, 256, 24, M_GOLD);
     for (int k = 0; k < 12; k++) {
         float a = 2 * kPi * k / 12;
-        vec3 base(52.5f + 70 * std::cos(a), 614, -272.6f + 70 * std::sin(a));
+        vec3 base(52.5f + 70 * std::cos(a), 613.5f, -272.6f + 70 * std::sin(a));
         g.cylinder(base, 2.0f, 16, 16, 2, M_CANDLE);
     }
     // a draped cloth (heightfield) on the landing: fine tessellation = most of the triangle budget
