@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(WF_BLOCK) traceKernel(MeshState st, MeshView m
     TravState s;
     float tMax = 0.0f;
     int steps = 0;
-    unsigned int nodeVisits = 0, triTests = 0, doneExtend = 0, doneShadow = 0, parked = 0;
+    unsigned int nodeVisits = 0, triTests = 0;
     r.o = r.d = r.inv = mk3(0.0f, 0.0f, 0.0f);
     travInit(s, 0.0f);
     s.idx = 0;
@@ -192,7 +192,10 @@ __global__ void __launch_bounds__(WF_BLOCK) traceKernel(MeshState st, MeshView m
 
         // ---- traverse
         const bool isShadow = (entry & ENTRY_SHADOW) != 0u;
-        travRun(mesh, r, RT_EPSILON, isShadow, live, s, steps, st.traceBudget, exhausted ? 1 : min((unsigned int)st.traceMinActive, take), nodeVisits, triTests);
+        if (take < 32u) // short queue: latency-bound launch, spend instructions on prefetching
+            travRun<true>(mesh, r, RT_EPSILON, isShadow, live, s, steps, st.traceBudget, 1, nodeVisits, triTests);
+        else
+            travRun<false>(mesh, r, RT_EPSILON, isShadow, live, s, steps, st.traceBudget, exhausted ? 1 : st.traceMinActive, nodeVisits, triTests);
 
         // ---- retire finished rays, park the ones that ran out of budget
         const unsigned int slot = entry & ENTRY_SLOT_MASK;
@@ -203,7 +206,6 @@ __global__ void __launch_bounds__(WF_BLOCK) traceKernel(MeshState st, MeshView m
             if (!isShadow) {
                 // hitMesh returns `closest` (== t_max when nothing was hit) or FLT_MAX; hit() tests `< t_max` (kernels.cu:330)
                 st.hit[slot] = make_float4(s.closest, s.u, s.v, __uint_as_float(s.triId));
-                doneExtend++;
             } else {
                 const float4 l = st.shL[slot];
                 const bool unoccluded = !(s.closest < tMax); // hit(...) false: p.color += p.lightContribution (kernels.cu:500-508)
@@ -217,7 +219,6 @@ __global__ void __launch_bounds__(WF_BLOCK) traceKernel(MeshState st, MeshView m
                     st.pcol[slot] = c;
                 }
                 st.pending[slot] = 0;
-                doneShadow++;
             }
             live = false;
         }
@@ -228,30 +229,31 @@ __global__ void __launch_bounds__(WF_BLOCK) traceKernel(MeshState st, MeshView m
                 st.travE[slot] = make_uint2(s.idx, s.bitStack);
                 st.hit[slot] = make_float4(s.closest, s.u, s.v, __uint_as_float(s.triId));
             }
-            parked++;
             live = false;
         }
-        const unsigned int posShade = warpAppend(toShade, &ctl->shadeCount[cur]);
-        if (toShade) shadeQ[posShade] = slot;
-        const unsigned int posPark = warpAppend(park, &ctl->traceCount[cur ^ 1]);
-        if (park) nextTrace[posPark] = entry | ENTRY_RESUME;
+        // queue appends and ray statistics: one atomic per warp per counter (ballot + popc)
+        const unsigned int mShade = __ballot_sync(0xFFFFFFFFu, toShade);
+        const unsigned int mPark = __ballot_sync(0xFFFFFFFFu, park);
+        const unsigned int mShadowDone = __ballot_sync(0xFFFFFFFFu, finished && isShadow);
+        unsigned int baseShade = 0, basePark = 0;
+        if (lane == 0) {
+            if (mShade) { baseShade = atomicAdd(&ctl->shadeCount[cur], __popc(mShade)); atomicAdd(&ctl->raysExtend, (unsigned long long)__popc(mShade)); }
+            if (mPark) { basePark = atomicAdd(&ctl->traceCount[cur ^ 1], __popc(mPark)); atomicAdd(&ctl->resumes, (unsigned long long)__popc(mPark)); }
+            if (mShadowDone) atomicAdd(&ctl->raysShadow, (unsigned long long)__popc(mShadowDone));
+        }
+        baseShade = __shfl_sync(0xFFFFFFFFu, baseShade, 0);
+        basePark = __shfl_sync(0xFFFFFFFFu, basePark, 0);
+        const unsigned int below = (1u << lane) - 1u;
+        if (toShade) shadeQ[baseShade + __popc(mShade & below)] = slot;
+        if (park) nextTrace[basePark + __popc(mPark & below)] = entry | ENTRY_RESUME;
     }
 
-    // per-warp statistics: one atomic per counter per warp
-    for (int o = 16; o > 0; o >>= 1) {
-        doneExtend += __shfl_xor_sync(0xFFFFFFFFu, doneExtend, o);
-        doneShadow += __shfl_xor_sync(0xFFFFFFFFu, doneShadow, o);
-        parked += __shfl_xor_sync(0xFFFFFFFFu, parked, o);
-        if (COUNT) {
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) {
             nodeVisits += __shfl_xor_sync(0xFFFFFFFFu, nodeVisits, o);
             triTests += __shfl_xor_sync(0xFFFFFFFFu, triTests, o);
         }
-    }
-    if (lane == 0) {
-        if (doneExtend) atomicAdd(&ctl->raysExtend, (unsigned long long)doneExtend);
-        if (doneShadow) atomicAdd(&ctl->raysShadow, (unsigned long long)doneShadow);
-        if (parked) atomicAdd(&ctl->resumes, (unsigned long long)parked);
-        if (COUNT) {
+        if (lane == 0) {
             atomicAdd(&ctl->nodeVisits, (unsigned long long)nodeVisits);
             atomicAdd(&ctl->triTests, (unsigned long long)triTests);
         }
@@ -418,4 +420,75 @@ __global__ void __launch_bounds__(WF_BLOCK) meshShadeKernel(MeshState st, ShadeS
         ctl->traceCursor = 0;
         ctl->blocksDone = 0;
     }
+}
+
+// ------------------------------------------------------------ express lane --
+// The frame's critical path is its heaviest pixels: one RNG stream per pixel means a pixel's bounces are strictly
+// sequential (kernels.cu:542-548), and a pixel looking into glass needs ~5x the bounces of an average one. In a single
+// wavefront those pixels advance one bounce per iteration while iterations are long (~1 ms with ~1.6 M rays), and then
+// drag a ~4000-iteration tail of nearly empty launches behind the bulk. So slots that fall behind (sample index well below
+// the mean of all live slots) are moved to a second, small wavefront -- same kernels, same state arrays, own queues and
+// control block -- that runs concurrently on its own stream with short iterations. Results do not change: every slot is
+// still processed by the same kernels in the same per-slot order, only by another queue.
+__global__ void laneStatsKernel(MeshState a, unsigned long long* sums) {
+    const unsigned int n1 = a.ctl->traceCount[0], n2 = a.ctl->shadeCount[0];
+    unsigned long long sum = 0, cnt = 0;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += gridDim.x * blockDim.x) {
+        const unsigned int entry = i < n1 ? a.traceQ[0][i] : a.shadeQ[0][i - n1];
+        if (entry & ENTRY_SHADOW) continue; // count every live slot once: by its extend entry or its deferred shade entry
+        sum += (unsigned long long)__float_as_int(a.atten[entry & ENTRY_SLOT_MASK].w);
+        cnt += 1;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+        cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+    }
+    if (laneId() == 0 && cnt) { atomicAdd(&sums[0], sum); atomicAdd(&sums[1], cnt); }
+}
+
+// Splits A's input queues (index 0): lagging slots go to B's input queues, the rest to A's spare queues (index 1).
+// A slot's entries (extend, shadow, deferred shade) all take the same side: the decision reads only per-slot state.
+__global__ void lanePartitionKernel(MeshState a, MeshState b, const unsigned long long* sums, float factor, int minMean, unsigned int moveAllBelow,
+                                    unsigned int capB) {
+    const unsigned int n1 = a.ctl->traceCount[0], n2 = a.ctl->shadeCount[0];
+    const float mean = sums[1] ? (float)((double)sums[0] / (double)sums[1]) : 0.0f;
+    const bool moveAll = n1 + n2 <= moveAllBelow;
+    const bool allowed = moveAll || (mean >= (float)minMean && b.ctl->traceCount[0] + b.ctl->shadeCount[0] < capB);
+    const float threshold = factor * mean;
+    const unsigned int stride = gridDim.x * blockDim.x;
+    for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n1 + n2; base += stride) {
+        const unsigned int i = base + laneId();
+        const bool valid = i < n1 + n2;
+        const bool isTrace = i < n1;
+        unsigned int entry = 0;
+        bool lag = false;
+        if (valid) {
+            entry = isTrace ? a.traceQ[0][i] : a.shadeQ[0][i - n1];
+            lag = allowed && (moveAll || (float)__float_as_int(a.atten[entry & ENTRY_SLOT_MASK].w) < threshold);
+        }
+        unsigned int pos;
+        pos = warpAppend(valid && isTrace && lag, &b.ctl->traceCount[0]);
+        if (valid && isTrace && lag) b.traceQ[0][pos] = entry;
+        pos = warpAppend(valid && isTrace && !lag, &a.ctl->traceCount[1]);
+        if (valid && isTrace && !lag) a.traceQ[1][pos] = entry;
+        pos = warpAppend(valid && !isTrace && lag, &b.ctl->shadeCount[0]);
+        if (valid && !isTrace && lag) b.shadeQ[0][pos] = entry;
+        pos = warpAppend(valid && !isTrace && !lag, &a.ctl->shadeCount[1]);
+        if (valid && !isTrace && !lag) a.shadeQ[1][pos] = entry;
+    }
+}
+
+__global__ void laneCopyBackKernel(MeshState a) {
+    const unsigned int n1 = a.ctl->traceCount[1], n2 = a.ctl->shadeCount[1];
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += gridDim.x * blockDim.x) {
+        if (i < n1) a.traceQ[0][i] = a.traceQ[1][i];
+        else a.shadeQ[0][i - n1] = a.shadeQ[1][i - n1];
+    }
+}
+
+__global__ void laneCommitKernel(MeshControl* ctl) {
+    ctl->traceCount[0] = ctl->traceCount[1];
+    ctl->shadeCount[0] = ctl->shadeCount[1];
+    ctl->traceCount[1] = 0;
+    ctl->shadeCount[1] = 0;
 }

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256, 4) intersectBatchKernel(MeshView mesh, co
             }
         }
         if (!__any_sync(0xFFFFFFFFu, live)) break;
-        travRun(mesh, r, tMin, false, live, s, steps, 0x7FFFFFFF, exhausted ? 1 : 20, nodeVisits, triTests);
+        travRun<false>(mesh, r, tMin, false, live, s, steps, 0x7FFFFFFF, exhausted ? 1 : 20, nodeVisits, triTests);
         if (live && s.idx == 0u) {
             float t = s.closest;
             unsigned int triId = s.triId;

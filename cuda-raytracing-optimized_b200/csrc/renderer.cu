@@ -6,6 +6,7 @@
 //   cleanupRenderer  kernels.cu:666-680
 // and keeps the reference's error behaviour (check_cuda, kernels.cu:30-37).
 // There is no CPU fallback: without a CUDA device every entry point exits(99).
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -77,7 +78,11 @@ static void freeMeshPipeline(RendererContext& c) {
     cudaFree(s.traceQ[0]); cudaFree(s.traceQ[1]); cudaFree(s.shadeQ[0]); cudaFree(s.shadeQ[1]);
     cudaFree(s.ctl);
     std::memset(&s, 0, sizeof(s));
+    MeshState& f = c.mpFast;
+    cudaFree(f.traceQ[0]); cudaFree(f.traceQ[1]); cudaFree(f.shadeQ[0]); cudaFree(f.shadeQ[1]); cudaFree(f.ctl);
+    std::memset(&f, 0, sizeof(f));
     if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
+    if (c.graphFast) { cudaGraphExecDestroy(c.graphFast); c.graphFast = nullptr; }
     c.graphKey = -1;
 }
 
@@ -103,6 +108,12 @@ static void allocMeshPipeline(RendererContext& c, unsigned int numSlots) {
         s.shadeQ[k] = devAlloc<unsigned int>(numSlots);
     }
     s.ctl = devAlloc<MeshControl>(1);
+    MeshState& f = c.mpFast;
+    for (int k = 0; k < 2; k++) {
+        f.traceQ[k] = devAlloc<unsigned int>(2 * (size_t)numSlots);
+        f.shadeQ[k] = devAlloc<unsigned int>(numSlots);
+    }
+    f.ctl = devAlloc<MeshControl>(1);
 }
 
 extern "C" void setRendererOptions(const renderer_options* opt) {
@@ -132,6 +143,12 @@ static void initCommon(RendererContext& c, const camera& cam, vec3** fb, int nx,
     c.cam.w = toF3(cam.w);
     c.cam.lensRadius = cam.lens_radius;
     CRT_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    int prLow = 0, prHigh = 0;
+    CRT_CHECK(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
+    CRT_CHECK(cudaStreamCreateWithPriority(&c.streamFast, cudaStreamNonBlocking, prHigh));
+    CRT_CHECK(cudaEventCreateWithFlags(&c.evLane, cudaEventDisableTiming));
+    c.laneSums = devAlloc<unsigned long long>(2);
+    CRT_CHECK(cudaMallocHost((void**)&c.hostCtlFast, sizeof(MeshControl)));
     CRT_CHECK(cudaEventCreate(&c.evStart));
     CRT_CHECK(cudaEventCreate(&c.evStop));
     const size_t npix = (size_t)nx * ny;
@@ -233,13 +250,25 @@ static ShadeScene shadeScene(const RendererContext& c) {
 }
 
 // One wavefront iteration on `stream`: trace (extend + shadow rays) -> shade (+ retire sample, + next camera ray).
-static void launchMeshIteration(RendererContext& c, cudaStream_t stream, int cur, cudaEvent_t* ev) {
+static void launchMeshIteration(RendererContext& c, const MeshState& mp, cudaStream_t stream, int cur, int traceBlocks, int shadeBlocks,
+                                cudaEvent_t* ev) {
     if (ev) cudaEventRecord(ev[0], stream);
-    if (c.counting) traceKernel<true><<<c.traceBlocks, WF_BLOCK, 0, stream>>>(c.mp, c.mesh, cur);
-    else traceKernel<false><<<c.traceBlocks, WF_BLOCK, 0, stream>>>(c.mp, c.mesh, cur);
+    if (c.counting) traceKernel<true><<<traceBlocks, WF_BLOCK, 0, stream>>>(mp, c.mesh, cur);
+    else traceKernel<false><<<traceBlocks, WF_BLOCK, 0, stream>>>(mp, c.mesh, cur);
     if (ev) cudaEventRecord(ev[1], stream);
-    meshShadeKernel<<<c.numSMs * 4, WF_BLOCK, 0, stream>>>(c.mp, shadeScene(c), c.cam, cur);
+    meshShadeKernel<<<shadeBlocks, WF_BLOCK, 0, stream>>>(mp, shadeScene(c), c.cam, cur);
     if (ev) cudaEventRecord(ev[2], stream);
+}
+
+static cudaGraphExec_t captureMeshBatch(RendererContext& c, const MeshState& mp, cudaStream_t stream, int batch, int traceBlocks, int shadeBlocks) {
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    CRT_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    for (int k = 0; k < batch; k++) launchMeshIteration(c, mp, stream, k & 1, traceBlocks, shadeBlocks, nullptr);
+    CRT_CHECK(cudaStreamEndCapture(stream, &graph));
+    CRT_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+    CRT_CHECK(cudaGraphDestroy(graph));
+    return exec;
 }
 
 #define MESH_KERNELS_PER_ITERATION 2
@@ -281,6 +310,8 @@ void crtRunMesh(RendererContext& c, int ns) {
 
         int batch = c.opts.megaBatch > 0 ? c.opts.megaBatch : 16;
         batch = (batch + 1) & ~1; // even: the two queue sets swap roles every iteration
+        const char* lanesEnv = std::getenv("CRT_EXPRESS_LANE");
+        const bool lanes = !g_profiling && !(lanesEnv && lanesEnv[0] == '0') && c.traceBlocks >= 2 * c.numSMs;
         if (g_profiling) {
             cudaEvent_t ev[3];
             for (auto& e : ev) CRT_CHECK(cudaEventCreate(&e));
@@ -290,7 +321,7 @@ void crtRunMesh(RendererContext& c, int ns) {
             while (true) {
                 for (int cur = 0; cur < 2; cur++) {
                     if (dump) CRT_CHECK(cudaMemcpyAsync(host, mp.ctl, sizeof(MeshControl), cudaMemcpyDeviceToHost, stream));
-                    launchMeshIteration(c, stream, cur, ev);
+                    launchMeshIteration(c, mp, stream, cur, c.traceBlocks, c.numSMs * 4, ev);
                     launches += MESH_KERNELS_PER_ITERATION;
                     CRT_CHECK(cudaStreamSynchronize(stream));
                     float msT, msS;
@@ -307,24 +338,76 @@ void crtRunMesh(RendererContext& c, int ns) {
             for (auto& e : ev) cudaEventDestroy(e);
         } else {
             const long long key = ((long long)mp.samplesPerSlot << 24) ^ ((long long)slotsPerPixel << 8) ^ batch ^
-                                  ((long long)c.counting << 60) ^ ((long long)c.maxDepth << 40) ^ ((long long)mp.streamBase << 48) ^ ((long long)mp.traceBudget << 12) ^
-                                  ((long long)mp.traceMinActive << 4);
+                                  ((long long)c.counting << 60) ^ ((long long)c.maxDepth << 40) ^ ((long long)mp.streamBase << 48) ^
+                                  ((long long)mp.traceBudget << 12) ^ ((long long)mp.traceMinActive << 4) ^ ((long long)lanes << 59);
+            // lane A (bulk) leaves one block per SM to lane B (express) so that both run at the same time
+            const int blocksA = lanes ? c.traceBlocks - c.numSMs : c.traceBlocks;
+            const int blocksB = c.numSMs;
+            MeshState& fast = c.mpFast;
+            if (lanes) {
+                MeshControl* ctlB = fast.ctl;
+                unsigned int* q[4] = {fast.traceQ[0], fast.traceQ[1], fast.shadeQ[0], fast.shadeQ[1]};
+                fast = mp; // same state arrays and frame parameters ...
+                fast.ctl = ctlB; // ... own control block and queues
+                fast.traceQ[0] = q[0]; fast.traceQ[1] = q[1]; fast.shadeQ[0] = q[2]; fast.shadeQ[1] = q[3];
+                CRT_CHECK(cudaMemsetAsync(fast.ctl, 0, sizeof(MeshControl), stream));
+            }
             if (!c.graphExec || c.graphKey != key) {
                 if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
-                cudaGraph_t graph;
-                CRT_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-                for (int k = 0; k < batch; k++) launchMeshIteration(c, stream, k & 1, nullptr);
-                CRT_CHECK(cudaStreamEndCapture(stream, &graph));
-                CRT_CHECK(cudaGraphInstantiate(&c.graphExec, graph, 0));
-                CRT_CHECK(cudaGraphDestroy(graph));
+                if (c.graphFast) { cudaGraphExecDestroy(c.graphFast); c.graphFast = nullptr; }
+                c.graphExec = captureMeshBatch(c, mp, stream, batch, blocksA, c.numSMs * (lanes ? 3 : 4));
+                if (lanes) c.graphFast = captureMeshBatch(c, fast, c.streamFast, batch, blocksB, c.numSMs);
                 c.graphKey = key;
             }
+            MeshControl* hostB = c.hostCtlFast;
+            bool workA = true, workB = false;
+            const bool dumpLanes = std::getenv("CRT_DUMP_LANES") != nullptr;
+            const auto t0 = std::chrono::steady_clock::now();
             while (true) {
-                CRT_CHECK(cudaGraphLaunch(c.graphExec, stream));
-                launches += (unsigned long long)batch * MESH_KERNELS_PER_ITERATION;
-                CRT_CHECK(cudaMemcpyAsync(host, mp.ctl, sizeof(MeshControl), cudaMemcpyDeviceToHost, stream));
+                if (lanes && workA) { // move lagging slots from A's input queues to B's (both lanes are idle here)
+                    CRT_CHECK(cudaMemsetAsync(c.laneSums, 0, 2 * sizeof(unsigned long long), stream));
+                    laneStatsKernel<<<c.numSMs * 2, WF_BLOCK, 0, stream>>>(mp, c.laneSums);
+                    lanePartitionKernel<<<c.numSMs * 2, WF_BLOCK, 0, stream>>>(mp, fast, c.laneSums, 0.4f, 6, 24576u, 131072u);
+                    laneCopyBackKernel<<<c.numSMs * 2, WF_BLOCK, 0, stream>>>(mp);
+                    laneCommitKernel<<<1, 1, 0, stream>>>(mp.ctl);
+                    launches += 4;
+                    CRT_CHECK(cudaEventRecord(c.evLane, stream));
+                    CRT_CHECK(cudaStreamWaitEvent(c.streamFast, c.evLane, 0));
+                }
+                if (workA) {
+                    CRT_CHECK(cudaGraphLaunch(c.graphExec, stream));
+                    launches += (unsigned long long)batch * MESH_KERNELS_PER_ITERATION;
+                    CRT_CHECK(cudaMemcpyAsync(host, mp.ctl, sizeof(MeshControl), cudaMemcpyDeviceToHost, stream));
+                    CRT_CHECK(cudaEventRecord(c.evLane, stream));
+                }
+                if (lanes) { // run B batches until A's batch is done (at least one)
+                    while (true) {
+                        CRT_CHECK(cudaGraphLaunch(c.graphFast, c.streamFast));
+                        launches += (unsigned long long)batch * MESH_KERNELS_PER_ITERATION;
+                        CRT_CHECK(cudaMemcpyAsync(hostB, fast.ctl, sizeof(MeshControl), cudaMemcpyDeviceToHost, c.streamFast));
+                        CRT_CHECK(cudaStreamSynchronize(c.streamFast));
+                        workB = hostB->traceCount[0] != 0 || hostB->shadeCount[0] != 0;
+                        if (!workB || !workA || cudaEventQuery(c.evLane) == cudaSuccess) break;
+                    }
+                }
                 CRT_CHECK(cudaStreamSynchronize(stream));
-                if (host->traceCount[0] == 0 && host->shadeCount[0] == 0) break;
+                workA = host->traceCount[0] != 0 || host->shadeCount[0] != 0;
+                if (dumpLanes) {
+                    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                    std::fprintf(stderr, "lanes t=%.2f ms  A: trace %u shade %u iters %llu   B: trace %u shade %u iters %llu\n", ms, host->traceCount[0],
+                                 host->shadeCount[0], host->iterations, lanes ? hostB->traceCount[0] : 0u, lanes ? hostB->shadeCount[0] : 0u,
+                                 lanes ? hostB->iterations : 0ull);
+                }
+                if (!workA && !workB) break;
+            }
+            if (lanes) { // fold lane B's counters into the frame's
+                host->raysExtend += hostB->raysExtend;
+                host->raysShadow += hostB->raysShadow;
+                host->resumes += hostB->resumes;
+                host->deferred += hostB->deferred;
+                host->iterations += hostB->iterations;
+                host->nodeVisits += hostB->nodeVisits;
+                host->triTests += hostB->triTests;
             }
         }
     } else {
@@ -424,6 +507,10 @@ extern "C" void cleanupRenderer() {
     c.texPtrHost.clear();
     cudaFree(c.texData); cudaFree(c.texWidth); cudaFree(c.texHeight);
     cudaFreeHost(c.hostCtl);
+    cudaFreeHost(c.hostCtlFast);
+    cudaFree(c.laneSums);
+    cudaEventDestroy(c.evLane);
+    cudaStreamDestroy(c.streamFast);
     cudaEventDestroy(c.evStart); cudaEventDestroy(c.evStop);
     cudaStreamDestroy(c.stream);
     const bool reset = c.opts.resetDeviceOnCleanup != 0;

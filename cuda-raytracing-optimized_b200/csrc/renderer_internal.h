@@ -45,6 +45,12 @@ struct RendererContext {
 
     // wavefront state: `mp` = mesh pipeline, `wf` = sphere pipeline (accum lives in wf.accum for both)
     MeshState mp = {};
+    MeshState mpFast = {}; // the express lane: same state arrays, own queues and control block
+    cudaStream_t streamFast = nullptr;
+    cudaGraphExec_t graphFast = nullptr;
+    cudaEvent_t evLane = nullptr;
+    unsigned long long* laneSums = nullptr;
+    MeshControl* hostCtlFast = nullptr; // pinned
     WfState wf = {};
     bool ownsAccum = false;
     WfControl* hostCtl = nullptr; // pinned

@@ -39,11 +39,31 @@ __device__ __forceinline__ void travPop(TravState& s) {
     s.idx = (s.idx >> m) ^ 1u;
 }
 
+__device__ __forceinline__ void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // One internal-node step (kernels.cu:163-197).
+// PREFETCH: whichever child is entered next, its record lies in the 96 bytes that start at float4 index 6*idx (children
+// 2*idx and 2*idx+1 are adjacent), or -- on the last internal level -- its triangles lie in the 2*N tiles that start at
+// leaf 2*idx - firstLeaf. Requesting those lines into L1 now overlaps the next step's memory latency with this step's
+// slab tests. Used when a launch has too few rays to hide latency with other warps (the tail of a frame).
+template <bool PREFETCH>
 __device__ __forceinline__ void travNodeStep(const MeshView& m, const RayPrep& r, TravState& s) {
     const float4 a = __ldg(m.nodes + 3 * s.idx);
     const float4 b = __ldg(m.nodes + 3 * s.idx + 1);
     const float4 c = __ldg(m.nodes + 3 * s.idx + 2);
+    if (PREFETCH) {
+        const unsigned int child = 2u * s.idx;
+        if (child < m.firstLeaf) {
+            const float4* p = m.nodes + 3 * child;
+            prefetchL1(p);
+            prefetchL1(p + 5);
+        } else {
+            const float4* p = m.tris + 3 * ((child - m.firstLeaf) * m.primsPerLeaf);
+            const unsigned int bytes = 2u * m.primsPerLeaf * 48u;
+            for (unsigned int o = 0; o < bytes; o += 128u) prefetchL1((const char*)p + o);
+            prefetchL1((const char*)p + bytes - 16u);
+        }
+    }
     const float leftHit = boxDist(mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), r, s.closest);
     const float rightHit = boxDist(mk3(b.z, b.w, c.x), mk3(c.y, c.z, c.w), r, s.closest);
     const bool traverseLeft = leftHit < s.closest;
@@ -61,6 +81,12 @@ __device__ __forceinline__ void travNodeStep(const MeshView& m, const RayPrep& r
 __device__ __forceinline__ bool travLeafStep(const MeshView& m, const RayPrep& r, float tMin, bool anyHit, TravState& s,
                                              unsigned int& triTests) {
     const unsigned int first = (s.idx - m.firstLeaf) * m.primsPerLeaf;
+    {   // the leaf's tiles are contiguous (N * 48 bytes): request all of its lines before the first test
+        const char* p = (const char*)(m.tris + 3 * first);
+        const unsigned int bytes = m.primsPerLeaf * 48u;
+        for (unsigned int o = 128u; o < bytes; o += 128u) prefetchL1(p + o);
+        prefetchL1(p + bytes - 16u);
+    }
     for (unsigned int i = 0; i < m.primsPerLeaf; i++) {
         // all 48 bytes of the tile are requested together (one round trip); unused slots are readable padding
         const float4 t0 = __ldg(m.tris + 3 * (first + i));
@@ -96,6 +122,7 @@ __device__ __forceinline__ bool travLeafStep(const MeshView& m, const RayPrep& r
 // retires / refills lanes and calls again.
 #define TRAV_NODE_QUORUM 16
 
+template <bool PREFETCH>
 __device__ __forceinline__ void travRun(const MeshView& m, const RayPrep& r, float tMin, bool anyHit, bool live, TravState& s,
                                         int& steps, int budget, int minActive, unsigned int& nodeVisits, unsigned int& triTests) {
     while (true) {
@@ -110,7 +137,7 @@ __device__ __forceinline__ void travRun(const MeshView& m, const RayPrep& r, flo
             if (__popc(nodeMask) < TRAV_NODE_QUORUM && leafMask != 0u) break;        // let the waiting lanes test their leaves
             if (__popc(nodeMask) + __popc(leafMask) < minActive) break;              // too few lanes left: let the caller refill
             if (atNode) {
-                travNodeStep(m, r, s);
+                travNodeStep<PREFETCH>(m, r, s);
                 nodeVisits++;
                 steps++;
                 work = s.idx != 0u && steps < budget;
