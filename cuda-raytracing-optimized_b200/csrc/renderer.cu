@@ -337,12 +337,15 @@ void crtRunMesh(RendererContext& c, int ns) {
             }
             for (auto& e : ev) cudaEventDestroy(e);
         } else {
+            // lane A (bulk) leaves one block per SM to lane B (express) so that both run at the same time
+            auto envInt = [](const char* name, int dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) : dflt; };
+            const int blocksB = lanes ? envInt("CRT_LANE_B_BLOCKS", c.numSMs) : 0; // tuning knobs (defaults are the measured best)
+            const int blocksA = c.traceBlocks - blocksB;
+            const int budgetB = envInt("CRT_LANE_B_BUDGET", mp.traceBudget);
             const long long key = ((long long)mp.samplesPerSlot << 24) ^ ((long long)slotsPerPixel << 8) ^ batch ^
                                   ((long long)c.counting << 60) ^ ((long long)c.maxDepth << 40) ^ ((long long)mp.streamBase << 48) ^
-                                  ((long long)mp.traceBudget << 12) ^ ((long long)mp.traceMinActive << 4) ^ ((long long)lanes << 59);
-            // lane A (bulk) leaves one block per SM to lane B (express) so that both run at the same time
-            const int blocksA = lanes ? c.traceBlocks - c.numSMs : c.traceBlocks;
-            const int blocksB = c.numSMs;
+                                  ((long long)mp.traceBudget << 12) ^ ((long long)mp.traceMinActive << 4) ^ ((long long)lanes << 59) ^
+                                  ((long long)blocksB << 30) ^ ((long long)budgetB << 20);
             MeshState& fast = c.mpFast;
             if (lanes) {
                 MeshControl* ctlB = fast.ctl;
@@ -350,6 +353,7 @@ void crtRunMesh(RendererContext& c, int ns) {
                 fast = mp; // same state arrays and frame parameters ...
                 fast.ctl = ctlB; // ... own control block and queues
                 fast.traceQ[0] = q[0]; fast.traceQ[1] = q[1]; fast.shadeQ[0] = q[2]; fast.shadeQ[1] = q[3];
+                fast.traceBudget = budgetB; // measured: 96 beats 48..1024 (a larger budget stretches every iteration of the lane to its longest ray)
                 CRT_CHECK(cudaMemsetAsync(fast.ctl, 0, sizeof(MeshControl), stream));
             }
             if (!c.graphExec || c.graphKey != key) {
