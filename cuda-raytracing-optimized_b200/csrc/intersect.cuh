@@ -6,8 +6,11 @@
 //   sphere               intersections.h:85-104 (both roots)
 //   dual-node traversal  kernels.cu:148-224     (near child first, tie -> left, bit-stack pop)
 // Layout differences (the device layout is ours):
-//   * nodes: the reference's bvh_node[] bytes, read as three 16-byte loads per
-//     internal node (children 2i and 2i+1 are adjacent = floats [12i,12i+12));
+//   * nodes: 96 bytes per internal node index i, holding the boxes of its children L = 2i and R = 2i+1 as six float4:
+//         [0] {Lmin.x, Lmax.x, Rmin.x, Rmax.x}   [1] {Lmax.x, Lmin.x, Rmax.x, Rmin.x}   [2],[3] the same for y   [4],[5] for z
+//     The slab test swaps t0/t1 when invD < 0 (intersections.h:30): that is a per-ray constant, so a ray picks per axis
+//     the copy whose {near, far} order suits its direction once, at ray set-up, and the inner loop has no selects. The
+//     first profile of the traversal loop was ALU-pipe bound (12 FSEL + 3 FSETP of every step were these swaps);
 //   * triangles: 48-byte tiles {v0, e1 = v1-v0, e2 = v2-v0} in three float4
 //     (the subtractions are the ones triangleHit does first; precomputing them
 //     does not change a bit), +inf in v0.x marks an unused leaf slot.
@@ -19,19 +22,19 @@
 
 #define RT_EPSILON 0.01f // kernels.cu:19
 
+struct MeshView {
+    const float4* __restrict__ nodes; // 6 float4 per internal node index (see travNodeStep / swizzleNodesKernel)
+    const float4* __restrict__ tris;  // 3 float4 per triangle slot
+    unsigned int firstLeaf;
+    unsigned int primsPerLeaf;
+    f3 boundsMin, boundsMax;
+};
+
 struct RayPrep {
     f3 o;    // origin
     f3 d;    // unit direction (ray.h:9)
     f3 inv;  // 1.0f / d  (IEEE)
 };
-
-__device__ __forceinline__ RayPrep prepRay(const f3& o, const f3& dirNormalised) {
-    RayPrep r;
-    r.o = o;
-    r.d = dirNormalised;
-    r.inv = mk3(1.0f / dirNormalised.x, 1.0f / dirNormalised.y, 1.0f / dirNormalised.z);
-    return r;
-}
 
 // One axis of the slab loop (intersections.h:27-36):
 //     t0 = (bmin - o) * invD; t1 = (bmax - o) * invD; if (invD < 0) swap(t0, t1);
@@ -102,76 +105,4 @@ __device__ __forceinline__ float sphereHitT(const f3& center, float radius, cons
         if (temp < tMax && temp > tMin) return temp;
     }
     return FLT_MAX;
-}
-
-struct MeshView {
-    const float4* __restrict__ nodes; // 3 float4 per internal node index (children pair)
-    const float4* __restrict__ tris;  // 3 float4 per triangle slot
-    unsigned int firstLeaf;
-    unsigned int primsPerLeaf;
-    f3 boundsMin, boundsMax;
-};
-
-struct TravCounters {
-    unsigned int nodeVisits; // internal (dual) node visits
-    unsigned int triTests;
-};
-
-// hitMesh (kernels.cu:296-323) + hitBvh (kernels.cu:154-224).
-// ANY = true is the reference's isShadow: return 0.0f on the first accepted triangle.
-// COUNT adds visit counters (used for the flop side of the roofline, never in timed runs).
-template <bool ANY, bool COUNT>
-__device__ __forceinline__ float traverseRefOrder(const MeshView& m, const RayPrep& r, float tMin, float tMax, unsigned int& triId,
-                                                  float& hitU, float& hitV, TravCounters* cnt) {
-    if (!boxHit(m.boundsMin, m.boundsMax, r, tMax)) return FLT_MAX;
-
-    unsigned int idx = 1;
-    float closest = tMax;
-    unsigned int bitStack = 1;
-    while (idx) {
-        if (idx < m.firstLeaf) {
-            const float4 a = __ldg(m.nodes + 3 * idx);
-            const float4 b = __ldg(m.nodes + 3 * idx + 1);
-            const float4 c = __ldg(m.nodes + 3 * idx + 2);
-            if (COUNT) cnt->nodeVisits++;
-            float leftHit = boxDist(mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), r, closest);
-            float rightHit = boxDist(mk3(b.z, b.w, c.x), mk3(c.y, c.z, c.w), r, closest);
-            bool traverseLeft = leftHit < closest;
-            bool traverseRight = rightHit < closest;
-            unsigned int swap = rightHit < leftHit ? 1u : 0u;
-            if (traverseLeft && traverseRight) {
-                idx = 2 * idx + swap;
-                bitStack = (bitStack << 1) + 1;
-            } else if (traverseLeft || traverseRight) {
-                idx = 2 * idx + swap;
-                bitStack = bitStack << 1;
-            } else {
-                int s = __ffs(bitStack) - 1;
-                bitStack = (bitStack >> s) ^ 1u;
-                idx = (idx >> s) ^ 1u;
-            }
-        } else {
-            unsigned int first = (idx - m.firstLeaf) * m.primsPerLeaf;
-            for (unsigned int i = 0; i < m.primsPerLeaf; i++) {
-                const float4 t0 = __ldg(m.tris + 3 * (first + i));
-                if (isinf(t0.x)) break;
-                const float4 t1 = __ldg(m.tris + 3 * (first + i) + 1);
-                const float4 t2 = __ldg(m.tris + 3 * (first + i) + 2);
-                if (COUNT) cnt->triTests++;
-                float u, v;
-                float hitT = triHit(mk3(t0.x, t0.y, t0.z), mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), r, tMin, closest, u, v);
-                if (hitT < closest) {
-                    if (ANY) return 0.0f;
-                    closest = hitT;
-                    triId = first + i;
-                    hitU = u;
-                    hitV = v;
-                }
-            }
-            int s = __ffs(bitStack) - 1;
-            bitStack = (bitStack >> s) ^ 1u;
-            idx = (idx >> s) ^ 1u;
-        }
-    }
-    return closest;
 }

@@ -117,135 +117,148 @@ __global__ void __launch_bounds__(WF_BLOCK) meshStartKernel(MeshState st, Camera
 }
 
 // ------------------------------------------------------------------- trace --
-#define TRACE_BUDGET 96      // default steps per ray per launch before it is parked
-#define TRACE_MIN_ACTIVE 20  // default: refill when fewer lanes than this still traverse
+#define TRACE_BUDGET 96        // default steps per ray per launch before it is parked
+#define TRACE_MIN_ACTIVE 20    // default: refill when fewer lanes than this hold a ray
+#define TRACE_BLOCKS_PER_SM 5  // register cap 48: occupancy is what hides the L1/L2 latency of the node fetches
 
 template <bool COUNT>
-__global__ void __launch_bounds__(WF_BLOCK) traceKernel(MeshState st, MeshView mesh, int cur) {
+__global__ void __launch_bounds__(WF_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(MeshState st, MeshView mesh, int cur) {
+    __shared__ RayCold coldAll[WF_BLOCK];
+    RayCold& c = coldAll[threadIdx.x];
     MeshControl* ctl = st.ctl;
     const unsigned int n = ctl->traceCount[cur];
     const unsigned int* __restrict__ queue = st.traceQ[cur];
     unsigned int* __restrict__ nextTrace = st.traceQ[cur ^ 1];
     unsigned int* __restrict__ shadeQ = st.shadeQ[cur];
     const unsigned int lane = laneId();
-    // Entries a warp takes per refill: 32 when the queue is long; when it is shorter than the grid (the tail of a frame)
-    // the rays are spread one per warp, so that no ray waits in lockstep for a longer one in the same warp.
+    // Rays a warp holds at a time: 32 when the queue is long; when it is shorter than the grid (the tail of a frame) the
+    // rays are spread over all warps, so that no ray waits in lockstep for a longer one in the same warp.
     const unsigned int totalWarps = gridDim.x * (WF_BLOCK / 32);
     const unsigned int take = min(32u, max(1u, (n + totalWarps - 1) / totalWarps));
+    const bool tail = take < 32u;
+    const unsigned int refillBelow = tail ? take : (unsigned int)st.traceMinActive;
 
     bool live = false;       // this lane holds a ray
     bool exhausted = false;  // the queue has no more entries for this warp
-    unsigned int entry = 0;
-    RayPrep r;
-    TravState s;
-    float tMax = 0.0f;
+    bool isShadow = false;
+    RayHot r;
+    TravHot s;
     int steps = 0;
     unsigned int nodeVisits = 0, triTests = 0;
-    r.o = r.d = r.inv = mk3(0.0f, 0.0f, 0.0f);
-    travInit(s, 0.0f);
-    s.idx = 0;
+    r.ox = r.oy = r.oz = r.ix = r.iy = r.iz = 0.0f;
+    r.offX = r.offY = r.offZ = 0u;
+    s.idx = 0u; s.bitStack = 0u; s.closest = 0.0f;
 
     while (true) {
-        // ---- refill idle lanes, one atomic per warp
-        if (!exhausted) {
-            const unsigned int idle = __ballot_sync(0xFFFFFFFFu, !live);
-            const unsigned int busy = 32u - __popc(idle);
-            if (idle != 0u && busy < take) {
-                const unsigned int count = min((unsigned int)__popc(idle), take - busy);
+        // Lanes that still traverse. Finished rays stay in their lanes until the warp runs low on work: retiring them one
+        // by one costs the whole warp a pass through the retire code per ray (measured: +25 % kernel time), so rays are
+        // retired -- and idle lanes refilled -- in batches.
+        bool working = live && s.idx != 0u && steps < st.traceBudget;
+        unsigned int workMask = __ballot_sync(0xFFFFFFFFu, working);
+        if (exhausted ? workMask == 0u : (unsigned int)__popc(workMask) < refillBelow) {
+            // ---- retire finished rays, park the ones that ran out of budget
+            const bool finished = live && s.idx == 0u;
+            const bool park = live && !finished && steps >= st.traceBudget;
+            const unsigned int entry = __float_as_uint(c.rec.w);
+            const unsigned int slot = entry & ENTRY_SLOT_MASK;
+            const bool toShade = finished && !isShadow;
+            if (finished) {
+                if (!isShadow) {
+                    // hitMesh returns `closest` (== t_max when nothing was hit) or FLT_MAX; hit() tests `< t_max` (kernels.cu:330)
+                    st.hit[slot] = make_float4(s.closest, c.rec.x, c.rec.y, c.rec.z);
+                } else {
+                    const float4 l = st.shL[slot];
+                    const bool unoccluded = !(s.closest < c.dir.w); // hit(...) false: p.color += p.lightContribution (kernels.cu:500-508)
+                    if (__float_as_uint(l.w) & SHADOW_FLAG_FINAL) {
+                        float4 col = st.shC[slot];
+                        if (unoccluded) { col.x += l.x; col.y += l.y; col.z += l.z; }
+                        accumulatePixel(st, slot % st.npix, col.x, col.y, col.z); // col += p.color (kernels.cu:558)
+                    } else if (unoccluded) {
+                        float4 col = st.pcol[slot];
+                        col.x += l.x; col.y += l.y; col.z += l.z;
+                        st.pcol[slot] = col;
+                    }
+                    st.pending[slot] = 0;
+                }
+                live = false;
+            }
+            if (park) {
+                if (isShadow) {
+                    st.travS[slot] = make_uint2(s.idx, s.bitStack);
+                } else {
+                    st.travE[slot] = make_uint2(s.idx, s.bitStack);
+                    st.hit[slot] = make_float4(s.closest, c.rec.x, c.rec.y, c.rec.z);
+                }
+                s.idx = 0u;
+                live = false;
+            }
+            // queue appends and ray statistics: one atomic per warp per counter (ballot + popc)
+            const unsigned int mShade = __ballot_sync(0xFFFFFFFFu, toShade);
+            const unsigned int mPark = __ballot_sync(0xFFFFFFFFu, park);
+            const unsigned int mShadowDone = __ballot_sync(0xFFFFFFFFu, finished && isShadow);
+            unsigned int baseShade = 0, basePark = 0;
+            if (lane == 0) {
+                if (mShade) { baseShade = atomicAdd(&ctl->shadeCount[cur], __popc(mShade)); atomicAdd(&ctl->raysExtend, (unsigned long long)__popc(mShade)); }
+                if (mPark) { basePark = atomicAdd(&ctl->traceCount[cur ^ 1], __popc(mPark)); atomicAdd(&ctl->resumes, (unsigned long long)__popc(mPark)); }
+                if (mShadowDone) atomicAdd(&ctl->raysShadow, (unsigned long long)__popc(mShadowDone));
+            }
+            baseShade = __shfl_sync(0xFFFFFFFFu, baseShade, 0);
+            basePark = __shfl_sync(0xFFFFFFFFu, basePark, 0);
+            const unsigned int below = (1u << lane) - 1u;
+            if (toShade) shadeQ[baseShade + __popc(mShade & below)] = slot;
+            if (park) nextTrace[basePark + __popc(mPark & below)] = entry | ENTRY_RESUME;
+
+            // ---- refill idle lanes, one atomic per warp
+            if (!exhausted) {
+                const unsigned int idle = ~workMask; // every lane that does not traverse has just been retired (or was empty)
+                const unsigned int count = tail ? min((unsigned int)__popc(idle), take - (unsigned int)__popc(workMask)) : (unsigned int)__popc(idle);
                 unsigned int base = 0;
                 if (lane == 0) base = atomicAdd(&ctl->traceCursor, count);
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
                 if (base + count >= n) exhausted = true; // warp-uniform: the tail of the queue has been handed out
-                const unsigned int rank = __popc(idle & ((1u << lane) - 1u));
+                const unsigned int rank = __popc(idle & below);
                 const unsigned int i = base + rank;
                 if (!live && rank < count && i < n) {
-                    entry = queue[i];
-                    const unsigned int slot = entry & ENTRY_SLOT_MASK;
-                    const bool isShadow = (entry & ENTRY_SHADOW) != 0u;
-                    const float4 ro = isShadow ? st.shO[slot] : st.rayO[slot];
-                    const float4 rd = isShadow ? st.shD[slot] : st.rayD[slot];
-                    r = prepRay(xyz(ro), unit(xyz(rd))); // hit(): ray(p.origin, dir) normalises again (kernels.cu:326)
-                    tMax = isShadow ? rd.w : FLT_MAX;
+                    const unsigned int e = queue[i];
+                    const unsigned int sl = e & ENTRY_SLOT_MASK;
+                    isShadow = (e & ENTRY_SHADOW) != 0u;
+                    const float4 ro = isShadow ? st.shO[sl] : st.rayO[sl];
+                    const float4 rd = isShadow ? st.shD[sl] : st.rayD[sl];
+                    const float tMax = isShadow ? rd.w : FLT_MAX;
+                    prepRay(r, c, xyz(ro), unit(xyz(rd)), tMax); // hit(): ray(p.origin, dir) normalises again (kernels.cu:326)
                     steps = 0;
                     live = true;
-                    if (entry & ENTRY_RESUME) {
-                        const uint2 t = isShadow ? st.travS[slot] : st.travE[slot];
+                    c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), __uint_as_float(e));
+                    if (e & ENTRY_RESUME) {
+                        const uint2 t = isShadow ? st.travS[sl] : st.travE[sl];
                         s.idx = t.x;
                         s.bitStack = t.y;
-                        if (isShadow) {
-                            s.closest = tMax;
-                        } else {
-                            const float4 h = st.hit[slot];
-                            s.closest = h.x; s.u = h.y; s.v = h.z; s.triId = __float_as_uint(h.w);
+                        s.closest = tMax;
+                        if (!isShadow) {
+                            const float4 h = st.hit[sl];
+                            s.closest = h.x;
+                            c.rec = make_float4(h.y, h.z, h.w, __uint_as_float(e));
                         }
                     } else {
-                        travInit(s, tMax);
-                        if (!boxHit(mesh.boundsMin, mesh.boundsMax, r, tMax)) { // hitMesh: scene bounds first (kernels.cu:297)
-                            s.idx = 0;
+                        s.idx = 1u; s.bitStack = 1u; s.closest = tMax;
+                        if (!rayHitsBounds(mesh, r, tMax)) { // hitMesh: scene bounds first (kernels.cu:297)
+                            s.idx = 0u;
                             s.closest = FLT_MAX;
                         }
                     }
                 }
             }
+            if (!__any_sync(0xFFFFFFFFu, live)) break;
+            working = live && s.idx != 0u;
+            workMask = __ballot_sync(0xFFFFFFFFu, working);
+            if (workMask == 0u) continue; // e.g. every new ray missed the scene bounds: retire them
         }
-        if (!__any_sync(0xFFFFFFFFu, live)) break;
 
-        // ---- traverse
-        const bool isShadow = (entry & ENTRY_SHADOW) != 0u;
-        if (take < 32u) // short queue: latency-bound launch, spend instructions on prefetching
-            travRun<true>(mesh, r, RT_EPSILON, isShadow, live, s, steps, st.traceBudget, 1, nodeVisits, triTests);
+        // ---- one scheduling round: node steps while enough lanes stand on nodes, then the leaves
+        if (tail) // short queue: latency-bound launch, spend instructions on prefetching
+            travRound<true>(mesh, r, c, RT_EPSILON, isShadow, working, s, steps, 1, nodeVisits, triTests);
         else
-            travRun<false>(mesh, r, RT_EPSILON, isShadow, live, s, steps, st.traceBudget, exhausted ? 1 : st.traceMinActive, nodeVisits, triTests);
-
-        // ---- retire finished rays, park the ones that ran out of budget
-        const unsigned int slot = entry & ENTRY_SLOT_MASK;
-        const bool finished = live && s.idx == 0u;
-        const bool park = live && !finished && steps >= st.traceBudget;
-        const bool toShade = finished && !isShadow;
-        if (finished) {
-            if (!isShadow) {
-                // hitMesh returns `closest` (== t_max when nothing was hit) or FLT_MAX; hit() tests `< t_max` (kernels.cu:330)
-                st.hit[slot] = make_float4(s.closest, s.u, s.v, __uint_as_float(s.triId));
-            } else {
-                const float4 l = st.shL[slot];
-                const bool unoccluded = !(s.closest < tMax); // hit(...) false: p.color += p.lightContribution (kernels.cu:500-508)
-                if (__float_as_uint(l.w) & SHADOW_FLAG_FINAL) {
-                    float4 c = st.shC[slot];
-                    if (unoccluded) { c.x += l.x; c.y += l.y; c.z += l.z; }
-                    accumulatePixel(st, slot % st.npix, c.x, c.y, c.z); // col += p.color (kernels.cu:558)
-                } else if (unoccluded) {
-                    float4 c = st.pcol[slot];
-                    c.x += l.x; c.y += l.y; c.z += l.z;
-                    st.pcol[slot] = c;
-                }
-                st.pending[slot] = 0;
-            }
-            live = false;
-        }
-        if (park) {
-            if (isShadow) {
-                st.travS[slot] = make_uint2(s.idx, s.bitStack);
-            } else {
-                st.travE[slot] = make_uint2(s.idx, s.bitStack);
-                st.hit[slot] = make_float4(s.closest, s.u, s.v, __uint_as_float(s.triId));
-            }
-            live = false;
-        }
-        // queue appends and ray statistics: one atomic per warp per counter (ballot + popc)
-        const unsigned int mShade = __ballot_sync(0xFFFFFFFFu, toShade);
-        const unsigned int mPark = __ballot_sync(0xFFFFFFFFu, park);
-        const unsigned int mShadowDone = __ballot_sync(0xFFFFFFFFu, finished && isShadow);
-        unsigned int baseShade = 0, basePark = 0;
-        if (lane == 0) {
-            if (mShade) { baseShade = atomicAdd(&ctl->shadeCount[cur], __popc(mShade)); atomicAdd(&ctl->raysExtend, (unsigned long long)__popc(mShade)); }
-            if (mPark) { basePark = atomicAdd(&ctl->traceCount[cur ^ 1], __popc(mPark)); atomicAdd(&ctl->resumes, (unsigned long long)__popc(mPark)); }
-            if (mShadowDone) atomicAdd(&ctl->raysShadow, (unsigned long long)__popc(mShadowDone));
-        }
-        baseShade = __shfl_sync(0xFFFFFFFFu, baseShade, 0);
-        basePark = __shfl_sync(0xFFFFFFFFu, basePark, 0);
-        const unsigned int below = (1u << lane) - 1u;
-        if (toShade) shadeQ[baseShade + __popc(mShade & below)] = slot;
-        if (park) nextTrace[basePark + __popc(mPark & below)] = entry | ENTRY_RESUME;
+            travRound<false>(mesh, r, c, RT_EPSILON, isShadow, working, s, steps, max(1, min(TRACE_NODE_QUORUM, __popc(workMask) >> 1)), nodeVisits, triTests);
     }
 
     if (COUNT) {

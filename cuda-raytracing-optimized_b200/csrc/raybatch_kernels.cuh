@@ -10,57 +10,56 @@
 #include "traverse.cuh"
 
 template <bool COUNT>
-__global__ void __launch_bounds__(256, 4) intersectBatchKernel(MeshView mesh, const float4* __restrict__ triShade,
+__global__ void __launch_bounds__(256, 5) intersectBatchKernel(MeshView mesh, const float4* __restrict__ triShade,
                                                             const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                             unsigned long long n, float4* __restrict__ outHit, int* __restrict__ outMesh,
                                                             unsigned long long* cursor, unsigned long long* counts) {
+    __shared__ RayCold coldAll[256];
+    __shared__ float tMinAll[256];
+    RayCold& c = coldAll[threadIdx.x];
     const unsigned int lane = threadIdx.x & 31u;
     bool live = false, exhausted = false;
     unsigned long long index = 0;
-    RayPrep r;
-    TravState s;
-    float tMin = 0.0f, tMax = 0.0f;
+    RayHot r;
+    TravHot s;
     int steps = 0;
     unsigned int nodeVisits = 0, triTests = 0;
-    r.o = r.d = r.inv = mk3(0.0f, 0.0f, 0.0f);
-    travInit(s, 0.0f);
-    s.idx = 0;
+    r.ox = r.oy = r.oz = r.ix = r.iy = r.iz = 0.0f;
+    r.offX = r.offY = r.offZ = 0u;
+    s.idx = 0u; s.bitStack = 0u; s.closest = 0.0f;
     while (true) {
-        if (!exhausted) { // refill idle lanes, one atomic per warp
-            const bool want = !live;
-            const unsigned int mask = __ballot_sync(0xFFFFFFFFu, want);
-            if (mask) {
-                unsigned long long base = 0;
-                const unsigned int leader = __ffs(mask) - 1;
-                if (lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(mask));
-                base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                if (base + __popc(mask) >= n) exhausted = true;
-                const unsigned long long i = base + __popc(mask & ((1u << lane) - 1u));
-                if (want && i < n) {
-                    index = i;
-                    const float4 ro = __ldg(rayO + i);
-                    const float4 rd = __ldg(rayD + i);
-                    r = prepRay(xyz(ro), unit(xyz(rd)));
-                    tMin = ro.w;
-                    tMax = rd.w;
-                    steps = 0;
-                    live = true;
-                    travInit(s, tMax);
-                    if (!boxHit(mesh.boundsMin, mesh.boundsMax, r, tMax)) {
-                        s.idx = 0;
-                        s.closest = FLT_MAX;
-                    }
+        unsigned int liveMask = __ballot_sync(0xFFFFFFFFu, live);
+        if (!exhausted && __popc(liveMask) < 20) { // refill idle lanes, one atomic per warp
+            const unsigned int mask = ~liveMask;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(cursor, (unsigned long long)__popc(mask));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (base + __popc(mask) >= n) exhausted = true;
+            const unsigned long long i = base + __popc(mask & ((1u << lane) - 1u));
+            if (!live && i < n) {
+                index = i;
+                const float4 ro = __ldg(rayO + i);
+                const float4 rd = __ldg(rayD + i);
+                prepRay(r, c, xyz(ro), unit(xyz(rd)), rd.w);
+                tMinAll[threadIdx.x] = ro.w;
+                c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), 0.0f);
+                live = true;
+                s.idx = 1u; s.bitStack = 1u; s.closest = rd.w;
+                if (!rayHitsBounds(mesh, r, rd.w)) {
+                    s.idx = 0u;
+                    s.closest = FLT_MAX;
                 }
             }
+            liveMask = __ballot_sync(0xFFFFFFFFu, live);
         }
-        if (!__any_sync(0xFFFFFFFFu, live)) break;
-        travRun<false>(mesh, r, tMin, false, live, s, steps, 0x7FFFFFFF, exhausted ? 1 : 20, nodeVisits, triTests);
+        if (liveMask == 0u) break;
+        travRound<false>(mesh, r, c, tMinAll[threadIdx.x], false, live, s, steps, max(1, min(TRACE_NODE_QUORUM, __popc(liveMask) >> 1)), nodeVisits, triTests);
         if (live && s.idx == 0u) {
             float t = s.closest;
-            unsigned int triId = s.triId;
-            float u = s.u, v = s.v;
+            unsigned int triId = __float_as_uint(c.rec.z);
+            float u = c.rec.x, v = c.rec.y;
             int meshID = -1;
-            if (t < tMax) {
+            if (t < c.dir.w) {
                 meshID = __float_as_int(__ldg(triShade + 3 * triId).w);
             } else {
                 t = FLT_MAX;

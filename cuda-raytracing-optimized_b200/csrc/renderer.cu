@@ -183,15 +183,23 @@ extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb,
     CRT_CHECK(cudaFree(staging));
     c.numTriSlots = numSlots;
 
-    // nodes: the caller's bytes, padded so the last 48-byte child-pair load stays in bounds
+    // nodes: upload the caller's 24-byte records, re-tile into 96-byte child-pair records on the device (intersect.cuh)
     const size_t nodeBytes = (size_t)m->numBvhNodes * sizeof(bvh_node);
-    CRT_CHECK(cudaMalloc((void**)&c.nodes, nodeBytes + 64));
-    CRT_CHECK(cudaMemset(c.nodes, 0, nodeBytes + 64));
-    CRT_CHECK(cudaMemcpy(c.nodes, m->bvh, nodeBytes, cudaMemcpyHostToDevice));
+    const unsigned int firstLeaf = (unsigned int)(m->numBvhNodes / 2); // kernels.cu:614
+    float* nodeStaging = nullptr;
+    CRT_CHECK(cudaMalloc((void**)&nodeStaging, nodeBytes + 64));
+    CRT_CHECK(cudaMemcpy(nodeStaging, m->bvh, nodeBytes, cudaMemcpyHostToDevice));
+    c.nodes = devAlloc<float4>(6 * (size_t)(firstLeaf ? firstLeaf : 1) + 8);
+    if (firstLeaf) {
+        swizzleNodesKernel<<<(firstLeaf + 255) / 256, 256>>>(nodeStaging, firstLeaf, c.nodes);
+        CRT_CHECK(cudaGetLastError());
+    }
+    CRT_CHECK(cudaDeviceSynchronize());
+    CRT_CHECK(cudaFree(nodeStaging));
 
     c.mesh.nodes = c.nodes;
     c.mesh.tris = c.triGeom;
-    c.mesh.firstLeaf = (unsigned int)(m->numBvhNodes / 2); // kernels.cu:614
+    c.mesh.firstLeaf = firstLeaf;
     c.mesh.primsPerLeaf = (unsigned int)sc.numPrimitivesPerLeaf;
     c.mesh.boundsMin = toF3(m->bounds.min);
     c.mesh.boundsMax = toF3(m->bounds.max);

@@ -5,7 +5,8 @@
 // of a 32-bit trail, and a pop jumps straight to the pending sibling (pop_bitstack, kernels.cu:148-152).  Because the
 // tree is an implicit complete heap and the trail is a bit-stack, the WHOLE traversal state of a ray is
 //     { idx, bitStack, closest, triId, u, v }                                  (24 bytes)
-// so a ray can stop after a bounded number of steps and continue in a later launch with no stack to spill.  The first
+// (+ the origin and direction it was set up with), so a ray can stop after a bounded number of steps and continue in a
+// later launch with no stack to spill.  The first
 // ncu capture (profiles/r01/a_extend_ncu_summary.txt) showed why that matters: every launch of the one-shot walk waited
 // for a single straggler ray (~1000 steps) with 5.8 of 32 lanes active.
 //
@@ -16,24 +17,47 @@
 
 #include "intersect.cuh"
 
-struct TravState {
-    unsigned int idx;       // current node (0 = traversal finished)
-    unsigned int bitStack;  // trail of pending siblings, sentinel bit on top
-    float closest;          // current t_max
-    unsigned int triId;
-    float u, v;
+#define TRACE_NODE_QUORUM 16 // node steps run while this many lanes (or half of the rays the warp holds) stand on nodes
+
+// A ray while it is being traversed. The fields the node loop touches every step stay in registers (RayHot, TravHot);
+// the rest -- direction (needed by the triangle test only), the hit record and the queue entry -- lives in shared memory,
+// one RayCold per thread: the second profile of the leaner node step (profiles/r01/c_trace_ncu_summary.txt) was bound by
+// L1/L2 latency at 36 % occupancy (64 registers), so registers are what buys more resident warps.
+struct RayHot {
+    float ox, oy, oz;                 // origin
+    float ix, iy, iz;                 // 1.0f / direction (IEEE), direction normalised by the ray constructor (ray.h:9)
+    unsigned int offX, offY, offZ;    // byte offset, inside a 96-byte node record, of the per-axis copy this ray reads
 };
 
-__device__ __forceinline__ void travInit(TravState& s, float tMax) {
-    s.idx = 1;
-    s.bitStack = 1;
-    s.closest = tMax;
-    s.triId = 0xFFFFFFFFu;
-    s.u = 0.0f;
-    s.v = 0.0f;
+struct TravHot {
+    unsigned int idx;       // current node (0 = traversal finished / lane idle)
+    unsigned int bitStack;  // trail of pending siblings, sentinel bit on top
+    float closest;          // current t_max
+};
+
+struct RayCold {
+    float4 dir;  // {unit direction, original t_max}
+    float4 rec;  // {u, v, triId bits, user word (queue entry / ray index)}
+};
+
+__device__ __forceinline__ void prepRay(RayHot& r, RayCold& c, const f3& o, const f3& dirNormalised, float tMax) {
+    r.ox = o.x; r.oy = o.y; r.oz = o.z;
+    r.ix = 1.0f / dirNormalised.x; r.iy = 1.0f / dirNormalised.y; r.iz = 1.0f / dirNormalised.z;
+    r.offX = r.ix < 0.0f ? 16u : 0u; // `if (invD < 0) swap(t0, t1)` (intersections.h:30), decided once per ray
+    r.offY = r.iy < 0.0f ? 48u : 32u;
+    r.offZ = r.iz < 0.0f ? 80u : 64u;
+    c.dir = make_float4(dirNormalised.x, dirNormalised.y, dirNormalised.z, tMax);
 }
 
-__device__ __forceinline__ void travPop(TravState& s) {
+// hit_bbox (intersections.h:7-23) against the scene bounds, hitMesh's early out (kernels.cu:297)
+__device__ __forceinline__ bool rayHitsBounds(const MeshView& m, const RayHot& r, float tMax) {
+    RayPrep p;
+    p.o = mk3(r.ox, r.oy, r.oz);
+    p.inv = mk3(r.ix, r.iy, r.iz);
+    return boxHit(m.boundsMin, m.boundsMax, p, tMax);
+}
+
+__device__ __forceinline__ void travPop(TravHot& s) {
     const int m = __ffs(s.bitStack) - 1;
     s.bitStack = (s.bitStack >> m) ^ 1u;
     s.idx = (s.idx >> m) ^ 1u;
@@ -41,22 +65,37 @@ __device__ __forceinline__ void travPop(TravState& s) {
 
 __device__ __forceinline__ void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// One internal-node step (kernels.cu:163-197).
-// PREFETCH: whichever child is entered next, its record lies in the 96 bytes that start at float4 index 6*idx (children
-// 2*idx and 2*idx+1 are adjacent), or -- on the last internal level -- its triangles lie in the 2*N tiles that start at
-// leaf 2*idx - firstLeaf. Requesting those lines into L1 now overlaps the next step's memory latency with this step's
-// slab tests. Used when a launch has too few rays to hide latency with other warps (the tail of a frame).
+__device__ __forceinline__ float4 ldNode(const MeshView& m, unsigned int byteOffset) {
+    return __ldg((const float4*)((const char*)m.nodes + byteOffset));
+}
+
+// One internal-node step (kernels.cu:163-197): both children's slab tests (hit_bbox_dist, intersections.h:25-41), then
+// descend to the nearer child / remember the other / pop.
+//
+// Node layout (intersect.cuh): the ray reads, per axis, the copy {Lnear, Lfar, Rnear, Rfar} for its direction sign, so
+// t0 = (near - o) * invD and t1 = (far - o) * invD need no swap. hit_bbox_dist returns FLT_MAX on a miss and its t_min
+// otherwise, and the caller compares that with `closest`; with tMax = min(closest, far...) folded in:
+//     traverse  <=>  !(tMax < tMin) && tMin < closest  <=>  tMin <= tMax && tMin < closest
+//     swap (rightHit < leftHit) matters only when a child is entered: both -> tMinR < tMinL; only right -> 1; only left -> 0.
+// fmaxf / fminf drop a NaN operand (0 * inf on an axis the ray is parallel to) exactly like the reference's
+// `t0 > t_min ? t0 : t_min`, and their result does not depend on the order of the operands.
+//
+// PREFETCH: whichever child is entered next, its record lies in the 192 bytes that start at byte 192*idx (children 2*idx
+// and 2*idx+1 are adjacent), or -- on the last internal level -- its triangles lie in the 2*N tiles that start at leaf
+// 2*idx - firstLeaf. Requesting those lines into L1 now overlaps the next step's memory latency with this step's slab
+// tests. Used when a launch has too few rays to hide latency with other warps (the tail of a frame).
 template <bool PREFETCH>
-__device__ __forceinline__ void travNodeStep(const MeshView& m, const RayPrep& r, TravState& s) {
-    const float4 a = __ldg(m.nodes + 3 * s.idx);
-    const float4 b = __ldg(m.nodes + 3 * s.idx + 1);
-    const float4 c = __ldg(m.nodes + 3 * s.idx + 2);
+__device__ __forceinline__ void travNodeStep(const MeshView& m, const RayHot& r, TravHot& s) {
+    const unsigned int at = 96u * s.idx;
+    const float4 qx = ldNode(m, at + r.offX);
+    const float4 qy = ldNode(m, at + r.offY);
+    const float4 qz = ldNode(m, at + r.offZ);
     if (PREFETCH) {
         const unsigned int child = 2u * s.idx;
         if (child < m.firstLeaf) {
-            const float4* p = m.nodes + 3 * child;
+            const char* p = (const char*)m.nodes + 96u * child;
             prefetchL1(p);
-            prefetchL1(p + 5);
+            prefetchL1(p + 128);
         } else {
             const float4* p = m.tris + 3 * ((child - m.firstLeaf) * m.primsPerLeaf);
             const unsigned int bytes = 2u * m.primsPerLeaf * 48u;
@@ -64,21 +103,27 @@ __device__ __forceinline__ void travNodeStep(const MeshView& m, const RayPrep& r
             prefetchL1((const char*)p + bytes - 16u);
         }
     }
-    const float leftHit = boxDist(mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), r, s.closest);
-    const float rightHit = boxDist(mk3(b.z, b.w, c.x), mk3(c.y, c.z, c.w), r, s.closest);
-    const bool traverseLeft = leftHit < s.closest;
-    const bool traverseRight = rightHit < s.closest;
-    const unsigned int swap = rightHit < leftHit ? 1u : 0u;
+    const float2 xl = slabPair(qx.x, qx.y, -r.ox, r.ix), xr = slabPair(qx.z, qx.w, -r.ox, r.ix);
+    const float2 yl = slabPair(qy.x, qy.y, -r.oy, r.iy), yr = slabPair(qy.z, qy.w, -r.oy, r.iy);
+    const float2 zl = slabPair(qz.x, qz.y, -r.oz, r.iz), zr = slabPair(qz.z, qz.w, -r.oz, r.iz);
+    const float tMinL = fmaxf(fmaxf(xl.x, yl.x), fmaxf(zl.x, 0.001f));
+    const float tMinR = fmaxf(fmaxf(xr.x, yr.x), fmaxf(zr.x, 0.001f));
+    const float tMaxL = fminf(fminf(xl.y, yl.y), fminf(zl.y, s.closest));
+    const float tMaxR = fminf(fminf(xr.y, yr.y), fminf(zr.y, s.closest));
+    const bool traverseLeft = tMinL <= tMaxL && tMinL < s.closest;
+    const bool traverseRight = tMinR <= tMaxR && tMinR < s.closest;
     if (traverseLeft || traverseRight) {
-        s.idx = 2 * s.idx + swap;
+        const bool swap = traverseRight && (!traverseLeft || tMinR < tMinL);
+        s.idx = 2u * s.idx + (swap ? 1u : 0u);
         s.bitStack = (s.bitStack << 1) + ((traverseLeft && traverseRight) ? 1u : 0u);
     } else {
         travPop(s);
     }
 }
 
-// One leaf visit (kernels.cu:198-217). Returns true when an any-hit ray is finished (occluded).
-__device__ __forceinline__ bool travLeafStep(const MeshView& m, const RayPrep& r, float tMin, bool anyHit, TravState& s,
+// One leaf visit (kernels.cu:198-217). An any-hit ray that finds a triangle is finished: closest = 0.0f is what the
+// reference returns (kernels.cu:207).
+__device__ __forceinline__ void travLeafStep(const MeshView& m, const RayHot& r, RayCold& c, float tMin, bool anyHit, TravHot& s,
                                              unsigned int& triTests) {
     const unsigned int first = (s.idx - m.firstLeaf) * m.primsPerLeaf;
     {   // the leaf's tiles are contiguous (N * 48 bytes): request all of its lines before the first test
@@ -87,6 +132,9 @@ __device__ __forceinline__ bool travLeafStep(const MeshView& m, const RayPrep& r
         for (unsigned int o = 128u; o < bytes; o += 128u) prefetchL1(p + o);
         prefetchL1(p + bytes - 16u);
     }
+    RayPrep rp;
+    rp.o = mk3(r.ox, r.oy, r.oz);
+    rp.d = xyz(c.dir);
     for (unsigned int i = 0; i < m.primsPerLeaf; i++) {
         // all 48 bytes of the tile are requested together (one round trip); unused slots are readable padding
         const float4 t0 = __ldg(m.tris + 3 * (first + i));
@@ -95,58 +143,43 @@ __device__ __forceinline__ bool travLeafStep(const MeshView& m, const RayPrep& r
         if (isinf(t0.x)) break;
         triTests++;
         float u, v;
-        const float hitT = triHit(mk3(t0.x, t0.y, t0.z), mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), r, tMin, s.closest, u, v);
+        const float hitT = triHit(mk3(t0.x, t0.y, t0.z), mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), rp, tMin, s.closest, u, v);
         if (hitT < s.closest) {
             if (anyHit) {
-                s.closest = 0.0f; // the reference returns 0.0f here (kernels.cu:207)
+                s.closest = 0.0f;
                 s.idx = 0;
-                return true;
+                return;
             }
             s.closest = hitT;
-            s.triId = first + i;
-            s.u = u;
-            s.v = v;
+            c.rec.x = u;
+            c.rec.y = v;
+            c.rec.z = __uint_as_float(first + i);
         }
     }
     travPop(s);
-    return false;
 }
 
-// Run one lane's traversal for at most `budget` steps (a node step costs 1, a leaf visit 2); `steps` accumulates.
-// Lanes of a warp call this together. Scheduling inside the warp (it does not change any lane's own sequence of steps):
-//   * node steps are issued while at least TRAV_NODE_QUORUM lanes stand on internal nodes; lanes that already reached a
-//     leaf wait for that long and no longer -- waiting for ALL lanes to reach a leaf (plain while-while) left 8 of 32
-//     lanes active in the node loop (profiles/r01/b_trace_ncu_summary.txt), a quorum of 16 doubles that in simulation;
-//   * then the leaves are processed for every lane that stands on one.
-// Returns when fewer than `minActive` lanes of the warp still have work (finished, out of budget or idle): the caller
-// retires / refills lanes and calls again.
-#define TRAV_NODE_QUORUM 16
-
+// One scheduling round of a warp (all 32 lanes call it together; it does not change any lane's own sequence of steps):
+//   * node steps are issued while at least `quorum` lanes stand on internal nodes; lanes that already reached a leaf wait
+//     for that long and no longer -- waiting for ALL lanes to reach a leaf (plain while-while, Aila & Laine 2009) left 8
+//     of 32 lanes active in the node loop (profiles/r01/b_trace_ncu_summary.txt); oracle/sched_sim.cpp replays logged
+//     traversals through this policy and its alternatives;
+//   * then every lane that stands on a leaf tests its triangles.
+// `steps` counts node steps + 2 per leaf visit, for the caller's parking budget; lanes with `on` == false sit the round out.
 template <bool PREFETCH>
-__device__ __forceinline__ void travRun(const MeshView& m, const RayPrep& r, float tMin, bool anyHit, bool live, TravState& s,
-                                        int& steps, int budget, int minActive, unsigned int& nodeVisits, unsigned int& triTests) {
+__device__ __forceinline__ void travRound(const MeshView& m, const RayHot& r, RayCold& c, float tMin, bool anyHit, bool on, TravHot& s,
+                                          int& steps, int quorum, unsigned int& nodeVisits, unsigned int& triTests) {
     while (true) {
-        bool work = live && s.idx != 0u && steps < budget;
-        if (__popc(__ballot_sync(0xFFFFFFFFu, work)) < minActive) break;
-        // node phase
-        while (true) {
-            const bool atNode = work && s.idx < m.firstLeaf;
-            const unsigned int nodeMask = __ballot_sync(0xFFFFFFFFu, atNode);
-            if (nodeMask == 0u) break;
-            const unsigned int leafMask = __ballot_sync(0xFFFFFFFFu, work && s.idx >= m.firstLeaf);
-            if (__popc(nodeMask) < TRAV_NODE_QUORUM && leafMask != 0u) break;        // let the waiting lanes test their leaves
-            if (__popc(nodeMask) + __popc(leafMask) < minActive) break;              // too few lanes left: let the caller refill
-            if (atNode) {
-                travNodeStep<PREFETCH>(m, r, s);
-                nodeVisits++;
-                steps++;
-                work = s.idx != 0u && steps < budget;
-            }
+        const bool atNode = on && (s.idx - 1u) < (m.firstLeaf - 1u); // idx != 0 && idx < firstLeaf
+        if (__popc(__ballot_sync(0xFFFFFFFFu, atNode)) < quorum) break;
+        if (atNode) {
+            travNodeStep<PREFETCH>(m, r, s);
+            nodeVisits++;
+            steps++;
         }
-        // leaf phase
-        if (work && s.idx >= m.firstLeaf) {
-            travLeafStep(m, r, tMin, anyHit, s, triTests);
-            steps += 2;
-        }
+    }
+    if (on && s.idx >= m.firstLeaf) {
+        travLeafStep(m, r, c, tMin, anyHit, s, triTests);
+        steps += 2;
     }
 }

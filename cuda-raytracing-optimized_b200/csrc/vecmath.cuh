@@ -51,3 +51,22 @@ __device__ __forceinline__ f3 subPinned(const f3& a, const f3& b) {
 }
 // a*p + b*q with the second product rounded on its own (the reference's compiled form)
 __device__ __forceinline__ float mad2(float a, float p, float b, float q) { return __fmaf_rn(a, p, __fmul_rn(b, q)); }
+
+// {(a - o) * inv, (b - o) * inv} with both operations IEEE round-to-nearest (the slab test's `(box - origin) * invD`,
+// intersections.h:28-29): sm_100's packed FADD2 / FMUL2 do the two lanes in one issue slot each. `negO` is -o: a + (-o)
+// and a - o are the same IEEE operation.
+__device__ __forceinline__ float2 slabPair(float a, float b, float negO, float inv) {
+    float2 r;
+    asm("{\n\t"
+        ".reg .b64 p, q, s;\n\t"
+        "mov.b64 p, {%2, %3};\n\t"
+        "mov.b64 q, {%4, %4};\n\t"
+        "mov.b64 s, {%5, %5};\n\t"
+        "add.rn.f32x2 p, p, q;\n\t"
+        "mul.rn.f32x2 p, p, s;\n\t"
+        "mov.b64 {%0, %1}, p;\n\t"
+        "}"
+        : "=f"(r.x), "=f"(r.y)
+        : "f"(a), "f"(b), "f"(negO), "f"(inv));
+    return r;
+}

@@ -199,6 +199,15 @@ inline void pop_bitstack(uint32_t& bitStack, int& idx) { // kernels.cu:148-152
     idx = (idx >> m) ^ 1;
 }
 
+#ifdef ORACLE_STEPLOG
+// Design aid (oracle/sched_sim.py): the sequence of steps every traversal takes -- 0 = dual-node step, 1+k = leaf visit
+// with k triangle tests, 255 = end of ray (254 = end of an any-hit ray). Single-threaded runs only.
+std::vector<uint8_t>* g_stepLog = nullptr;
+#define STEPLOG(x) do { if (g_stepLog) g_stepLog->push_back((uint8_t)(x)); } while (0)
+#else
+#define STEPLOG(x) do { } while (0)
+#endif
+
 float hitBvh(const Ray& r, const Ctx& c, float t_min, float t_max, TriHit& rec, bool isShadow, Counters* cnt) { // kernels.cu:154-224
     int idx = 1;
     float closest = t_max;
@@ -209,6 +218,7 @@ float hitBvh(const Ray& r, const Ctx& c, float t_min, float t_max, TriHit& rec, 
             const bvh_node& left = c.bvh[idx2];
             const bvh_node& right = c.bvh[idx2 + 1];
             if (cnt) cnt->nodeVisits++;
+            STEPLOG(0);
             float leftHit = hit_bbox_dist(v3(left.a), v3(left.b), r, closest);
             bool traverseLeft = leftHit < closest;
             float rightHit = hit_bbox_dist(v3(right.a), v3(right.b), r, closest);
@@ -225,6 +235,13 @@ float hitBvh(const Ray& r, const Ctx& c, float t_min, float t_max, TriHit& rec, 
             }
         } else {
             int first = (idx - c.firstLeafIdx) * c.numPrimitivesPerLeaf;
+#ifdef ORACLE_STEPLOG
+            if (g_stepLog) {
+                uint32_t k = 0;
+                while (k < c.numPrimitivesPerLeaf && !std::isinf(c.tris[first + k].v[0].e[0])) k++;
+                STEPLOG(1 + k);
+            }
+#endif
             for (uint32_t i = 0; i < c.numPrimitivesPerLeaf; i++) {
                 const triangle& tri = c.tris[first + i];
                 if (std::isinf(tri.v[0].e[0])) break;
@@ -232,7 +249,7 @@ float hitBvh(const Ray& r, const Ctx& c, float t_min, float t_max, TriHit& rec, 
                 float u, v;
                 float hitT = triangleHit(tri, r, t_min, closest, u, v);
                 if (hitT < closest) {
-                    if (isShadow) return 0.0f;
+                    if (isShadow) { STEPLOG(254); return 0.0f; }
                     closest = hitT;
                     rec.triId = first + i;
                     rec.u = u;
@@ -242,6 +259,7 @@ float hitBvh(const Ray& r, const Ctx& c, float t_min, float t_max, TriHit& rec, 
             pop_bitstack(bitStack, idx);
         }
     }
+    STEPLOG(isShadow ? 254 : 255);
     return closest;
 }
 
@@ -625,6 +643,19 @@ float oracleBoxDist(const float bmin[3], const float bmax[3], const float o[3], 
     Ray r(v3(o[0], o[1], o[2]), v3(d[0], d[1], d[2]));
     return hit_bbox_dist(v3(bmin[0], bmin[1], bmin[2]), v3(bmax[0], bmax[1], bmax[2]), r, tMax);
 }
+#ifdef ORACLE_STEPLOG
+// start logging (call with OMP_NUM_THREADS=1), then fetch: returns the number of bytes; copies min(n, cap) of them
+void oracleStepLogStart() {
+    delete g_stepLog;
+    g_stepLog = new std::vector<uint8_t>();
+}
+unsigned long long oracleStepLogFetch(unsigned char* out, unsigned long long cap) {
+    if (!g_stepLog) return 0;
+    const unsigned long long n = g_stepLog->size();
+    if (out) memcpy(out, g_stepLog->data(), n < cap ? n : cap);
+    return n;
+}
+#endif
 int oracleNumThreads() {
     int n = 1;
 #ifdef _OPENMP
