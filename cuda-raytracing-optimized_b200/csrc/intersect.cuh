@@ -6,11 +6,12 @@
 //   sphere               intersections.h:85-104 (both roots)
 //   dual-node traversal  kernels.cu:148-224     (near child first, tie -> left, bit-stack pop)
 // Layout differences (the device layout is ours):
-//   * nodes: 96 bytes per internal node index i, holding the boxes of its children L = 2i and R = 2i+1 as six float4:
-//         [0] {Lmin.x, Lmax.x, Rmin.x, Rmax.x}   [1] {Lmax.x, Lmin.x, Rmax.x, Rmin.x}   [2],[3] the same for y   [4],[5] for z
-//     The slab test swaps t0/t1 when invD < 0 (intersections.h:30): that is a per-ray constant, so a ray picks per axis
-//     the copy whose {near, far} order suits its direction once, at ray set-up, and the inner loop has no selects. The
-//     first profile of the traversal loop was ALU-pipe bound (12 FSEL + 3 FSETP of every step were these swaps);
+//   * nodes: 64 bytes per internal node index i, holding the boxes of its children L = 2i and R = 2i+1 as three float4
+//         [0] {Lmin.x, Lmax.x, Rmin.x, Rmax.x}   [1] the same for y   [2] for z   [3] padding
+//     so that one 32-byte load (LDG.E.ENL2.256) and one 16-byte load fetch both children from one 128-byte line
+//     (2 L1 requests per step instead of 3; an earlier 96-byte record with a pre-swapped copy per direction sign cost
+//     no selects but a third of the L1 lines held dead copies). The slab test's swap of t0/t1 when invD < 0
+//     (intersections.h:30) is a select after the two products;
 //   * triangles: 48-byte tiles {v0, e1 = v1-v0, e2 = v2-v0} in three float4
 //     (the subtractions are the ones triangleHit does first; precomputing them
 //     does not change a bit), +inf in v0.x marks an unused leaf slot.
@@ -23,7 +24,7 @@
 #define RT_EPSILON 0.01f // kernels.cu:19
 
 struct MeshView {
-    const float4* __restrict__ nodes; // 6 float4 per internal node index (see travNodeStep / swizzleNodesKernel)
+    const float4* __restrict__ nodes; // 4 float4 per internal node index (see travNodeStep / swizzleNodesKernel)
     const float4* __restrict__ tris;  // 3 float4 per triangle slot
     unsigned int firstLeaf;
     unsigned int primsPerLeaf;

@@ -25,7 +25,6 @@ __global__ void __launch_bounds__(256, 5) intersectBatchKernel(MeshView mesh, co
     int steps = 0;
     unsigned int nodeVisits = 0, triTests = 0;
     r.ox = r.oy = r.oz = r.ix = r.iy = r.iz = 0.0f;
-    r.offX = r.offY = r.offZ = 0u;
     s.idx = 0u; s.bitStack = 0u; s.closest = 0.0f;
     while (true) {
         unsigned int liveMask = __ballot_sync(0xFFFFFFFFu, live);

@@ -183,13 +183,13 @@ extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb,
     CRT_CHECK(cudaFree(staging));
     c.numTriSlots = numSlots;
 
-    // nodes: upload the caller's 24-byte records, re-tile into 96-byte child-pair records on the device (intersect.cuh)
+    // nodes: upload the caller's 24-byte records, re-tile into 64-byte child-pair records on the device (intersect.cuh)
     const size_t nodeBytes = (size_t)m->numBvhNodes * sizeof(bvh_node);
     const unsigned int firstLeaf = (unsigned int)(m->numBvhNodes / 2); // kernels.cu:614
     float* nodeStaging = nullptr;
     CRT_CHECK(cudaMalloc((void**)&nodeStaging, nodeBytes + 64));
     CRT_CHECK(cudaMemcpy(nodeStaging, m->bvh, nodeBytes, cudaMemcpyHostToDevice));
-    c.nodes = devAlloc<float4>(6 * (size_t)(firstLeaf ? firstLeaf : 1) + 8);
+    c.nodes = devAlloc<float4>(4 * (size_t)(firstLeaf ? firstLeaf : 1) + 8);
     if (firstLeaf) {
         swizzleNodesKernel<<<(firstLeaf + 255) / 256, 256>>>(nodeStaging, firstLeaf, c.nodes);
         CRT_CHECK(cudaGetLastError());

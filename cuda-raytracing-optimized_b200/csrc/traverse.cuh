@@ -26,7 +26,6 @@
 struct RayHot {
     float ox, oy, oz;                 // origin
     float ix, iy, iz;                 // 1.0f / direction (IEEE), direction normalised by the ray constructor (ray.h:9)
-    unsigned int offX, offY, offZ;    // byte offset, inside a 96-byte node record, of the per-axis copy this ray reads
 };
 
 struct TravHot {
@@ -43,9 +42,6 @@ struct RayCold {
 __device__ __forceinline__ void prepRay(RayHot& r, RayCold& c, const f3& o, const f3& dirNormalised, float tMax) {
     r.ox = o.x; r.oy = o.y; r.oz = o.z;
     r.ix = 1.0f / dirNormalised.x; r.iy = 1.0f / dirNormalised.y; r.iz = 1.0f / dirNormalised.z;
-    r.offX = r.ix < 0.0f ? 16u : 0u; // `if (invD < 0) swap(t0, t1)` (intersections.h:30), decided once per ray
-    r.offY = r.iy < 0.0f ? 48u : 32u;
-    r.offZ = r.iz < 0.0f ? 80u : 64u;
     c.dir = make_float4(dirNormalised.x, dirNormalised.y, dirNormalised.z, tMax);
 }
 
@@ -65,37 +61,39 @@ __device__ __forceinline__ void travPop(TravHot& s) {
 
 __device__ __forceinline__ void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-__device__ __forceinline__ float4 ldNode(const MeshView& m, unsigned int byteOffset) {
-    return __ldg((const float4*)((const char*)m.nodes + byteOffset));
+// 32-byte and 16-byte loads through the read-only path (sm_100 has 256-bit global loads: LDG.E.ENL2.256)
+__device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "l"(p));
 }
 
 // One internal-node step (kernels.cu:163-197): both children's slab tests (hit_bbox_dist, intersections.h:25-41), then
 // descend to the nearer child / remember the other / pop.
 //
-// Node layout (intersect.cuh): the ray reads, per axis, the copy {Lnear, Lfar, Rnear, Rfar} for its direction sign, so
-// t0 = (near - o) * invD and t1 = (far - o) * invD need no swap. hit_bbox_dist returns FLT_MAX on a miss and its t_min
-// otherwise, and the caller compares that with `closest`; with tMax = min(closest, far...) folded in:
+// Node record (intersect.cuh): 64 bytes per internal node index, {Lmin, Lmax, Rmin, Rmax} per axis, fetched with one
+// 32-byte and one 16-byte load (2 L1 requests instead of 3: the kernel is bound by L1 wavefronts). The slab test's
+// `if (invD < 0) swap(t0, t1)` becomes a select of {near, far} after the two products. hit_bbox_dist returns FLT_MAX on a
+// miss and its t_min otherwise, and the caller compares that with `closest`; with tMax = min(closest, far...) folded in:
 //     traverse  <=>  !(tMax < tMin) && tMin < closest  <=>  tMin <= tMax && tMin < closest
 //     swap (rightHit < leftHit) matters only when a child is entered: both -> tMinR < tMinL; only right -> 1; only left -> 0.
 // fmaxf / fminf drop a NaN operand (0 * inf on an axis the ray is parallel to) exactly like the reference's
 // `t0 > t_min ? t0 : t_min`, and their result does not depend on the order of the operands.
 //
-// PREFETCH: whichever child is entered next, its record lies in the 192 bytes that start at byte 192*idx (children 2*idx
+// PREFETCH: whichever child is entered next, its record lies in the 128 bytes that start at byte 128*idx (children 2*idx
 // and 2*idx+1 are adjacent), or -- on the last internal level -- its triangles lie in the 2*N tiles that start at leaf
 // 2*idx - firstLeaf. Requesting those lines into L1 now overlaps the next step's memory latency with this step's slab
 // tests. Used when a launch has too few rays to hide latency with other warps (the tail of a frame).
 template <bool PREFETCH>
 __device__ __forceinline__ void travNodeStep(const MeshView& m, const RayHot& r, TravHot& s) {
-    const unsigned int at = 96u * s.idx;
-    const float4 qx = ldNode(m, at + r.offX);
-    const float4 qy = ldNode(m, at + r.offY);
-    const float4 qz = ldNode(m, at + r.offZ);
+    const char* rec = (const char*)m.nodes + 64u * s.idx;
+    float4 qx, qy;
+    ldg256(rec, qx, qy);
+    const float4 qz = __ldg((const float4*)(rec + 32));
     if (PREFETCH) {
         const unsigned int child = 2u * s.idx;
         if (child < m.firstLeaf) {
-            const char* p = (const char*)m.nodes + 96u * child;
-            prefetchL1(p);
-            prefetchL1(p + 128);
+            prefetchL1((const char*)m.nodes + 64u * child);
         } else {
             const float4* p = m.tris + 3 * ((child - m.firstLeaf) * m.primsPerLeaf);
             const unsigned int bytes = 2u * m.primsPerLeaf * 48u;
@@ -106,10 +104,11 @@ __device__ __forceinline__ void travNodeStep(const MeshView& m, const RayHot& r,
     const float2 xl = slabPair(qx.x, qx.y, -r.ox, r.ix), xr = slabPair(qx.z, qx.w, -r.ox, r.ix);
     const float2 yl = slabPair(qy.x, qy.y, -r.oy, r.iy), yr = slabPair(qy.z, qy.w, -r.oy, r.iy);
     const float2 zl = slabPair(qz.x, qz.y, -r.oz, r.iz), zr = slabPair(qz.z, qz.w, -r.oz, r.iz);
-    const float tMinL = fmaxf(fmaxf(xl.x, yl.x), fmaxf(zl.x, 0.001f));
-    const float tMinR = fmaxf(fmaxf(xr.x, yr.x), fmaxf(zr.x, 0.001f));
-    const float tMaxL = fminf(fminf(xl.y, yl.y), fminf(zl.y, s.closest));
-    const float tMaxR = fminf(fminf(xr.y, yr.y), fminf(zr.y, s.closest));
+    const bool nx = r.ix < 0.0f, ny = r.iy < 0.0f, nz = r.iz < 0.0f; // `if (invD < 0) swap(t0, t1)` (intersections.h:30)
+    const float tMinL = fmaxf(fmaxf(nx ? xl.y : xl.x, ny ? yl.y : yl.x), fmaxf(nz ? zl.y : zl.x, 0.001f));
+    const float tMinR = fmaxf(fmaxf(nx ? xr.y : xr.x, ny ? yr.y : yr.x), fmaxf(nz ? zr.y : zr.x, 0.001f));
+    const float tMaxL = fminf(fminf(nx ? xl.x : xl.y, ny ? yl.x : yl.y), fminf(nz ? zl.x : zl.y, s.closest));
+    const float tMaxR = fminf(fminf(nx ? xr.x : xr.y, ny ? yr.x : yr.y), fminf(nz ? zr.x : zr.y, s.closest));
     const bool traverseLeft = tMinL <= tMaxL && tMinL < s.closest;
     const bool traverseRight = tMinR <= tMaxR && tMinR < s.closest;
     if (traverseLeft || traverseRight) {

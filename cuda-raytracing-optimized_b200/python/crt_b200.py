@@ -130,7 +130,7 @@ def device_lib():
     """The CUDA library. Loading needs libcudart's dependencies only; calling anything needs a GPU."""
     global _dev
     if _dev is None:
-        path = os.path.join(BUILD, "libcrt_b200.so")
+        path = os.environ.get("CRT_B200_LIB") or os.path.join(BUILD, "libcrt_b200.so")  # override: A/B runs of two builds
         if not os.path.exists(path):
             raise RuntimeError(f"{path} is missing: the CUDA extension was not built; there is no CPU fallback")
         L = C.CDLL(path)
