@@ -22,6 +22,9 @@
 #include "vecmath.cuh"
 
 #define RT_EPSILON 0.01f // kernels.cu:19
+#ifndef TRI_F4
+#define TRI_F4 3 // float4 per traversal tile: 3 = 48-byte tiles; 4 = 64-byte tiles fetched with one 256-bit + one 32-bit load
+#endif
 
 struct MeshView {
     const float4* __restrict__ nodes; // 4 float4 per internal node index (see travNodeStep / swizzleNodesKernel)

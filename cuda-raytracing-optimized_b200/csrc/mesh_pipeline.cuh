@@ -133,10 +133,18 @@ __global__ void __launch_bounds__(WF_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(Mes
     const unsigned int lane = laneId();
     // Rays a warp holds at a time: 32 when the queue is long; when it is shorter than the grid (the tail of a frame) the
     // rays are spread over all warps, so that no ray waits in lockstep for a longer one in the same warp.
-    const unsigned int totalWarps = gridDim.x * (WF_BLOCK / 32);
-    const unsigned int take = min(32u, max(1u, (n + totalWarps - 1) / totalWarps));
-    const bool tail = take < 32u;
-    const unsigned int refillBelow = tail ? take : (unsigned int)st.traceMinActive;
+    // (`take` is a launch constant, but under the 48-register cap ptxas spilled it to local memory; it lives in shared
+    // memory instead, read through a volatile pointer where it is used: local-memory traffic of this kernel is zero.)
+    __shared__ unsigned int takeShared;
+    if (threadIdx.x == 0) {
+        const unsigned int totalWarps = gridDim.x * (WF_BLOCK / 32);
+        takeShared = min(32u, max(1u, (n + totalWarps - 1) / totalWarps));
+    }
+    __syncthreads();
+    const volatile unsigned int* takePtr = &takeShared;
+#define take (*takePtr)
+#define tail (take < 32u)
+#define refillBelow (tail ? take : (unsigned int)st.traceMinActive)
 
     bool live = false;       // this lane holds a ray
     bool exhausted = false;  // the queue has no more entries for this warp
@@ -271,6 +279,9 @@ __global__ void __launch_bounds__(WF_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(Mes
         }
     }
 }
+#undef take
+#undef tail
+#undef refillBelow
 
 // ------------------------------------------------------------------- shade --
 __global__ void __launch_bounds__(WF_BLOCK) meshShadeKernel(MeshState st, ShadeScene sc, CameraDev cam, int cur) {

@@ -32,19 +32,112 @@ static int g_profiling = 0;
 
 static f3 toF3(const vec3& v) { return mk3(v.e[0], v.e[1], v.e[2]); }
 
-template <class T>
-static T* devAlloc(size_t count) {
-    T* p = nullptr;
-    CRT_CHECK(cudaMalloc((void**)&p, count * sizeof(T) > 0 ? count * sizeof(T) : 16));
+// CRT_TIMING=1: host wall time of the phases of initRenderer / runRenderer on stderr (diagnostic)
+struct PhaseTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    PhaseTimer() : on(std::getenv("CRT_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[crt timing] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
+
+// ------------------------------------------------------------ allocation --
+// Device memory comes from one arena that outlives cleanupRenderer: a host program that renders frame after frame
+// (initRenderer -> runRenderer -> cleanupRenderer, bench.py's e2e step) was spending 100 ms .. 1.6 s per frame in ~40
+// cudaMalloc/cudaFree calls (measured with CRT_TIMING=1; cudaFree synchronises and unmaps). The first frame of a process
+// allocates block by block; cleanupRenderer folds what the frame needed into ONE block that the next frame bumps through,
+// so a warm frame makes no allocation call at all. Streams, events and the pinned buffers are kept the same way.
+// rendererReleaseCaches() (and cleanup with resetDeviceOnCleanup) gives everything back.
+struct DeviceArena {
+    std::vector<std::pair<char*, size_t>> blocks; // blocks[0] = main block (may be absent), others = overflow of this frame
+    bool hasMain = false;
+    size_t used = 0;     // bytes handed out of the main block
+    size_t wanted = 0;   // bytes requested since the last reset
+    int device = -1;
+};
+static DeviceArena g_arena;
+
+static void arenaFreeAll() {
+    for (auto& b : g_arena.blocks) cudaFree(b.first);
+    g_arena.blocks.clear();
+    g_arena.hasMain = false;
+    g_arena.used = g_arena.wanted = 0;
+}
+
+static void* arenaAlloc(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (!bytes) bytes = 256;
+    g_arena.wanted += bytes;
+    if (g_arena.hasMain && g_arena.used + bytes <= g_arena.blocks[0].second) {
+        void* p = g_arena.blocks[0].first + g_arena.used;
+        g_arena.used += bytes;
+        return p;
+    }
+    char* p = nullptr;
+    CRT_CHECK(cudaMalloc((void**)&p, bytes));
+    g_arena.blocks.push_back({p, bytes});
     return p;
 }
 
+// End of a frame's lifetime: every arena pointer dies. If the frame overflowed the main block, replace the blocks by one
+// block of the size the frame needed.
+static void arenaReset() {
+    const size_t need = g_arena.wanted;
+    const bool overflowed = g_arena.blocks.size() > (g_arena.hasMain ? 1u : 0u);
+    if (overflowed) {
+        arenaFreeAll();
+        char* p = nullptr;
+        if (need && cudaMalloc((void**)&p, need) == cudaSuccess) {
+            g_arena.blocks.push_back({p, need});
+            g_arena.hasMain = true;
+        } else {
+            cudaGetLastError(); // no room for the cache: the next frame allocates block by block again
+        }
+    }
+    g_arena.used = g_arena.wanted = 0;
+}
+
+template <class T>
+static T* devAlloc(size_t count) {
+    return (T*)arenaAlloc(count * sizeof(T));
+}
+
+// Streams, events and pinned host buffers, created once per process (per device).
+struct HostCache {
+    int device = -1;
+    cudaStream_t stream = nullptr, streamFast = nullptr;
+    cudaEvent_t evLane = nullptr, evStart = nullptr, evStop = nullptr;
+    void* hostCtl = nullptr;      // pinned
+    void* hostCtlFast = nullptr;  // pinned
+    void* fb = nullptr;           // pinned + mapped frame buffer
+    size_t fbBytes = 0;
+};
+static HostCache g_cache;
+
+static void releaseCaches() {
+    if (g_cache.device >= 0) {
+        cudaFreeHost(g_cache.hostCtl); cudaFreeHost(g_cache.hostCtlFast); cudaFreeHost(g_cache.fb);
+        cudaEventDestroy(g_cache.evLane); cudaEventDestroy(g_cache.evStart); cudaEventDestroy(g_cache.evStop);
+        cudaStreamDestroy(g_cache.streamFast); cudaStreamDestroy(g_cache.stream);
+    }
+    g_cache = HostCache();
+    arenaFreeAll();
+    g_arena.device = -1;
+    cudaGetLastError();
+}
+
+extern "C" void rendererReleaseCaches() {
+    if (g_ctx.initialised) return; // the live frame owns arena memory: call after cleanupRenderer
+    releaseCaches();
+}
+
 static void freeWavefront(RendererContext& c) { // everything sized by the slot count; `accum` is per pixel and stays
-    WfState& s = c.wf;
-    cudaFree(s.rayO); cudaFree(s.rayD); cudaFree(s.atten); cudaFree(s.pcol); cudaFree(s.hit);
-    cudaFree(s.shO); cudaFree(s.shD); cudaFree(s.shL);
-    cudaFree(s.queueA); cudaFree(s.queueB); cudaFree(s.regen);
-    cudaFree(s.ctl);
+    WfState& s = c.wf; // (arena memory: nothing to free one by one)
     float4* accum = s.accum;
     std::memset(&s, 0, sizeof(s));
     s.accum = accum;
@@ -72,14 +165,9 @@ static void allocWavefront(RendererContext& c, unsigned int numSlots) {
 }
 
 static void freeMeshPipeline(RendererContext& c) {
-    MeshState& s = c.mp;
-    cudaFree(s.rayO); cudaFree(s.rayD); cudaFree(s.atten); cudaFree(s.pcol); cudaFree(s.hit); cudaFree(s.travE);
-    cudaFree(s.shO); cudaFree(s.shD); cudaFree(s.shL); cudaFree(s.shC); cudaFree(s.travS); cudaFree(s.pending);
-    cudaFree(s.traceQ[0]); cudaFree(s.traceQ[1]); cudaFree(s.shadeQ[0]); cudaFree(s.shadeQ[1]);
-    cudaFree(s.ctl);
+    MeshState& s = c.mp; // (arena memory: nothing to free one by one)
     std::memset(&s, 0, sizeof(s));
     MeshState& f = c.mpFast;
-    cudaFree(f.traceQ[0]); cudaFree(f.traceQ[1]); cudaFree(f.shadeQ[0]); cudaFree(f.shadeQ[1]); cudaFree(f.ctl);
     std::memset(&f, 0, sizeof(f));
     if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
     if (c.graphFast) { cudaGraphExecDestroy(c.graphFast); c.graphFast = nullptr; }
@@ -127,9 +215,7 @@ static void initCommon(RendererContext& c, const camera& cam, vec3** fb, int nx,
     if (g_opts.device >= 0) CRT_CHECK(cudaSetDevice(g_opts.device));
     int dev = 0;
     CRT_CHECK(cudaGetDevice(&dev));
-    cudaDeviceProp prop;
-    CRT_CHECK(cudaGetDeviceProperties(&prop, dev));
-    c.numSMs = prop.multiProcessorCount;
+    CRT_CHECK(cudaDeviceGetAttribute(&c.numSMs, cudaDevAttrMultiProcessorCount, dev)); // (cudaGetDeviceProperties costs milliseconds)
     c.opts = g_opts;
     c.nx = nx;
     c.ny = ny;
@@ -142,21 +228,49 @@ static void initCommon(RendererContext& c, const camera& cam, vec3** fb, int nx,
     c.cam.v = toF3(cam.v);
     c.cam.w = toF3(cam.w);
     c.cam.lensRadius = cam.lens_radius;
-    CRT_CHECK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    int prLow = 0, prHigh = 0;
-    CRT_CHECK(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
-    CRT_CHECK(cudaStreamCreateWithPriority(&c.streamFast, cudaStreamNonBlocking, prHigh));
-    CRT_CHECK(cudaEventCreateWithFlags(&c.evLane, cudaEventDisableTiming));
+    if (g_cache.device != dev || g_arena.device != dev) { // first frame of the process, or the caller moved to another GPU
+        if (g_cache.device >= 0 && g_cache.device != dev) {
+            CRT_CHECK(cudaSetDevice(g_cache.device));
+            releaseCaches();
+            CRT_CHECK(cudaSetDevice(dev));
+        }
+        if (g_cache.device < 0) {
+            CRT_CHECK(cudaStreamCreateWithFlags(&g_cache.stream, cudaStreamNonBlocking));
+            int prLow = 0, prHigh = 0;
+            CRT_CHECK(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
+            CRT_CHECK(cudaStreamCreateWithPriority(&g_cache.streamFast, cudaStreamNonBlocking, prHigh));
+            CRT_CHECK(cudaEventCreateWithFlags(&g_cache.evLane, cudaEventDisableTiming));
+            CRT_CHECK(cudaEventCreate(&g_cache.evStart));
+            CRT_CHECK(cudaEventCreate(&g_cache.evStop));
+            CRT_CHECK(cudaMallocHost(&g_cache.hostCtlFast, sizeof(MeshControl)));
+            CRT_CHECK(cudaMallocHost(&g_cache.hostCtl, sizeof(WfControl) > sizeof(MeshControl) ? sizeof(WfControl) : sizeof(MeshControl)));
+            g_cache.device = dev;
+        }
+        g_arena.device = dev;
+    }
+    c.stream = g_cache.stream;
+    c.streamFast = g_cache.streamFast;
+    c.evLane = g_cache.evLane;
+    c.evStart = g_cache.evStart;
+    c.evStop = g_cache.evStop;
+    c.hostCtlFast = (MeshControl*)g_cache.hostCtlFast;
+    c.hostCtl = (WfControl*)g_cache.hostCtl;
     c.laneSums = devAlloc<unsigned long long>(2);
-    CRT_CHECK(cudaMallocHost((void**)&c.hostCtlFast, sizeof(MeshControl)));
-    CRT_CHECK(cudaEventCreate(&c.evStart));
-    CRT_CHECK(cudaEventCreate(&c.evStop));
+    c.batchScratch = devAlloc<unsigned long long>(4);
     const size_t npix = (size_t)nx * ny;
-    CRT_CHECK(cudaMallocManaged((void**)&c.fb, (npix ? npix : 1) * sizeof(vec3))); // kernels.cu:578-580
+    // The frame buffer the caller reads after runRenderer (kernels.cu:578-580 uses managed memory; main.cpp:105,119 only
+    // ever dereferences it on the host): pinned, device-mapped host memory that finalizeKernel writes directly, so the frame
+    // needs no page-fault migration (7.4 ms for 1200x800) and no extra copy.
+    const size_t fbBytes = (npix ? npix : 1) * sizeof(vec3);
+    if (g_cache.fbBytes < fbBytes) {
+        if (g_cache.fb) CRT_CHECK(cudaFreeHost(g_cache.fb));
+        CRT_CHECK(cudaHostAlloc(&g_cache.fb, fbBytes, cudaHostAllocMapped));
+        g_cache.fbBytes = fbBytes;
+    }
+    c.fb = (vec3*)g_cache.fb;
     if (fb) *fb = c.fb;
     c.wf.accum = devAlloc<float4>(npix);
     c.ownsAccum = true;
-    CRT_CHECK(cudaMallocHost((void**)&c.hostCtl, sizeof(WfControl) > sizeof(MeshControl) ? sizeof(WfControl) : sizeof(MeshControl)));
     std::memset(&c.stats, 0, sizeof(c.stats));
     c.initialised = true;
 }
@@ -164,38 +278,37 @@ static void initCommon(RendererContext& c, const camera& cam, vec3** fb, int nx,
 extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb, int nx, int ny, int maxDepth) {
     RendererContext& c = g_ctx;
     if (c.initialised) cleanupRenderer();
+    PhaseTimer pt;
     initCommon(c, cam, fb, nx, ny, maxDepth);
+    pt.mark("init: common");
     c.kind = SCENE_MESH;
 
     const mesh* m = sc.m;
     const unsigned int numSlots = m->numTris;
     // triangles: upload the caller's 64-byte records once, re-tile on the device, drop the staging copy
-    float* staging = nullptr;
-    CRT_CHECK(cudaMalloc((void**)&staging, (size_t)(numSlots ? numSlots : 1) * sizeof(triangle)));
+    float* staging = (float*)arenaAlloc((size_t)(numSlots ? numSlots : 1) * sizeof(triangle));
     CRT_CHECK(cudaMemcpy(staging, m->tris, (size_t)numSlots * sizeof(triangle), cudaMemcpyHostToDevice));
-    c.triGeom = devAlloc<float4>(3 * (size_t)numSlots);
+    c.triGeom = devAlloc<float4>(TRI_F4 * (size_t)numSlots + 8);
     c.triShade = devAlloc<float4>(3 * (size_t)numSlots);
     if (numSlots) {
         retileTrianglesKernel<<<(numSlots + 255) / 256, 256>>>(staging, numSlots, c.triGeom, c.triShade);
         CRT_CHECK(cudaGetLastError());
     }
-    CRT_CHECK(cudaDeviceSynchronize());
-    CRT_CHECK(cudaFree(staging));
     c.numTriSlots = numSlots;
+    pt.mark("init: triangles");
 
     // nodes: upload the caller's 24-byte records, re-tile into 64-byte child-pair records on the device (intersect.cuh)
     const size_t nodeBytes = (size_t)m->numBvhNodes * sizeof(bvh_node);
     const unsigned int firstLeaf = (unsigned int)(m->numBvhNodes / 2); // kernels.cu:614
-    float* nodeStaging = nullptr;
-    CRT_CHECK(cudaMalloc((void**)&nodeStaging, nodeBytes + 64));
+    float* nodeStaging = (float*)arenaAlloc(nodeBytes + 64);
     CRT_CHECK(cudaMemcpy(nodeStaging, m->bvh, nodeBytes, cudaMemcpyHostToDevice));
     c.nodes = devAlloc<float4>(4 * (size_t)(firstLeaf ? firstLeaf : 1) + 8);
     if (firstLeaf) {
         swizzleNodesKernel<<<(firstLeaf + 255) / 256, 256>>>(nodeStaging, firstLeaf, c.nodes);
         CRT_CHECK(cudaGetLastError());
     }
-    CRT_CHECK(cudaDeviceSynchronize());
-    CRT_CHECK(cudaFree(nodeStaging));
+    CRT_CHECK(cudaDeviceSynchronize()); // the re-tiling kernels ran on the default stream, the frame runs on c.stream
+    pt.mark("init: nodes");
 
     c.mesh.nodes = c.nodes;
     c.mesh.tris = c.triGeom;
@@ -228,7 +341,7 @@ extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb,
         texW[i] = t.width;
         texH[i] = t.height;
         const size_t bytes = (size_t)t.width * t.height * 3 * sizeof(float);
-        CRT_CHECK(cudaMalloc((void**)&texPtr[i], bytes ? bytes : 16));
+        texPtr[i] = (float*)arenaAlloc(bytes);
         CRT_CHECK(cudaMemcpy(texPtr[i], t.data, bytes, cudaMemcpyHostToDevice));
     }
     c.texPtrHost = texPtr;
@@ -239,6 +352,7 @@ extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb,
     CRT_CHECK(cudaMemcpy(c.texWidth, texW.data(), texW.size() * sizeof(int), cudaMemcpyHostToDevice));
     CRT_CHECK(cudaMemcpy(c.texHeight, texH.data(), texH.size() * sizeof(int), cudaMemcpyHostToDevice));
 
+    pt.mark("init: materials+textures");
     // light: RenderContext default members, kernels.cu:93-94
     c.light.center = mk3(52.514355f, 715.686951f, -272.620972f);
     c.light.radius = 50.0f;
@@ -285,7 +399,9 @@ void crtRunMesh(RendererContext& c, int ns) {
     const unsigned int npix = (unsigned int)c.nx * (unsigned int)c.ny;
     int slotsPerPixel = c.opts.reserved[0] > 0 ? c.opts.reserved[0] : 1;
     if (ns % slotsPerPixel != 0) slotsPerPixel = 1;
+    PhaseTimer pt;
     allocMeshPipeline(c, npix * (unsigned int)slotsPerPixel);
+    pt.mark("run: state allocation");
     MeshState& mp = c.mp;
     mp.accum = c.wf.accum;
     mp.npix = npix;
@@ -370,6 +486,7 @@ void crtRunMesh(RendererContext& c, int ns) {
                 c.graphExec = captureMeshBatch(c, mp, stream, batch, blocksA, c.numSMs * (lanes ? 3 : 4));
                 if (lanes) c.graphFast = captureMeshBatch(c, fast, c.streamFast, batch, blocksB, c.numSMs);
                 c.graphKey = key;
+                pt.mark("run: graph capture");
             }
             MeshControl* hostB = c.hostCtlFast;
             bool workA = true, workB = false;
@@ -434,6 +551,7 @@ void crtRunMesh(RendererContext& c, int ns) {
     CRT_CHECK(cudaStreamSynchronize(stream));
     CRT_CHECK(cudaGetLastError());
     CRT_CHECK(cudaEventElapsedTime(&c.stats.msTotal, c.evStart, c.evStop));
+    pt.mark("run: frame");
     c.stats.raysExtend = host->raysExtend;
     c.stats.raysShadow = host->raysShadow;
     c.stats.iterations = host->iterations;
@@ -469,7 +587,6 @@ extern "C" void* getRendererAccumDevice() { return g_ctx.initialised ? (void*)g_
 extern "C" void setRendererAccumDevice(void* dAccum) {
     RendererContext& c = g_ctx;
     if (!c.initialised || !dAccum) return;
-    if (c.ownsAccum) cudaFree(c.wf.accum);
     c.wf.accum = (float4*)dAccum;
     c.ownsAccum = false;
 }
@@ -508,26 +625,21 @@ extern "C" void getRendererTraversalCounts(unsigned long long* nodeVisits, unsig
 extern "C" void cleanupRenderer() {
     RendererContext& c = g_ctx;
     if (!c.initialised) return;
-    CRT_CHECK(cudaDeviceSynchronize());
+    PhaseTimer pt;
+    CRT_CHECK(cudaStreamSynchronize(c.stream));
+    CRT_CHECK(cudaStreamSynchronize(c.streamFast));
     freeWavefront(c);
     freeMeshPipeline(c);
-    if (c.ownsAccum) cudaFree(c.wf.accum);
     c.wf.accum = nullptr;
-    cudaFree(c.fb);
-    cudaFree(c.triGeom); cudaFree(c.triShade); cudaFree(c.nodes); cudaFree(c.materials);
-    for (float* p : c.texPtrHost) cudaFree(p);
     c.texPtrHost.clear();
-    cudaFree(c.texData); cudaFree(c.texWidth); cudaFree(c.texHeight);
-    cudaFreeHost(c.hostCtl);
-    cudaFreeHost(c.hostCtlFast);
-    cudaFree(c.laneSums);
-    cudaEventDestroy(c.evLane);
-    cudaStreamDestroy(c.streamFast);
-    cudaEventDestroy(c.evStart); cudaEventDestroy(c.evStop);
-    cudaStreamDestroy(c.stream);
+    arenaReset(); // every device pointer of the frame dies here; the memory stays with the process for the next frame
     const bool reset = c.opts.resetDeviceOnCleanup != 0;
     c = RendererContext();
-    if (reset) cudaDeviceReset(); // kernels.cu:679
+    pt.mark("cleanup");
+    if (reset) { // kernels.cu:679
+        releaseCaches();
+        cudaDeviceReset();
+    }
 }
 
 // ------------------------------------------------------------- ray batches --
@@ -537,8 +649,8 @@ extern "C" float intersectBatchDevice(const void* dRayO, const void* dRayD, long
         std::fprintf(stderr, "intersectBatchDevice needs a mesh scene (initRenderer)\n");
         std::exit(99);
     }
-    unsigned long long* cursor = devAlloc<unsigned long long>(2);
-    unsigned long long* counts = devAlloc<unsigned long long>(2);
+    unsigned long long* cursor = c.batchScratch;
+    unsigned long long* counts = c.batchScratch + 2;
     CRT_CHECK(cudaMemsetAsync(cursor, 0, 2 * sizeof(unsigned long long), c.stream));
     CRT_CHECK(cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), c.stream));
     const int blocks = c.numSMs * 8;
@@ -560,8 +672,6 @@ extern "C" float intersectBatchDevice(const void* dRayO, const void* dRayD, long
         c.lastNodeVisits = h[0];
         c.lastTriTests = h[1];
     }
-    cudaFree(cursor);
-    cudaFree(counts);
     return ms;
 }
 
@@ -587,10 +697,12 @@ extern "C" void intersectBatch(const float* origins, const float* dirs, long lon
         o[i] = make_float4(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2], tMin);
         d[i] = make_float4(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], tMax);
     }
-    float4* dO = devAlloc<float4>((size_t)n);
-    float4* dD = devAlloc<float4>((size_t)n);
-    float4* dH = devAlloc<float4>((size_t)n);
-    int* dM = devAlloc<int>((size_t)n);
+    float4 *dO = nullptr, *dD = nullptr, *dH = nullptr; // per-call buffers: plain allocations, not the frame's arena
+    int* dM = nullptr;
+    CRT_CHECK(cudaMalloc((void**)&dO, (size_t)n * sizeof(float4)));
+    CRT_CHECK(cudaMalloc((void**)&dD, (size_t)n * sizeof(float4)));
+    CRT_CHECK(cudaMalloc((void**)&dH, (size_t)n * sizeof(float4)));
+    CRT_CHECK(cudaMalloc((void**)&dM, (size_t)n * sizeof(int)));
     CRT_CHECK(cudaMemcpy(dO, o.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice));
     CRT_CHECK(cudaMemcpy(dD, d.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice));
     intersectBatchDevice(dO, dD, n, dH, dM);

@@ -24,7 +24,7 @@ struct RendererContext {
     int nx = 0, ny = 0, maxDepth = 0;
     CameraDev cam;
     LightDesc light;
-    vec3* fb = nullptr; // managed memory, handed to the caller (kernels.cu:578-580)
+    vec3* fb = nullptr; // pinned, device-mapped host memory handed to the caller (kernels.cu:578-580 uses managed memory)
 
     // mesh scene
     float4* triGeom = nullptr;
@@ -50,6 +50,7 @@ struct RendererContext {
     cudaGraphExec_t graphFast = nullptr;
     cudaEvent_t evLane = nullptr;
     unsigned long long* laneSums = nullptr;
+    unsigned long long* batchScratch = nullptr; // cursor + counters of intersectBatchDevice
     MeshControl* hostCtlFast = nullptr; // pinned
     WfState wf = {};
     bool ownsAccum = false;

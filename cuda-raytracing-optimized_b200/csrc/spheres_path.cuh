@@ -150,7 +150,7 @@ extern "C" void initRendererSpheres(const sphere* spheres, const material* mater
         mats[2 * i + 1] = b;
     }
     CRT_CHECK(cudaMemcpyToSymbol(c_spheres, sp.data(), (size_t)n * sizeof(float4)));
-    CRT_CHECK(cudaMalloc((void**)&c.materials, mats.size() * sizeof(float4)));
+    c.materials = (float4*)arenaAlloc(mats.size() * sizeof(float4));
     CRT_CHECK(cudaMemcpy(c.materials, mats.data(), mats.size() * sizeof(float4), cudaMemcpyHostToDevice));
 }
 

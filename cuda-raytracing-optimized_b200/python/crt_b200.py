@@ -122,7 +122,7 @@ DEVICE_SYMBOLS = [
     "initRenderer", "runRenderer", "cleanupRenderer", "setRendererOptions", "initRendererSpheres", "intersectBatch",
     "intersectBatchDevice", "generateRayBatchDevice", "rendererDeviceAlloc", "rendererDeviceFree", "rendererCopyToHost",
     "rendererCopyToDevice", "getRendererStats", "setRendererProfiling", "getRendererAccumDevice", "setRendererAccumDevice",
-    "finalizeFrame", "setRendererCounting", "getRendererTraversalCounts", "rendererDebugRead",
+    "finalizeFrame", "setRendererCounting", "getRendererTraversalCounts", "rendererDebugRead", "rendererReleaseCaches",
 ]
 
 

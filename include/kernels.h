@@ -25,9 +25,10 @@ extern "C" {
 
 // ---------------------------------------------------------------- part 1 ----
 // reference kernels.h:6 / kernels.cu:571.  Copies the scene to the device
-// (nothing host-side is retained), allocates the frame buffer as managed
-// memory and returns it through *fb (host-dereferenceable after runRenderer,
-// valid until cleanupRenderer).  fb[j*nx+i] is linear RGB, row 0 = bottom.
+// (nothing host-side is retained), allocates the frame buffer as pinned,
+// device-mapped host memory (the reference uses managed memory; its caller only
+// dereferences it on the host) and returns it through *fb (host-dereferenceable
+// after runRenderer, valid until cleanupRenderer).  fb[j*nx+i] is linear RGB, row 0 = bottom.
 void initRenderer(const kernel_scene sc, const camera cam, vec3** fb, int nx, int ny, int maxDepth);
 
 // reference kernels.h:7 / kernels.cu:652.  Blocking.  Overwrites fb with the
@@ -36,8 +37,12 @@ void initRenderer(const kernel_scene sc, const camera cam, vec3** fb, int nx, in
 // ignored (they never changed the image).
 void runRenderer(int ns, int tx, int ty);
 
-// reference kernels.h:8 / kernels.cu:666.  Frees everything initRenderer made.
-// (The reference also calls cudaDeviceReset(); see renderer_options.)
+// reference kernels.h:8 / kernels.cu:666.  Ends the frame: every pointer
+// initRenderer produced (including *fb) is dead afterwards.  The device memory,
+// streams and pinned buffers stay cached inside the library for the next
+// initRenderer of the process (a warm frame makes no allocation call); they are
+// returned by rendererReleaseCaches(), or here when resetDeviceOnCleanup is set
+// (the reference ends with cudaDeviceReset(); see renderer_options).
 void cleanupRenderer();
 
 // ---------------------------------------------------------------- part 2 ----
@@ -83,6 +88,10 @@ float intersectBatchDevice(const void* dRayO, const void* dRayD, long long n, vo
 // from the unit-sphere rejection sampler), seeded per ray with the
 // kernels.cu:542 formula applied to the ray index.
 void generateRayBatchDevice(void* dRayO, void* dRayD, long long n, int filmW, int filmH, float tMin, float tMax);
+
+// Returns the cached device arena, streams, events and pinned buffers to the
+// driver.  No-op while a frame is live (between initRenderer and cleanupRenderer).
+void rendererReleaseCaches();
 
 void* rendererDeviceAlloc(size_t bytes);
 void rendererDeviceFree(void* p);

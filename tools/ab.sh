@@ -1,9 +1,4 @@
-set -x
 cd $GRAFT_REPO_ROOT
-for d in 0 8 16 24 33; do
-  echo "=== drain $d lanes"; CRT_TRACE_DRAIN=$d python tools/render_once.py --steps 2
-done
-for d in 0 16 33; do
-  echo "=== drain $d nolanes"; CRT_EXPRESS_LANE=0 CRT_TRACE_DRAIN=$d python tools/render_once.py --steps 1
-done
-CRT_TRACE_DRAIN=33 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python tools/e2e_breakdown.py 100
+CRT_TIMING=1 python tools/e2e_breakdown.py 8 2>&1 | tail -22
