@@ -28,7 +28,8 @@
 #define ENTRY_SHADOW 0x40000000u
 #define ENTRY_SLOT_MASK 0x3FFFFFFFu
 
-#define SHADOW_FLAG_FINAL 1u
+#define SHADOW_FLAG_FINAL 1u  // the path ended at this bounce: the shadow ray carries the finished sample's colour
+#define SHADOW_FLAG_LAST 2u   // ... and it was the slot's last sample: this shadow ray is all that is left of the slot
 
 struct MeshControl {
     unsigned int traceCount[2];  // entries in traceQ[k]
@@ -75,8 +76,8 @@ struct MeshState {
 };
 
 __device__ __forceinline__ void accumulatePixel(const MeshState& st, unsigned int pixel, float r, float g, float b) {
-    if (st.slotsPerPixel == 1) { // one slot per pixel: plain read-modify-write, in sample order
-        float4 a = st.accum[pixel];
+    if (st.slotsPerPixel == 1) { // one slot per pixel: plain read-modify-write, in sample order (read from L2: the
+        float4 a = __ldcg(&st.accum[pixel]); // previous add may have come from another SM while this kernel was running)
         a.x += r; a.y += g; a.z += b;
         st.accum[pixel] = a;
     } else {
@@ -86,18 +87,172 @@ __device__ __forceinline__ void accumulatePixel(const MeshState& st, unsigned in
     }
 }
 
+// A path between two hit() calls, in registers (`path`, helper_structs.h:48-71, minus what the wavefront keeps elsewhere).
+struct PathRegs {
+    f3 origin, dir, att;   // rayDir is NOT normalised here: hit() normalises (kernels.cu:326), color() advances along the raw one (:485)
+    unsigned int rng;
+    unsigned int flags;    // bounce | PATH_FLAG_SPECULAR | PATH_FLAG_INSIDE
+    int sample;            // index of the sample this path belongs to
+    f3 color;              // p.color
+};
+
 // Starts sample `sample` of `slot`: kernels.cu:549-555.
-__device__ __forceinline__ void startSample(const MeshState& st, const CameraDev& cam, unsigned int slot, unsigned int rng, int sample) {
+__device__ __forceinline__ void startSample(const MeshState& st, const CameraDev& cam, unsigned int slot, unsigned int rng, int sample, PathRegs& p) {
     const unsigned int pixel = slot % st.npix;
     const int px = (int)(pixel % (unsigned int)st.nx), py = (int)(pixel / (unsigned int)st.nx);
     const float u = float(px + rnd(rng)) / float(st.nx);
     const float v = float(py + rnd(rng)) / float(st.ny);
-    f3 o, d;
-    cameraRay(cam, u, v, rng, o, d);
-    st.rayO[slot] = mk4(o, __uint_as_float(rng));
-    st.rayD[slot] = mk4(d, __uint_as_float(0u));
-    st.atten[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(sample));
-    st.pcol[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    cameraRay(cam, u, v, rng, p.origin, p.dir);
+    p.rng = rng;
+    p.flags = 0u; // bounce 0, specular = inside = false (kernels.cu:554-555)
+    p.att = mk3(1.0f, 1.0f, 1.0f);
+    p.sample = sample;
+    p.color = mk3(0.0f, 0.0f, 0.0f);
+}
+
+__device__ __forceinline__ void storePath(const MeshState& st, unsigned int slot, const PathRegs& p, bool withColor) {
+    st.rayO[slot] = mk4(p.origin, __uint_as_float(p.rng));
+    st.rayD[slot] = mk4(p.dir, __uint_as_float(p.flags));
+    st.atten[slot] = mk4(p.att, __int_as_float(p.sample));
+    if (withColor) st.pcol[slot] = mk4(p.color, 0.0f);
+}
+
+// What shadePath decided.
+struct ShadeResult {
+    bool traceNext;    // `p` now holds the next extend ray of the slot (the path continues, or the next sample started)
+    bool continued;    // ... it is the same path (p.color did not change)
+    bool castsShadow;  // the bounce cast a shadow ray (handed to the sink)
+};
+
+// Where shadePath puts what leaves the path, as soon as it is known (so that the values do not stay in registers while the
+// next camera ray is generated): the SoA arrays for meshShadeKernel, the partner lane's shared memory for chaseKernel.
+//   castShadow(origin, dir, lightDist, contribution, flags, carried)  the bounce's shadow ray (kernels.cu:493-508); SHADOW_FLAG_FINAL = the
+//                                                                     path ended at this bounce and the ray carries the sample's colour
+//   retire(colour)                                                    the sample ended without a shadow ray: col += p.color (kernels.cu:558)
+struct ArraySink {
+    const MeshState& st;
+    unsigned int slot;
+    __device__ __forceinline__ void castShadow(const f3& origin, const f3& dir, float lightDist, const f3& contribution, unsigned int flags, const f3& carried) {
+        st.shO[slot] = mk4(origin, 0.0f);
+        st.shD[slot] = mk4(dir, lightDist);
+        st.shL[slot] = mk4(contribution, __uint_as_float(flags));
+        if (flags & SHADOW_FLAG_FINAL) st.shC[slot] = mk4(carried, 0.0f);
+        st.pending[slot] = 1;
+    }
+    __device__ __forceinline__ void retire(const f3& c) { accumulatePixel(st, slot % st.npix, c.x, c.y, c.z); }
+};
+
+// Everything between two hit() calls of color() (kernels.cu:402-531) for one path whose closest-hit record is `h`
+// {t (FLT_MAX = no mesh hit), u, v, triId}: miss / light / albedo / scatter / next-event sample / Russian roulette, and
+// -- when the path ends -- the start of the slot's next sample (kernels.cu:549-555). Shared by meshShadeKernel (state in
+// the SoA arrays) and chaseKernel (state in registers).
+template <class Sink>
+__device__ __forceinline__ ShadeResult shadePath(const MeshState& st, const ShadeScene& sc, const CameraDev& cam, unsigned int slot, PathRegs& p,
+                                                 const float4& h, Sink& sink) {
+    ShadeResult out;
+    out.traceNext = false; out.continued = false; out.castsShadow = false;
+    f3 origin = p.origin, dir = p.dir, att = p.att;
+    unsigned int rng = p.rng;
+    unsigned int flags = p.flags;
+    const bool specularIn = (flags & PATH_FLAG_SPECULAR) != 0u;
+    bool inside = (flags & PATH_FLAG_INSIDE) != 0u;
+    unsigned int bounce = flags & PATH_BOUNCE_MASK;
+    const f3 rdir = unit(dir); // direction of the ray hit() traced
+    f3 pc = p.color;
+    bool continues = false;
+    f3 shDir = mk3(0.0f, 0.0f, 0.0f), shL = mk3(0.0f, 0.0f, 0.0f);
+    float lightDist = 0.0f;
+
+    if (!(h.x < FLT_MAX)) {
+        // no mesh hit. Specular paths may still see the light sphere (kernels.cu:346-349); it ends the path
+        // without adding emission because SHADOW is defined (:440-446). Otherwise: constant grey sky (:424).
+        const bool hitsLight = specularIn && sphereHitT(sc.light.center, sc.light.radius, origin, rdir, RT_EPSILON, FLT_MAX) < FLT_MAX;
+        if (!hitsLight) {
+            const f3 add = att * mk3(0.5f, 0.5f, 0.5f);
+            pc.x += add.x; pc.y += add.y; pc.z += add.z;
+        }
+    } else {
+        const unsigned int triId = __float_as_uint(h.w);
+        const float4 s0 = __ldg(sc.triShade + 3 * triId);
+        const float4 s1 = __ldg(sc.triShade + 3 * triId + 1);
+        const float4 s2 = __ldg(sc.triShade + 3 * triId + 2);
+        const int meshID = __float_as_int(s0.w);
+        SurfacePoint sp;
+        sp.normal = xyz(s0);
+        sp.t = h.x;
+        sp.inside = inside;
+        const float hu = h.y, hv = h.z;
+        // texCoords: u weights vertex 1, v weights vertex 2 (kernels.cu:337-338)
+        const float hw = (1 - hu - hv);
+        float tu = __fmaf_rn(hw, s1.x, mad2(hu, s1.z, hv, s2.x)); // hu*tc[2] + hv*tc[4] + (1-hu-hv)*tc[0]
+        float tv = __fmaf_rn(hw, s1.y, mad2(hu, s1.w, hv, s2.y));
+        if (dot(rdir, sp.normal) > 0.0f) sp.normal = -sp.normal;
+
+        const float4 m0 = __ldg(sc.mats.mats + 2 * meshID);
+        const float4 m1 = __ldg(sc.mats.mats + 2 * meshID + 1);
+        const int texId = __float_as_int(m1.y);
+        f3 albedo;
+        if (texId != -1) { // kernels.cu:457-471: nearest texel, frac() wrap
+            const int width = sc.mats.texWidth[texId];
+            const int height = sc.mats.texHeight[texId];
+            tu = tu - floorf(tu);
+            tv = tv - floorf(tv);
+            const int tx = (width - 1) * tu;
+            const int ty = (height - 1) * tv;
+            const int tIdx = ty * width + tx;
+            const float* td = sc.mats.texData[texId];
+            albedo = mk3(__ldg(td + tIdx * 3 + 0), __ldg(td + tIdx * 3 + 1), __ldg(td + tIdx * 3 + 2));
+        } else {
+            albedo = xyz(m0);
+        }
+
+        Scatter scat;
+        scat.specular = false;
+        scat.throughput = mk3(1.0f, 1.0f, 1.0f);
+        scat.refracted = false;
+        scat.t = h.x;
+        scat.wi = mk3(0.0f, 0.0f, 0.0f);
+        materialScatter(scat, sp, dir, __float_as_int(m1.x), m0.w, albedo, rng);
+
+        origin = origin + scat.t * dir; // kernels.cu:485 (not inters.p)
+        dir = scat.wi;
+        att = att * scat.throughput;
+        const bool specular = scat.specular;
+        inside = scat.refracted ? !inside : inside;
+
+        if (!specular && sampleLight(sc.light, origin, sp.normal, att, rng, shDir, shL, lightDist)) out.castsShadow = true;
+
+        continues = true;
+        if (bounce > 3u) { // Russian roulette, kernels.cu:514-526
+            const float m = maxcomp(att);
+            if (rnd(rng) > m) continues = false;
+            else att = att * (1 / m);
+        }
+        if (continues) {
+            bounce = (bounce + 1u) & PATH_BOUNCE_MASK; // p.bounce is a uint8_t (helper_structs.h:58)
+            if (!((int)bounce < sc.maxDepth)) continues = false;
+        }
+        flags = bounce | (specular ? PATH_FLAG_SPECULAR : 0u) | (inside ? PATH_FLAG_INSIDE : 0u);
+    }
+
+    if (out.castsShadow)
+        sink.castShadow(origin, shDir, lightDist, shL,
+                        continues ? 0u : (p.sample + 1 < st.samplesPerSlot ? SHADOW_FLAG_FINAL : (SHADOW_FLAG_FINAL | SHADOW_FLAG_LAST)), pc);
+    if (continues) {
+        p.origin = origin; p.dir = dir; p.att = att; p.rng = rng; p.flags = flags; p.color = pc;
+        out.traceNext = true;
+        out.continued = true;
+    } else {
+        // the sample is finished: retire its colour (now, or by its FINAL shadow ray) and start the next one
+        if (!out.castsShadow) sink.retire(pc);
+        const int sample = p.sample + 1;
+        p.rng = rng; // the slot's stream runs on into the next sample (kernels.cu:542-548)
+        if (sample < st.samplesPerSlot) {
+            startSample(st, cam, slot, rng, sample, p);
+            out.traceNext = true;
+        }
+    }
+    return out;
 }
 
 __global__ void __launch_bounds__(WF_BLOCK) meshStartKernel(MeshState st, CameraDev cam) {
@@ -109,7 +264,9 @@ __global__ void __launch_bounds__(WF_BLOCK) meshStartKernel(MeshState st, Camera
             const unsigned int pixel = slot % st.npix;
             const unsigned int stream = st.streamBase * (unsigned int)st.slotsPerPixel + slot / st.npix;
             st.pending[slot] = 0;
-            startSample(st, cam, slot, pathSeed(pixel + stream * st.npix), 0); // kernels.cu:541-542 is stream 0
+            PathRegs p;
+            startSample(st, cam, slot, pathSeed(pixel + stream * st.npix), 0, p); // kernels.cu:541-542 is stream 0
+            storePath(st, slot, p, true);
         }
         const unsigned int pos = warpAppend(alive, &st.ctl->traceCount[0]);
         if (alive) st.traceQ[0][pos] = slot;
@@ -119,11 +276,14 @@ __global__ void __launch_bounds__(WF_BLOCK) meshStartKernel(MeshState st, Camera
 // ------------------------------------------------------------------- trace --
 #define TRACE_BUDGET 96        // default steps per ray per launch before it is parked
 #define TRACE_MIN_ACTIVE 20    // default: refill when fewer lanes than this hold a ray
-#define TRACE_BLOCKS_PER_SM 5  // register cap 48: occupancy is what hides the L1/L2 latency of the node fetches
+#ifndef TRACE_BLOCK
+#define TRACE_BLOCK 256
+#endif
+#define TRACE_BLOCKS_PER_SM (1280 / TRACE_BLOCK) // 40 warps per SM, register cap 48: occupancy is what hides the L1/L2 latency of the node fetches
 
 template <bool COUNT>
-__global__ void __launch_bounds__(WF_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(MeshState st, MeshView mesh, int cur) {
-    __shared__ RayCold coldAll[WF_BLOCK];
+__global__ void __launch_bounds__(TRACE_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(MeshState st, MeshView mesh, int cur) {
+    __shared__ RayCold coldAll[TRACE_BLOCK];
     RayCold& c = coldAll[threadIdx.x];
     MeshControl* ctl = st.ctl;
     const unsigned int n = ctl->traceCount[cur];
@@ -137,7 +297,7 @@ __global__ void __launch_bounds__(WF_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(Mes
     // memory instead, read through a volatile pointer where it is used: local-memory traffic of this kernel is zero.)
     __shared__ unsigned int takeShared;
     if (threadIdx.x == 0) {
-        const unsigned int totalWarps = gridDim.x * (WF_BLOCK / 32);
+        const unsigned int totalWarps = gridDim.x * (TRACE_BLOCK / 32);
         takeShared = min(32u, max(1u, (n + totalWarps - 1) / totalWarps));
     }
     __syncthreads();
@@ -192,6 +352,7 @@ __global__ void __launch_bounds__(WF_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(Mes
             if (park) {
                 if (isShadow) {
                     st.travS[slot] = make_uint2(s.idx, s.bitStack);
+                    st.pending[slot] = 2; // in flight AND parked: whoever continues the slot resumes from travS
                 } else {
                     st.travE[slot] = make_uint2(s.idx, s.bitStack);
                     st.hit[slot] = make_float4(s.closest, c.rec.x, c.rec.y, c.rec.z);
@@ -284,7 +445,7 @@ __global__ void __launch_bounds__(WF_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(Mes
 #undef refillBelow
 
 // ------------------------------------------------------------------- shade --
-__global__ void __launch_bounds__(WF_BLOCK) meshShadeKernel(MeshState st, ShadeScene sc, CameraDev cam, int cur) {
+__global__ void __launch_bounds__(WF_BLOCK, 4) meshShadeKernel(MeshState st, ShadeScene sc, CameraDev cam, int cur) {
     MeshControl* ctl = st.ctl;
     const unsigned int n = ctl->shadeCount[cur];
     const unsigned int* __restrict__ queue = st.shadeQ[cur];
@@ -305,111 +466,18 @@ __global__ void __launch_bounds__(WF_BLOCK) meshShadeKernel(MeshState st, ShadeS
                 const float4 ro = st.rayO[slot];
                 const float4 rd = st.rayD[slot];
                 const float4 att4 = st.atten[slot];
-                f3 origin = xyz(ro), dir = xyz(rd), att = xyz(att4);
-                unsigned int rng = __float_as_uint(ro.w);
-                unsigned int flags = __float_as_uint(rd.w);
-                const bool specularIn = (flags & PATH_FLAG_SPECULAR) != 0u;
-                bool inside = (flags & PATH_FLAG_INSIDE) != 0u;
-                unsigned int bounce = flags & PATH_BOUNCE_MASK;
-                const f3 rdir = unit(dir); // direction of the ray hit() traced
-                float4 pc = st.pcol[slot];
-                bool continues = false;
-                f3 shDir = mk3(0.0f, 0.0f, 0.0f), shL = mk3(0.0f, 0.0f, 0.0f);
-                float lightDist = 0.0f;
-
-                if (!(h.x < FLT_MAX)) {
-                    // no mesh hit. Specular paths may still see the light sphere (kernels.cu:346-349); it ends the path
-                    // without adding emission because SHADOW is defined (:440-446). Otherwise: constant grey sky (:424).
-                    const bool hitsLight = specularIn && sphereHitT(sc.light.center, sc.light.radius, origin, rdir, RT_EPSILON, FLT_MAX) < FLT_MAX;
-                    if (!hitsLight) {
-                        const f3 add = att * mk3(0.5f, 0.5f, 0.5f);
-                        pc.x += add.x; pc.y += add.y; pc.z += add.z;
-                    }
-                } else {
-                    const unsigned int triId = __float_as_uint(h.w);
-                    const float4 s0 = __ldg(sc.triShade + 3 * triId);
-                    const float4 s1 = __ldg(sc.triShade + 3 * triId + 1);
-                    const float4 s2 = __ldg(sc.triShade + 3 * triId + 2);
-                    const int meshID = __float_as_int(s0.w);
-                    SurfacePoint sp;
-                    sp.normal = xyz(s0);
-                    sp.t = h.x;
-                    sp.inside = inside;
-                    const float hu = h.y, hv = h.z;
-                    // texCoords: u weights vertex 1, v weights vertex 2 (kernels.cu:337-338)
-                    const float hw = (1 - hu - hv);
-                    float tu = __fmaf_rn(hw, s1.x, mad2(hu, s1.z, hv, s2.x)); // hu*tc[2] + hv*tc[4] + (1-hu-hv)*tc[0]
-                    float tv = __fmaf_rn(hw, s1.y, mad2(hu, s1.w, hv, s2.y));
-                    if (dot(rdir, sp.normal) > 0.0f) sp.normal = -sp.normal;
-
-                    const float4 m0 = __ldg(sc.mats.mats + 2 * meshID);
-                    const float4 m1 = __ldg(sc.mats.mats + 2 * meshID + 1);
-                    const int texId = __float_as_int(m1.y);
-                    f3 albedo;
-                    if (texId != -1) { // kernels.cu:457-471: nearest texel, frac() wrap
-                        const int width = sc.mats.texWidth[texId];
-                        const int height = sc.mats.texHeight[texId];
-                        tu = tu - floorf(tu);
-                        tv = tv - floorf(tv);
-                        const int tx = (width - 1) * tu;
-                        const int ty = (height - 1) * tv;
-                        const int tIdx = ty * width + tx;
-                        const float* td = sc.mats.texData[texId];
-                        albedo = mk3(__ldg(td + tIdx * 3 + 0), __ldg(td + tIdx * 3 + 1), __ldg(td + tIdx * 3 + 2));
-                    } else {
-                        albedo = xyz(m0);
-                    }
-
-                    Scatter scat;
-                    scat.specular = false;
-                    scat.throughput = mk3(1.0f, 1.0f, 1.0f);
-                    scat.refracted = false;
-                    scat.t = h.x;
-                    scat.wi = mk3(0.0f, 0.0f, 0.0f);
-                    materialScatter(scat, sp, dir, __float_as_int(m1.x), m0.w, albedo, rng);
-
-                    origin = origin + scat.t * dir; // kernels.cu:485 (not inters.p)
-                    dir = scat.wi;
-                    att = att * scat.throughput;
-                    const bool specular = scat.specular;
-                    inside = scat.refracted ? !inside : inside;
-
-                    if (!specular && sampleLight(sc.light, origin, sp.normal, att, rng, shDir, shL, lightDist)) castsShadow = true;
-
-                    continues = true;
-                    if (bounce > 3u) { // Russian roulette, kernels.cu:514-526
-                        const float m = maxcomp(att);
-                        if (rnd(rng) > m) continues = false;
-                        else att = att * (1 / m);
-                    }
-                    if (continues) {
-                        bounce = (bounce + 1u) & PATH_BOUNCE_MASK; // p.bounce is a uint8_t (helper_structs.h:58)
-                        if (!((int)bounce < sc.maxDepth)) continues = false;
-                    }
-                    flags = bounce | (specular ? PATH_FLAG_SPECULAR : 0u) | (inside ? PATH_FLAG_INSIDE : 0u);
-                }
-
-                if (castsShadow) {
-                    st.shO[slot] = mk4(origin, 0.0f);
-                    st.shD[slot] = mk4(shDir, lightDist);
-                    st.shL[slot] = mk4(shL, __uint_as_float(continues ? 0u : SHADOW_FLAG_FINAL));
-                    st.pending[slot] = 1;
-                }
-                if (continues) {
-                    st.rayO[slot] = mk4(origin, __uint_as_float(rng));
-                    st.rayD[slot] = mk4(dir, __uint_as_float(flags));
-                    st.atten[slot] = mk4(att, att4.w);
-                    traceNext = true;
-                } else {
-                    // the sample is finished: retire its colour (now, or by its FINAL shadow ray) and start the next one
-                    if (castsShadow) st.shC[slot] = pc;
-                    else accumulatePixel(st, slot % st.npix, pc.x, pc.y, pc.z);
-                    const int sample = __float_as_int(att4.w) + 1;
-                    if (sample < st.samplesPerSlot) {
-                        startSample(st, cam, slot, rng, sample);
-                        traceNext = true;
-                    }
-                }
+                const float4 pc4 = st.pcol[slot];
+                PathRegs p;
+                p.origin = xyz(ro); p.dir = xyz(rd); p.att = xyz(att4);
+                p.rng = __float_as_uint(ro.w);
+                p.flags = __float_as_uint(rd.w);
+                p.sample = __float_as_int(att4.w);
+                p.color = xyz(pc4);
+                ArraySink sink{st, slot};
+                const ShadeResult r = shadePath(st, sc, cam, slot, p, h, sink);
+                traceNext = r.traceNext;
+                castsShadow = r.castsShadow;
+                if (traceNext) storePath(st, slot, p, !r.continued);
             }
         }
         const unsigned int posDefer = warpAppend(defer, &ctl->shadeCount[cur ^ 1]);
@@ -445,16 +513,297 @@ __global__ void __launch_bounds__(WF_BLOCK) meshShadeKernel(MeshState st, ShadeS
     }
 }
 
-// ------------------------------------------------------------ express lane --
+// ------------------------------------------------------------------ chaser --
 // The frame's critical path is its heaviest pixels: one RNG stream per pixel means a pixel's bounces are strictly
-// sequential (kernels.cu:542-548), and a pixel looking into glass needs ~5x the bounces of an average one. In a single
-// wavefront those pixels advance one bounce per iteration while iterations are long (~1 ms with ~1.6 M rays), and then
+// sequential (kernels.cu:542-548), and a pixel looking into glass needs ~10x the bounces of an average one. In the
+// wavefront those pixels advance one bounce per iteration while iterations are long (~1.1 ms with ~1.6 M rays), and then
 // drag a ~4000-iteration tail of nearly empty launches behind the bulk. So slots that fall behind (sample index well below
-// the mean of all live slots) are moved to a second, small wavefront -- same kernels, same state arrays, own queues and
-// control block -- that runs concurrently on its own stream with short iterations. Results do not change: every slot is
-// still processed by the same kernels in the same per-slot order, only by another queue.
-__global__ void laneStatsKernel(MeshState a, unsigned long long* sums) {
+// the mean of all live slots) leave the wavefront for good: between two batches of iterations lanePartitionKernel moves
+// them into a ring, and chaseKernel -- ONE persistent launch that runs beside the wavefront on its own stream, one block
+// per SM -- takes them from there and runs each to its last sample without ever leaving the SM:
+//   * a warp owns up to 16 slots; lane i (< 16) traces the slot's extend ray and shades, lane i + 16 traces its shadow ray,
+//     so that both rays of a bounce are in flight at the same time exactly as in the wavefront;
+//   * a bounce costs its own traversal plus its own shading: no launch, no queue, no step budget, and no waiting for the
+//     longest ray of 8000 others (the wavefront express lane this replaces needed 190-250 us per bounce beside the bulk);
+//   * the arithmetic is the same code (travRound, shadePath), the per-slot order of operations is the same (the next bounce
+//     is shaded only after the previous bounce's shadow ray has been applied; a FINAL shadow ray adds the finished sample to
+//     the pixel while the next sample is already being traced), so frames stay bit-identical.
+// State hand-over: the wavefront's last writes to a moved slot precede the ring's `tail` update by a kernel boundary; the
+// chaser reads the slot with L2 loads (__ldcg: its SM's L1 may hold lines from before) and never writes it back.
+#ifndef CHASE_BLOCK
+#define CHASE_BLOCK 256
+#endif
+#ifndef CHASE_MIN_BLOCKS
+#define CHASE_MIN_BLOCKS 4 // register cap 64: one chaser block fits beside four trace blocks (or three shade blocks) of the wavefront
+#endif
+#define CHASE_SLOTS_PER_WARP 16
+#define CHASE_ENTRY_SHADE 0x40000000u // ring entry: the slot waits to be shaded (ENTRY_RESUME keeps its meaning: parked extend ray)
+#define CHASE_ENTRY_DRAIN 0xC0000000u // ring entry: the slot has no path any more, only the FINAL shadow ray of its last sample
+
+struct ChaseRing {
+    unsigned int* entries;           // numSlots entries: a slot enters at most once per frame
+    unsigned int* ctl;               // [0] head (claimed) [1] tail (published) [2] reserved (appended) [3] closed [4] slots finished
+    unsigned long long* counters;    // [0] extend rays [1] shadow rays [2] node visits [3] triangle tests (counting builds)
+};
+
+struct ChasePathSm {   // a main lane's path between two bounces
+    float4 oRng, dFlags, attSample, color;
+};
+struct ChaseShadowSm { // a partner lane's shadow ray
+    float4 o, dDist, lFlags, carried;
+};
+
+struct ChaseSink {
+    const MeshState& st;
+    unsigned int slot;
+    ChaseShadowSm* partner;
+    __device__ __forceinline__ void castShadow(const f3& origin, const f3& dir, float lightDist, const f3& contribution, unsigned int flags, const f3& carried) {
+        partner->o = mk4(origin, 0.0f);
+        partner->dDist = mk4(dir, lightDist);
+        partner->lFlags = mk4(contribution, __uint_as_float(flags));
+        partner->carried = mk4(carried, 0.0f);
+    }
+    __device__ __forceinline__ void retire(const f3& c) { accumulatePixel(st, slot % st.npix, c.x, c.y, c.z); }
+};
+
+__device__ __forceinline__ unsigned int ldVolatile(const unsigned int* p) { return *(const volatile unsigned int*)p; }
+
+template <bool COUNT>
+__global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(MeshState st, MeshView mesh, ShadeScene sc, CameraDev cam, ChaseRing ring) {
+    __shared__ RayCold coldAll[CHASE_BLOCK];
+    __shared__ ChasePathSm pathAll[CHASE_BLOCK / 2];
+    __shared__ ChaseShadowSm shadowAll[CHASE_BLOCK / 2];
+    const unsigned int lane = laneId();
+    const unsigned int warpInBlock = threadIdx.x >> 5;
+    const bool isMain = lane < CHASE_SLOTS_PER_WARP;
+    const unsigned int pairIdx = warpInBlock * CHASE_SLOTS_PER_WARP + (lane & (CHASE_SLOTS_PER_WARP - 1u)); // shared by a main lane and its partner
+    RayCold& c = coldAll[threadIdx.x];
+    ChasePathSm& path = pathAll[pairIdx];
+    ChaseShadowSm& shadow = shadowAll[pairIdx];
+
+    // lane state
+    enum { IDLE = 0, TRACE = 1, READY = 2, DRAIN = 3 };
+    //   main lane:    IDLE no slot | TRACE extend ray in flight | READY extend ray done, to be shaded | DRAIN no more samples, partner still busy
+    //   partner lane: IDLE         | TRACE shadow ray in flight | READY shadow ray done, result not yet applied
+    int state = IDLE;
+    unsigned int slot = 0;
+    bool unoccluded = false;
+    RayHot r;
+    TravHot s;
+    int steps = 0;
+    unsigned int nodeVisits = 0, triTests = 0, doneExtend = 0, doneShadow = 0;
+    r.ox = r.oy = r.oz = r.ix = r.iy = r.iz = 0.0f;
+    s.idx = 0u; s.bitStack = 0u; s.closest = 0.0f;
+    bool ringDone = false; // closed and fully claimed
+    unsigned int idleSpins = 0;
+
+    while (true) {
+        // ---- 1. idle pairs take slots from the ring (one compare-and-swap per warp)
+        const unsigned int busyMask = __ballot_sync(0xFFFFFFFFu, state != IDLE);
+        const unsigned int pairBusy = (busyMask | (busyMask >> CHASE_SLOTS_PER_WARP)) & 0xFFFFu; // a pair is free when both lanes are idle
+        const unsigned int freePairs = ~pairBusy & 0xFFFFu;
+        unsigned int got = 0, base = 0;
+        if (freePairs != 0u && !ringDone) {
+            if (lane == 0) {
+                const unsigned int tail = ldVolatile(&ring.ctl[1]);
+                const unsigned int head = ldVolatile(&ring.ctl[0]);
+                if (head < tail) {
+                    const unsigned int want = min((unsigned int)__popc(freePairs), tail - head);
+                    if (atomicCAS(&ring.ctl[0], head, head + want) == head) { got = want; base = head; }
+                } else if (ldVolatile(&ring.ctl[3]) != 0u && head >= ldVolatile(&ring.ctl[1])) {
+                    got = 0xFFFFFFFFu; // closed and nothing left
+                }
+            }
+            got = __shfl_sync(0xFFFFFFFFu, got, 0);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (got == 0xFFFFFFFFu) { ringDone = true; got = 0; }
+        }
+        bool ingested = false;
+        unsigned int entry = 0;
+        if (got != 0u) {
+            __threadfence(); // entries and slot state were published before `tail`
+            const unsigned int rank = __popc(freePairs & ((1u << (lane & 15u)) - 1u));
+            if (((freePairs >> (lane & 15u)) & 1u) && rank < got) {
+                entry = __ldcg(&ring.entries[base + rank]);
+                slot = entry & ENTRY_SLOT_MASK;
+                ingested = true;
+            }
+        }
+        if (ingested) {
+            steps = 0;
+            if (isMain) {
+                const float4 ro = __ldcg(&st.rayO[slot]);
+                const float4 rd = __ldcg(&st.rayD[slot]);
+                path.oRng = ro;
+                path.dFlags = rd;
+                path.attSample = __ldcg(&st.atten[slot]);
+                path.color = __ldcg(&st.pcol[slot]);
+                prepRay(r, c, xyz(ro), unit(xyz(rd)), FLT_MAX); // hit(): ray(p.origin, dir) normalises again (kernels.cu:326)
+                c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), 0.0f);
+                if ((entry & CHASE_ENTRY_DRAIN) == CHASE_ENTRY_DRAIN) {
+                    s.idx = 0u; s.bitStack = 0u; s.closest = FLT_MAX;
+                    state = DRAIN;
+                } else if (entry & CHASE_ENTRY_SHADE) {
+                    const float4 h = __ldcg(&st.hit[slot]);
+                    s.idx = 0u; s.bitStack = 0u; s.closest = h.x;
+                    c.rec = make_float4(h.y, h.z, h.w, 0.0f);
+                    state = READY;
+                } else if (entry & ENTRY_RESUME) {
+                    const uint2 t = __ldcg(&st.travE[slot]);
+                    const float4 h = __ldcg(&st.hit[slot]);
+                    s.idx = t.x; s.bitStack = t.y; s.closest = h.x;
+                    c.rec = make_float4(h.y, h.z, h.w, 0.0f);
+                    state = TRACE;
+                } else {
+                    s.idx = 1u; s.bitStack = 1u; s.closest = FLT_MAX;
+                    if (!rayHitsBounds(mesh, r, FLT_MAX)) { s.idx = 0u; s.closest = FLT_MAX; } // hitMesh: scene bounds first (kernels.cu:297)
+                    state = TRACE;
+                }
+            } else {
+                const unsigned int pend = (unsigned int)__ldcg(&st.pending[slot]);
+                if (pend != 0u) {
+                    const float4 so = __ldcg(&st.shO[slot]);
+                    const float4 sd = __ldcg(&st.shD[slot]);
+                    shadow.o = so;
+                    shadow.dDist = sd;
+                    shadow.lFlags = __ldcg(&st.shL[slot]);
+                    shadow.carried = __ldcg(&st.shC[slot]);
+                    prepRay(r, c, xyz(so), unit(xyz(sd)), sd.w);
+                    c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), 0.0f);
+                    if (pend == 2u) {
+                        const uint2 t = __ldcg(&st.travS[slot]);
+                        s.idx = t.x; s.bitStack = t.y; s.closest = sd.w;
+                    } else {
+                        s.idx = 1u; s.bitStack = 1u; s.closest = sd.w;
+                        if (!rayHitsBounds(mesh, r, sd.w)) { s.idx = 0u; s.closest = FLT_MAX; }
+                    }
+                    state = TRACE;
+                }
+            }
+        }
+
+        // ---- 2. one scheduling round of traversal for every ray in flight
+        const bool working = state == TRACE && s.idx != 0u;
+        if (__any_sync(0xFFFFFFFFu, working)) travRound<true>(mesh, r, c, RT_EPSILON, !isMain, working, s, steps, 1, nodeVisits, triTests);
+
+        // ---- 3. finished rays
+        if (state == TRACE && s.idx == 0u) {
+            state = READY;
+            if (isMain) doneExtend++;
+            else { doneShadow++; unoccluded = !(s.closest < c.dir.w); } // hit(...) false: p.color += p.lightContribution (kernels.cu:500-508)
+        }
+
+        // ---- 4. a main lane whose extend ray is done and whose partner is not tracing: apply the shadow result, then shade
+        const unsigned int readyMask = __ballot_sync(0xFFFFFFFFu, state == READY);
+        const unsigned int traceMask = __ballot_sync(0xFFFFFFFFu, state == TRACE);
+        const unsigned int drainMask = __ballot_sync(0xFFFFFFFFu, state == DRAIN);
+        const unsigned int unoccMask = __ballot_sync(0xFFFFFFFFu, unoccluded);
+        const unsigned int partnerBit = 1u << ((lane & 15u) + CHASE_SLOTS_PER_WARP);
+        const bool act = isMain && (((readyMask | drainMask) >> lane) & 1u) && !(traceMask & partnerBit);
+        bool cast = false, freed = false;
+        if (act) {
+            if (readyMask & partnerBit) { // the previous bounce's shadow ray has finished
+                const float4 l = shadow.lFlags;
+                const bool lit = (unoccMask & partnerBit) != 0u;
+                if (__float_as_uint(l.w) & SHADOW_FLAG_FINAL) {
+                    float4 col = shadow.carried;
+                    if (lit) { col.x += l.x; col.y += l.y; col.z += l.z; }
+                    accumulatePixel(st, slot % st.npix, col.x, col.y, col.z); // col += p.color (kernels.cu:558)
+                } else if (lit) {
+                    float4 col = path.color;
+                    col.x += l.x; col.y += l.y; col.z += l.z;
+                    path.color = col;
+                }
+            }
+            if (state == DRAIN) {
+                state = IDLE;
+                freed = true;
+            } else {
+                PathRegs p;
+                p.origin = xyz(path.oRng); p.dir = xyz(path.dFlags); p.att = xyz(path.attSample);
+                p.rng = __float_as_uint(path.oRng.w);
+                p.flags = __float_as_uint(path.dFlags.w);
+                p.sample = __float_as_int(path.attSample.w);
+                p.color = xyz(path.color);
+                const float4 h = make_float4(s.closest, c.rec.x, c.rec.y, c.rec.z);
+                ChaseSink sink{st, slot, &shadow};
+                const ShadeResult res = shadePath(st, sc, cam, slot, p, h, sink);
+                cast = res.castsShadow;
+                if (res.traceNext) {
+                    path.oRng = mk4(p.origin, __uint_as_float(p.rng));
+                    path.dFlags = mk4(p.dir, __uint_as_float(p.flags));
+                    path.attSample = mk4(p.att, __int_as_float(p.sample));
+                    path.color = mk4(p.color, 0.0f);
+                    prepRay(r, c, p.origin, unit(p.dir), FLT_MAX);
+                    c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), 0.0f);
+                    s.idx = 1u; s.bitStack = 1u; s.closest = FLT_MAX;
+                    if (!rayHitsBounds(mesh, r, FLT_MAX)) { s.idx = 0u; s.closest = FLT_MAX; }
+                    steps = 0;
+                    state = TRACE;
+                } else if (cast) {
+                    state = DRAIN; // the last sample's FINAL shadow ray is still to be traced
+                } else {
+                    state = IDLE;
+                    freed = true;
+                }
+            }
+        }
+        __syncwarp();
+        // partners: the applied result is consumed; a freshly cast shadow ray starts
+        const unsigned int actMask = __ballot_sync(0xFFFFFFFFu, act);
+        const unsigned int castMask = __ballot_sync(0xFFFFFFFFu, cast);
+        const unsigned int freedMask = __ballot_sync(0xFFFFFFFFu, freed);
+        if (!isMain) {
+            const unsigned int mainBit = 1u << (lane & 15u);
+            if ((actMask & mainBit) && state == READY) { state = IDLE; unoccluded = false; }
+            if (castMask & mainBit) {
+                const float4 so = shadow.o;
+                const float4 sd = shadow.dDist;
+                prepRay(r, c, xyz(so), unit(xyz(sd)), sd.w);
+                c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), 0.0f);
+                s.idx = 1u; s.bitStack = 1u; s.closest = sd.w;
+                if (!rayHitsBounds(mesh, r, sd.w)) { s.idx = 0u; s.closest = FLT_MAX; }
+                steps = 0;
+                state = TRACE;
+            }
+        }
+        if (freedMask != 0u && lane == 0) atomicAdd(&ring.ctl[4], (unsigned int)__popc(freedMask));
+
+        // ---- 5. nothing in flight: leave when the ring is closed and drained, else wait for the next hand-over
+        if (__ballot_sync(0xFFFFFFFFu, state != IDLE) == 0u) {
+            if (ringDone) break;
+            if (ldVolatile(&ring.ctl[0]) >= ldVolatile(&ring.ctl[1])) {
+                __nanosleep(2000);
+                if (++idleSpins > 5000000u) break; // ~10 s without work: the host is gone
+            }
+        } else {
+            idleSpins = 0;
+        }
+    }
+
+    for (int o = 16; o > 0; o >>= 1) {
+        doneExtend += __shfl_xor_sync(0xFFFFFFFFu, doneExtend, o);
+        doneShadow += __shfl_xor_sync(0xFFFFFFFFu, doneShadow, o);
+        if (COUNT) {
+            nodeVisits += __shfl_xor_sync(0xFFFFFFFFu, nodeVisits, o);
+            triTests += __shfl_xor_sync(0xFFFFFFFFu, triTests, o);
+        }
+    }
+    if (lane == 0) {
+        if (doneExtend) atomicAdd(&ring.counters[0], (unsigned long long)doneExtend);
+        if (doneShadow) atomicAdd(&ring.counters[1], (unsigned long long)doneShadow);
+        if (COUNT) {
+            atomicAdd(&ring.counters[2], (unsigned long long)nodeVisits);
+            atomicAdd(&ring.counters[3], (unsigned long long)triTests);
+        }
+    }
+}
+
+// Mean sample index of the live slots of the wavefront's input queues (index 0).
+// sums[2] = slots the chaser holds right now (one snapshot, so that every thread of the partition decides alike).
+__global__ void laneStatsKernel(MeshState a, ChaseRing ring, unsigned long long* sums) {
     const unsigned int n1 = a.ctl->traceCount[0], n2 = a.ctl->shadeCount[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) sums[2] = (unsigned long long)(ring.ctl[2] - ldVolatile(&ring.ctl[4]));
     unsigned long long sum = 0, cnt = 0;
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += gridDim.x * blockDim.x) {
         const unsigned int entry = i < n1 ? a.traceQ[0][i] : a.shadeQ[0][i - n1];
@@ -469,14 +818,17 @@ __global__ void laneStatsKernel(MeshState a, unsigned long long* sums) {
     if (laneId() == 0 && cnt) { atomicAdd(&sums[0], sum); atomicAdd(&sums[1], cnt); }
 }
 
-// Splits A's input queues (index 0): lagging slots go to B's input queues, the rest to A's spare queues (index 1).
-// A slot's entries (extend, shadow, deferred shade) all take the same side: the decision reads only per-slot state.
-__global__ void lanePartitionKernel(MeshState a, MeshState b, const unsigned long long* sums, float factor, int minMean, unsigned int moveAllBelow,
-                                    unsigned int capB) {
+// Splits the wavefront's input queues (index 0): lagging slots go to the chaser's ring, the rest to the spare queues
+// (index 1). A slot enters the ring once, by its extend entry or its deferred shade entry; its shadow entry is dropped
+// (the chaser finds the shadow ray's state in pending[]: 1 = not started, 2 = parked) unless the slot has nothing else
+// left (SHADOW_FLAG_LAST). The decision reads only per-slot
+// state, so all entries of a slot take the same side.
+__global__ void lanePartitionKernel(MeshState a, ChaseRing ring, const unsigned long long* sums, float factor, int minMean, unsigned int moveAllBelow,
+                                    unsigned int capacity) {
     const unsigned int n1 = a.ctl->traceCount[0], n2 = a.ctl->shadeCount[0];
     const float mean = sums[1] ? (float)((double)sums[0] / (double)sums[1]) : 0.0f;
     const bool moveAll = n1 + n2 <= moveAllBelow;
-    const bool allowed = moveAll || (mean >= (float)minMean && b.ctl->traceCount[0] + b.ctl->shadeCount[0] < capB);
+    const bool allowed = moveAll || (mean >= (float)minMean && sums[2] < (unsigned long long)capacity);
     const float threshold = factor * mean;
     const unsigned int stride = gridDim.x * blockDim.x;
     for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n1 + n2; base += stride) {
@@ -489,13 +841,15 @@ __global__ void lanePartitionKernel(MeshState a, MeshState b, const unsigned lon
             entry = isTrace ? a.traceQ[0][i] : a.shadeQ[0][i - n1];
             lag = allowed && (moveAll || (float)__float_as_int(a.atten[entry & ENTRY_SLOT_MASK].w) < threshold);
         }
+        const bool isShadowEntry = isTrace && (entry & ENTRY_SHADOW) != 0u;
+        // a shadow entry is all that is left of a slot whose last sample has ended: then IT takes the slot into the ring
+        const bool lastShadow = valid && lag && isShadowEntry && (__float_as_uint(a.shL[entry & ENTRY_SLOT_MASK].w) & SHADOW_FLAG_LAST) != 0u;
+        const bool toRing = valid && lag && (!isShadowEntry || lastShadow);
         unsigned int pos;
-        pos = warpAppend(valid && isTrace && lag, &b.ctl->traceCount[0]);
-        if (valid && isTrace && lag) b.traceQ[0][pos] = entry;
+        pos = warpAppend(toRing, &ring.ctl[2]);
+        if (toRing) ring.entries[pos] = lastShadow ? ((entry & ENTRY_SLOT_MASK) | CHASE_ENTRY_DRAIN) : (isTrace ? entry : (entry | CHASE_ENTRY_SHADE));
         pos = warpAppend(valid && isTrace && !lag, &a.ctl->traceCount[1]);
         if (valid && isTrace && !lag) a.traceQ[1][pos] = entry;
-        pos = warpAppend(valid && !isTrace && lag, &b.ctl->shadeCount[0]);
-        if (valid && !isTrace && lag) b.shadeQ[0][pos] = entry;
         pos = warpAppend(valid && !isTrace && !lag, &a.ctl->shadeCount[1]);
         if (valid && !isTrace && !lag) a.shadeQ[1][pos] = entry;
     }
@@ -509,9 +863,17 @@ __global__ void laneCopyBackKernel(MeshState a) {
     }
 }
 
-__global__ void laneCommitKernel(MeshControl* ctl) {
+// Makes the split visible: the wavefront continues with the spare queues' contents, the chaser sees the new ring entries
+// (everything the earlier kernels of this stream wrote precedes the `tail` store).
+__global__ void laneCommitKernel(MeshControl* ctl, ChaseRing ring, int close) {
     ctl->traceCount[0] = ctl->traceCount[1];
     ctl->shadeCount[0] = ctl->shadeCount[1];
     ctl->traceCount[1] = 0;
     ctl->shadeCount[1] = 0;
+    __threadfence();
+    *(volatile unsigned int*)&ring.ctl[1] = ring.ctl[2];
+    if (close) {
+        __threadfence();
+        *(volatile unsigned int*)&ring.ctl[3] = 1u;
+    }
 }

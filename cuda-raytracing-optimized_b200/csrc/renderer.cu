@@ -167,10 +167,8 @@ static void allocWavefront(RendererContext& c, unsigned int numSlots) {
 static void freeMeshPipeline(RendererContext& c) {
     MeshState& s = c.mp; // (arena memory: nothing to free one by one)
     std::memset(&s, 0, sizeof(s));
-    MeshState& f = c.mpFast;
-    std::memset(&f, 0, sizeof(f));
+    std::memset(&c.ring, 0, sizeof(c.ring));
     if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
-    if (c.graphFast) { cudaGraphExecDestroy(c.graphFast); c.graphFast = nullptr; }
     c.graphKey = -1;
 }
 
@@ -196,12 +194,9 @@ static void allocMeshPipeline(RendererContext& c, unsigned int numSlots) {
         s.shadeQ[k] = devAlloc<unsigned int>(numSlots);
     }
     s.ctl = devAlloc<MeshControl>(1);
-    MeshState& f = c.mpFast;
-    for (int k = 0; k < 2; k++) {
-        f.traceQ[k] = devAlloc<unsigned int>(2 * (size_t)numSlots);
-        f.shadeQ[k] = devAlloc<unsigned int>(numSlots);
-    }
-    f.ctl = devAlloc<MeshControl>(1);
+    c.ring.entries = devAlloc<unsigned int>(numSlots);
+    c.ring.ctl = devAlloc<unsigned int>(8);
+    c.ring.counters = devAlloc<unsigned long long>(4);
 }
 
 extern "C" void setRendererOptions(const renderer_options* opt) {
@@ -255,7 +250,7 @@ static void initCommon(RendererContext& c, const camera& cam, vec3** fb, int nx,
     c.evStop = g_cache.evStop;
     c.hostCtlFast = (MeshControl*)g_cache.hostCtlFast;
     c.hostCtl = (WfControl*)g_cache.hostCtl;
-    c.laneSums = devAlloc<unsigned long long>(2);
+    c.laneSums = devAlloc<unsigned long long>(4);
     c.batchScratch = devAlloc<unsigned long long>(4);
     const size_t npix = (size_t)nx * ny;
     // The frame buffer the caller reads after runRenderer (kernels.cu:578-580 uses managed memory; main.cpp:105,119 only
@@ -373,20 +368,21 @@ static ShadeScene shadeScene(const RendererContext& c) {
 
 // One wavefront iteration on `stream`: trace (extend + shadow rays) -> shade (+ retire sample, + next camera ray).
 static void launchMeshIteration(RendererContext& c, const MeshState& mp, cudaStream_t stream, int cur, int traceBlocks, int shadeBlocks,
-                                cudaEvent_t* ev) {
+                                cudaEvent_t* ev, int shadeThreads = WF_BLOCK) {
     if (ev) cudaEventRecord(ev[0], stream);
-    if (c.counting) traceKernel<true><<<traceBlocks, WF_BLOCK, 0, stream>>>(mp, c.mesh, cur);
-    else traceKernel<false><<<traceBlocks, WF_BLOCK, 0, stream>>>(mp, c.mesh, cur);
+    if (c.counting) traceKernel<true><<<traceBlocks, TRACE_BLOCK, 0, stream>>>(mp, c.mesh, cur);
+    else traceKernel<false><<<traceBlocks, TRACE_BLOCK, 0, stream>>>(mp, c.mesh, cur);
     if (ev) cudaEventRecord(ev[1], stream);
-    meshShadeKernel<<<shadeBlocks, WF_BLOCK, 0, stream>>>(mp, shadeScene(c), c.cam, cur);
+    meshShadeKernel<<<shadeBlocks, shadeThreads, 0, stream>>>(mp, shadeScene(c), c.cam, cur);
     if (ev) cudaEventRecord(ev[2], stream);
 }
 
-static cudaGraphExec_t captureMeshBatch(RendererContext& c, const MeshState& mp, cudaStream_t stream, int batch, int traceBlocks, int shadeBlocks) {
+static cudaGraphExec_t captureMeshBatch(RendererContext& c, const MeshState& mp, cudaStream_t stream, int batch, int traceBlocks, int shadeBlocks,
+                                        int shadeThreads = WF_BLOCK) {
     cudaGraph_t graph;
     cudaGraphExec_t exec;
     CRT_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-    for (int k = 0; k < batch; k++) launchMeshIteration(c, mp, stream, k & 1, traceBlocks, shadeBlocks, nullptr);
+    for (int k = 0; k < batch; k++) launchMeshIteration(c, mp, stream, k & 1, traceBlocks, shadeBlocks, nullptr, shadeThreads);
     CRT_CHECK(cudaStreamEndCapture(stream, &graph));
     CRT_CHECK(cudaGraphInstantiate(&exec, graph, 0));
     CRT_CHECK(cudaGraphDestroy(graph));
@@ -414,7 +410,7 @@ void crtRunMesh(RendererContext& c, int ns) {
     mp.traceMinActive = c.opts.reserved[2] > 0 ? c.opts.reserved[2] : TRACE_MIN_ACTIVE;
     if (!c.traceBlocks) {
         int perSM = 0;
-        CRT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, traceKernel<false>, WF_BLOCK, 0));
+        CRT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, traceKernel<false>, TRACE_BLOCK, 0));
         c.traceBlocks = c.numSMs * (perSM > 0 ? perSM : 1); // persistent: exactly one resident wave
     }
     cudaStream_t stream = c.stream;
@@ -461,82 +457,84 @@ void crtRunMesh(RendererContext& c, int ns) {
             }
             for (auto& e : ev) cudaEventDestroy(e);
         } else {
-            // lane A (bulk) leaves one block per SM to lane B (express) so that both run at the same time
+            // The wavefront leaves one trace-block slot per SM to the chaser (mesh_pipeline.cuh), which runs beside it for the whole
+            // frame on its own stream. Between two batches of iterations the slots that fell behind are moved into the ring.
             auto envInt = [](const char* name, int dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) : dflt; };
-            const int blocksB = lanes ? envInt("CRT_LANE_B_BLOCKS", c.numSMs) : 0; // tuning knobs (defaults are the measured best)
-            const int blocksA = c.traceBlocks - blocksB;
-            const int budgetB = envInt("CRT_LANE_B_BUDGET", mp.traceBudget);
+            const bool chase = lanes;
+            const int chaseBlocks = chase ? envInt("CRT_CHASE_BLOCKS", c.numSMs) : 0; // tuning knobs (defaults are the measured best)
+            const int blocksA = c.traceBlocks - (chase ? envInt("CRT_CHASE_RESERVE", c.numSMs) * (WF_BLOCK / TRACE_BLOCK) : 0);
+            const int shadeBlocksA = chase ? envInt("CRT_LANE_A_SHADE_BLOCKS", c.numSMs * 3) : c.numSMs * 4;
+            const int extraBlocks = envInt("CRT_CHASE_EXTRA", c.numSMs * 3);
+            const float lagFactor = (float)envInt("CRT_CHASE_LAG_PCT", 40) * 0.01f;
+            const unsigned int moveAllBelow = (unsigned int)envInt("CRT_CHASE_MOVE_ALL", 24576);
+            const unsigned int capacity = (unsigned int)envInt("CRT_CHASE_CAPACITY", chaseBlocks * (CHASE_BLOCK / 32) * CHASE_SLOTS_PER_WARP);
             const long long key = ((long long)mp.samplesPerSlot << 24) ^ ((long long)slotsPerPixel << 8) ^ batch ^
                                   ((long long)c.counting << 60) ^ ((long long)c.maxDepth << 40) ^ ((long long)mp.streamBase << 48) ^
-                                  ((long long)mp.traceBudget << 12) ^ ((long long)mp.traceMinActive << 4) ^ ((long long)lanes << 59) ^
-                                  ((long long)blocksB << 30) ^ ((long long)budgetB << 20);
-            MeshState& fast = c.mpFast;
-            if (lanes) {
-                MeshControl* ctlB = fast.ctl;
-                unsigned int* q[4] = {fast.traceQ[0], fast.traceQ[1], fast.shadeQ[0], fast.shadeQ[1]};
-                fast = mp; // same state arrays and frame parameters ...
-                fast.ctl = ctlB; // ... own control block and queues
-                fast.traceQ[0] = q[0]; fast.traceQ[1] = q[1]; fast.shadeQ[0] = q[2]; fast.shadeQ[1] = q[3];
-                fast.traceBudget = budgetB; // measured: 96 beats 48..1024 (a larger budget stretches every iteration of the lane to its longest ray)
-                CRT_CHECK(cudaMemsetAsync(fast.ctl, 0, sizeof(MeshControl), stream));
-            }
+                                  ((long long)mp.traceBudget << 12) ^ ((long long)mp.traceMinActive << 4) ^ ((long long)chase << 59) ^
+                                  ((long long)blocksA << 30) ^ ((long long)shadeBlocksA << 17);
             if (!c.graphExec || c.graphKey != key) {
                 if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
-                if (c.graphFast) { cudaGraphExecDestroy(c.graphFast); c.graphFast = nullptr; }
-                c.graphExec = captureMeshBatch(c, mp, stream, batch, blocksA, c.numSMs * (lanes ? 3 : 4));
-                if (lanes) c.graphFast = captureMeshBatch(c, fast, c.streamFast, batch, blocksB, c.numSMs);
+                c.graphExec = captureMeshBatch(c, mp, stream, batch, blocksA, shadeBlocksA);
                 c.graphKey = key;
                 pt.mark("run: graph capture");
             }
-            MeshControl* hostB = c.hostCtlFast;
-            bool workA = true, workB = false;
+            const ChaseRing ring = c.ring;
+            const ShadeScene scene = shadeScene(c);
+            auto launchChasers = [&](int blocks, cudaStream_t on) {
+                if (c.counting) chaseKernel<true><<<blocks, CHASE_BLOCK, 0, on>>>(mp, c.mesh, scene, c.cam, ring);
+                else chaseKernel<false><<<blocks, CHASE_BLOCK, 0, on>>>(mp, c.mesh, scene, c.cam, ring);
+                CRT_CHECK(cudaGetLastError());
+                launches += 1;
+            };
+            if (chase) {
+                CRT_CHECK(cudaMemsetAsync(ring.ctl, 0, 8 * sizeof(unsigned int), stream));
+                CRT_CHECK(cudaMemsetAsync(ring.counters, 0, 4 * sizeof(unsigned long long), stream));
+                CRT_CHECK(cudaEventRecord(c.evLane, stream));
+                CRT_CHECK(cudaStreamWaitEvent(c.streamFast, c.evLane, 0));
+                launchChasers(chaseBlocks, c.streamFast);
+            }
             const bool dumpLanes = std::getenv("CRT_DUMP_LANES") != nullptr;
+            unsigned int* hostRing = (unsigned int*)c.hostCtlFast;
             const auto t0 = std::chrono::steady_clock::now();
             while (true) {
-                if (lanes && workA) { // move lagging slots from A's input queues to B's (both lanes are idle here)
-                    CRT_CHECK(cudaMemsetAsync(c.laneSums, 0, 2 * sizeof(unsigned long long), stream));
-                    laneStatsKernel<<<c.numSMs * 2, WF_BLOCK, 0, stream>>>(mp, c.laneSums);
-                    lanePartitionKernel<<<c.numSMs * 2, WF_BLOCK, 0, stream>>>(mp, fast, c.laneSums, 0.4f, 6, 24576u, 131072u);
+                if (chase) { // the wavefront is idle here: move lagging slots from its input queues to the ring
+                    CRT_CHECK(cudaMemsetAsync(c.laneSums, 0, 4 * sizeof(unsigned long long), stream));
+                    laneStatsKernel<<<c.numSMs * 2, WF_BLOCK, 0, stream>>>(mp, ring, c.laneSums);
+                    lanePartitionKernel<<<c.numSMs * 2, WF_BLOCK, 0, stream>>>(mp, ring, c.laneSums, lagFactor, 6, moveAllBelow, capacity);
                     laneCopyBackKernel<<<c.numSMs * 2, WF_BLOCK, 0, stream>>>(mp);
-                    laneCommitKernel<<<1, 1, 0, stream>>>(mp.ctl);
+                    laneCommitKernel<<<1, 1, 0, stream>>>(mp.ctl, ring, 0);
                     launches += 4;
-                    CRT_CHECK(cudaEventRecord(c.evLane, stream));
-                    CRT_CHECK(cudaStreamWaitEvent(c.streamFast, c.evLane, 0));
                 }
-                if (workA) {
-                    CRT_CHECK(cudaGraphLaunch(c.graphExec, stream));
-                    launches += (unsigned long long)batch * MESH_KERNELS_PER_ITERATION;
-                    CRT_CHECK(cudaMemcpyAsync(host, mp.ctl, sizeof(MeshControl), cudaMemcpyDeviceToHost, stream));
-                    CRT_CHECK(cudaEventRecord(c.evLane, stream));
-                }
-                if (lanes) { // run B batches until A's batch is done (at least one)
-                    while (true) {
-                        CRT_CHECK(cudaGraphLaunch(c.graphFast, c.streamFast));
-                        launches += (unsigned long long)batch * MESH_KERNELS_PER_ITERATION;
-                        CRT_CHECK(cudaMemcpyAsync(hostB, fast.ctl, sizeof(MeshControl), cudaMemcpyDeviceToHost, c.streamFast));
-                        CRT_CHECK(cudaStreamSynchronize(c.streamFast));
-                        workB = hostB->traceCount[0] != 0 || hostB->shadeCount[0] != 0;
-                        if (!workB || !workA || cudaEventQuery(c.evLane) == cudaSuccess) break;
-                    }
-                }
+                CRT_CHECK(cudaGraphLaunch(c.graphExec, stream));
+                launches += (unsigned long long)batch * MESH_KERNELS_PER_ITERATION;
+                CRT_CHECK(cudaMemcpyAsync(host, mp.ctl, sizeof(MeshControl), cudaMemcpyDeviceToHost, stream));
+                if (dumpLanes && chase) CRT_CHECK(cudaMemcpyAsync(hostRing, ring.ctl, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
                 CRT_CHECK(cudaStreamSynchronize(stream));
-                workA = host->traceCount[0] != 0 || host->shadeCount[0] != 0;
+                const bool work = host->traceCount[0] != 0 || host->shadeCount[0] != 0;
                 if (dumpLanes) {
                     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-                    std::fprintf(stderr, "lanes t=%.2f ms  A: trace %u shade %u iters %llu   B: trace %u shade %u iters %llu\n", ms, host->traceCount[0],
-                                 host->shadeCount[0], host->iterations, lanes ? hostB->traceCount[0] : 0u, lanes ? hostB->shadeCount[0] : 0u,
-                                 lanes ? hostB->iterations : 0ull);
+                    std::fprintf(stderr, "lanes t=%.2f ms  wavefront: trace %u shade %u iters %llu   chaser: claimed %u published %u finished %u\n", ms,
+                                 host->traceCount[0], host->shadeCount[0], host->iterations, chase ? hostRing[0] : 0u, chase ? hostRing[1] : 0u,
+                                 chase ? hostRing[4] : 0u);
                 }
-                if (!workA && !workB) break;
+                if (!work) break;
             }
-            if (lanes) { // fold lane B's counters into the frame's
-                host->raysExtend += hostB->raysExtend;
-                host->raysShadow += hostB->raysShadow;
-                host->resumes += hostB->resumes;
-                host->deferred += hostB->deferred;
-                host->iterations += hostB->iterations;
-                host->nodeVisits += hostB->nodeVisits;
-                host->triTests += hostB->triTests;
+            if (chase) { // nothing is left in the wavefront: close the ring, give the chaser the rest of the GPU, wait for it
+                laneCommitKernel<<<1, 1, 0, stream>>>(mp.ctl, ring, 1);
+                launches += 1;
+                if (extraBlocks > 0) launchChasers(extraBlocks, stream);
+                CRT_CHECK(cudaStreamSynchronize(c.streamFast));
+                CRT_CHECK(cudaMemcpyAsync(hostRing, ring.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+                CRT_CHECK(cudaStreamSynchronize(stream));
+                const unsigned long long* hc = (const unsigned long long*)hostRing;
+                host->raysExtend += hc[0];
+                host->raysShadow += hc[1];
+                host->nodeVisits += hc[2];
+                host->triTests += hc[3];
+                if (dumpLanes) {
+                    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                    std::fprintf(stderr, "lanes t=%.2f ms  chaser done: %llu extend + %llu shadow rays\n", ms, hc[0], hc[1]);
+                }
             }
         }
     } else {

@@ -45,9 +45,8 @@ struct RendererContext {
 
     // wavefront state: `mp` = mesh pipeline, `wf` = sphere pipeline (accum lives in wf.accum for both)
     MeshState mp = {};
-    MeshState mpFast = {}; // the express lane: same state arrays, own queues and control block
-    cudaStream_t streamFast = nullptr;
-    cudaGraphExec_t graphFast = nullptr;
+    ChaseRing ring = {};   // hand-over of lagging slots from the wavefront to chaseKernel
+    cudaStream_t streamFast = nullptr; // the chaser's stream
     cudaEvent_t evLane = nullptr;
     unsigned long long* laneSums = nullptr;
     unsigned long long* batchScratch = nullptr; // cursor + counters of intersectBatchDevice
