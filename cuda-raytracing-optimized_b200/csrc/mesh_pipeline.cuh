@@ -519,8 +519,9 @@ __global__ void __launch_bounds__(WF_BLOCK, 4) meshShadeKernel(MeshState st, Sha
 // wavefront those pixels advance one bounce per iteration while iterations are long (~1.1 ms with ~1.6 M rays), and then
 // drag a ~4000-iteration tail of nearly empty launches behind the bulk. So slots that fall behind (sample index well below
 // the mean of all live slots) leave the wavefront for good: between two batches of iterations lanePartitionKernel moves
-// them into a ring, and chaseKernel -- ONE persistent launch that runs beside the wavefront on its own stream, one block
-// per SM -- takes them from there and runs each to its last sample without ever leaving the SM:
+// them into a ring, and chaseKernel -- launched as a small wave after every hand-over, on high-priority streams beside the
+// wavefront; a warp leaves as soon as the ring is empty and its slots are done -- takes them from there and runs each to its
+// last sample without ever leaving the SM:
 //   * a warp owns up to 16 slots; lane i (< 16) traces the slot's extend ray and shades, lane i + 16 traces its shadow ray,
 //     so that both rays of a bounce are in flight at the same time exactly as in the wavefront;
 //   * a bounce costs its own traversal plus its own shading: no launch, no queue, no step budget, and no waiting for the
@@ -528,21 +529,23 @@ __global__ void __launch_bounds__(WF_BLOCK, 4) meshShadeKernel(MeshState st, Sha
 //   * the arithmetic is the same code (travRound, shadePath), the per-slot order of operations is the same (the next bounce
 //     is shaded only after the previous bounce's shadow ray has been applied; a FINAL shadow ray adds the finished sample to
 //     the pixel while the next sample is already being traced), so frames stay bit-identical.
-// State hand-over: the wavefront's last writes to a moved slot precede the ring's `tail` update by a kernel boundary; the
+// State hand-over: the wavefront's last writes to a moved slot precede the ring's `tail` update by a kernel boundary (and a
+// wave is launched after every update, so no entry waits for a warp that has already left); the
 // chaser reads the slot with L2 loads (__ldcg: its SM's L1 may hold lines from before) and never writes it back.
 #ifndef CHASE_BLOCK
-#define CHASE_BLOCK 256
+#define CHASE_BLOCK 64     // small blocks: a block gives its registers back when both its warps are done
 #endif
 #ifndef CHASE_MIN_BLOCKS
-#define CHASE_MIN_BLOCKS 4 // register cap 64: one chaser block fits beside four trace blocks (or three shade blocks) of the wavefront
+#define CHASE_MIN_BLOCKS 12 // register cap 80
 #endif
 #define CHASE_SLOTS_PER_WARP 16
 #define CHASE_ENTRY_SHADE 0x40000000u // ring entry: the slot waits to be shaded (ENTRY_RESUME keeps its meaning: parked extend ray)
 #define CHASE_ENTRY_DRAIN 0xC0000000u // ring entry: the slot has no path any more, only the FINAL shadow ray of its last sample
 
 struct ChaseRing {
-    unsigned int* entries;           // numSlots entries: a slot enters at most once per frame
-    unsigned int* ctl;               // [0] head (claimed) [1] tail (published) [2] reserved (appended) [3] closed [4] slots finished
+    // two rings: [0] shared (a warp takes up to 16 slots), [1] exclusive (the most lagging slots: one per warp, lowest latency)
+    unsigned int* entries[2];        // numSlots entries each: a slot enters at most once per frame
+    unsigned int* ctl;               // per ring r at ctl[8*r + ..]: [0] head (claimed) [1] tail (published) [2] reserved (appended) [4] slots finished
     unsigned long long* counters;    // [0] extend rays [1] shadow rays [2] node visits [3] triangle tests (counting builds)
 };
 
@@ -569,12 +572,17 @@ struct ChaseSink {
 __device__ __forceinline__ unsigned int ldVolatile(const unsigned int* p) { return *(const volatile unsigned int*)p; }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(MeshState st, MeshView mesh, ShadeScene sc, CameraDev cam, ChaseRing ring) {
+__global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(MeshState st, MeshView mesh, ShadeScene sc, CameraDev cam, ChaseRing ring, unsigned int exclusiveEvery,
+                                                                              unsigned int exclusivePairs) {
     __shared__ RayCold coldAll[CHASE_BLOCK];
     __shared__ ChasePathSm pathAll[CHASE_BLOCK / 2];
     __shared__ ChaseShadowSm shadowAll[CHASE_BLOCK / 2];
     const unsigned int lane = laneId();
     const unsigned int warpInBlock = threadIdx.x >> 5;
+    const bool exclusive = ((blockIdx.x * (CHASE_BLOCK / 32) + warpInBlock) % exclusiveEvery) == 0u;
+    unsigned int* const rctl = ring.ctl + (exclusive ? 8 : 0);
+    const unsigned int* const rentries = ring.entries[exclusive ? 1 : 0];
+    const unsigned int pairLimit = exclusive ? exclusivePairs : 0xFFFFu; // mask of the pairs this warp may fill
     const bool isMain = lane < CHASE_SLOTS_PER_WARP;
     const unsigned int pairIdx = warpInBlock * CHASE_SLOTS_PER_WARP + (lane & (CHASE_SLOTS_PER_WARP - 1u)); // shared by a main lane and its partner
     RayCold& c = coldAll[threadIdx.x];
@@ -594,37 +602,35 @@ __global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(Mes
     unsigned int nodeVisits = 0, triTests = 0, doneExtend = 0, doneShadow = 0;
     r.ox = r.oy = r.oz = r.ix = r.iy = r.iz = 0.0f;
     s.idx = 0u; s.bitStack = 0u; s.closest = 0.0f;
-    bool ringDone = false; // closed and fully claimed
-    unsigned int idleSpins = 0;
 
     while (true) {
         // ---- 1. idle pairs take slots from the ring (one compare-and-swap per warp)
         const unsigned int busyMask = __ballot_sync(0xFFFFFFFFu, state != IDLE);
         const unsigned int pairBusy = (busyMask | (busyMask >> CHASE_SLOTS_PER_WARP)) & 0xFFFFu; // a pair is free when both lanes are idle
-        const unsigned int freePairs = ~pairBusy & 0xFFFFu;
+        const unsigned int freePairs = ~pairBusy & pairLimit;
         unsigned int got = 0, base = 0;
-        if (freePairs != 0u && !ringDone) {
+        if (freePairs != 0u) {
             if (lane == 0) {
-                const unsigned int tail = ldVolatile(&ring.ctl[1]);
-                const unsigned int head = ldVolatile(&ring.ctl[0]);
+                const unsigned int tail = ldVolatile(&rctl[1]);
+                const unsigned int head = ldVolatile(&rctl[0]);
                 if (head < tail) {
                     const unsigned int want = min((unsigned int)__popc(freePairs), tail - head);
-                    if (atomicCAS(&ring.ctl[0], head, head + want) == head) { got = want; base = head; }
-                } else if (ldVolatile(&ring.ctl[3]) != 0u && head >= ldVolatile(&ring.ctl[1])) {
-                    got = 0xFFFFFFFFu; // closed and nothing left
+                    if (atomicCAS(&rctl[0], head, head + want) == head) { got = want; base = head; }
+                    else got = 0xFFFFFFFFu; // lost the race: try again
                 }
             }
             got = __shfl_sync(0xFFFFFFFFu, got, 0);
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (got == 0xFFFFFFFFu) { ringDone = true; got = 0; }
         }
+        const bool retry = got == 0xFFFFFFFFu;
+        if (retry) got = 0;
         bool ingested = false;
         unsigned int entry = 0;
         if (got != 0u) {
             __threadfence(); // entries and slot state were published before `tail`
             const unsigned int rank = __popc(freePairs & ((1u << (lane & 15u)) - 1u));
             if (((freePairs >> (lane & 15u)) & 1u) && rank < got) {
-                entry = __ldcg(&ring.entries[base + rank]);
+                entry = __ldcg(&rentries[base + rank]);
                 slot = entry & ENTRY_SLOT_MASK;
                 ingested = true;
             }
@@ -767,17 +773,13 @@ __global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(Mes
                 state = TRACE;
             }
         }
-        if (freedMask != 0u && lane == 0) atomicAdd(&ring.ctl[4], (unsigned int)__popc(freedMask));
+        if (freedMask != 0u && lane == 0) atomicAdd(&rctl[4], (unsigned int)__popc(freedMask));
 
-        // ---- 5. nothing in flight: leave when the ring is closed and drained, else wait for the next hand-over
-        if (__ballot_sync(0xFFFFFFFFu, state != IDLE) == 0u) {
-            if (ringDone) break;
-            if (ldVolatile(&ring.ctl[0]) >= ldVolatile(&ring.ctl[1])) {
-                __nanosleep(2000);
-                if (++idleSpins > 5000000u) break; // ~10 s without work: the host is gone
-            }
-        } else {
-            idleSpins = 0;
+        // ---- 5. nothing in flight and nothing to take: this warp is done (the next hand-over brings its own wave)
+        if (!retry && __ballot_sync(0xFFFFFFFFu, state != IDLE) == 0u) {
+            unsigned int empty = 0;
+            if (lane == 0) empty = ldVolatile(&rctl[0]) >= ldVolatile(&rctl[1]) ? 1u : 0u;
+            if (__shfl_sync(0xFFFFFFFFu, empty, 0)) break;
         }
     }
 
@@ -799,55 +801,74 @@ __global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(Mes
     }
 }
 
-// Mean sample index of the live slots of the wavefront's input queues (index 0).
-// sums[2] = slots the chaser holds right now (one snapshot, so that every thread of the partition decides alike).
-__global__ void laneStatsKernel(MeshState a, ChaseRing ring, unsigned long long* sums) {
+// Statistics of the live slots of the wavefront's input queues (index 0) for the hand-over that follows:
+//   sums[0], sums[1]  sum and count of the slots' sample indices (their mean measures the frame's progress)
+//   sums[2]           slots the chaser holds right now (one snapshot, so that every thread of the partition decides alike)
+//   sums[3]           slots whose sample index is below factor * (mean of the previous hand-over, sums[4])
+//   sums[4]           that mean, as float bits (written by laneCommitKernel; survives from hand-over to hand-over)
+__global__ void laneStatsKernel(MeshState a, ChaseRing ring, unsigned long long* sums, float factor) {
     const unsigned int n1 = a.ctl->traceCount[0], n2 = a.ctl->shadeCount[0];
-    if (blockIdx.x == 0 && threadIdx.x == 0) sums[2] = (unsigned long long)(ring.ctl[2] - ldVolatile(&ring.ctl[4]));
-    unsigned long long sum = 0, cnt = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        sums[2] = (unsigned long long)(ring.ctl[2] - ldVolatile(&ring.ctl[4])) + (unsigned long long)(ring.ctl[8 + 2] - ldVolatile(&ring.ctl[8 + 4]));
+    const float prevThreshold = factor * __uint_as_float((unsigned int)sums[4]);
+    unsigned long long sum = 0, cnt = 0, under = 0;
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += gridDim.x * blockDim.x) {
         const unsigned int entry = i < n1 ? a.traceQ[0][i] : a.shadeQ[0][i - n1];
         if (entry & ENTRY_SHADOW) continue; // count every live slot once: by its extend entry or its deferred shade entry
-        sum += (unsigned long long)__float_as_int(a.atten[entry & ENTRY_SLOT_MASK].w);
+        const int sample = __float_as_int(a.atten[entry & ENTRY_SLOT_MASK].w);
+        sum += (unsigned long long)sample;
         cnt += 1;
+        if ((float)sample < prevThreshold) under += 1;
     }
     for (int o = 16; o > 0; o >>= 1) {
         sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
         cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+        under += __shfl_xor_sync(0xFFFFFFFFu, under, o);
     }
-    if (laneId() == 0 && cnt) { atomicAdd(&sums[0], sum); atomicAdd(&sums[1], cnt); }
+    if (laneId() == 0 && cnt) { atomicAdd(&sums[0], sum); atomicAdd(&sums[1], cnt); if (under) atomicAdd(&sums[3], under); }
 }
 
-// Splits the wavefront's input queues (index 0): lagging slots go to the chaser's ring, the rest to the spare queues
-// (index 1). A slot enters the ring once, by its extend entry or its deferred shade entry; its shadow entry is dropped
+// Splits the wavefront's input queues (index 0): lagging slots go to the chaser's rings, the rest to the spare queues
+// (index 1). A slot lags when its sample index is below `factor` x the mean; when more slots lag than the chaser has room
+// for, a hash of the slot number picks which of them go now (every entry of a slot reads the same per-slot values, so all
+// entries of a slot take the same side). Slots below `exclusiveFactor` x the mean always go, into the exclusive ring.
+// A slot enters a ring once, by its extend entry or its deferred shade entry; its shadow entry is dropped
 // (the chaser finds the shadow ray's state in pending[]: 1 = not started, 2 = parked) unless the slot has nothing else
-// left (SHADOW_FLAG_LAST). The decision reads only per-slot
-// state, so all entries of a slot take the same side.
-__global__ void lanePartitionKernel(MeshState a, ChaseRing ring, const unsigned long long* sums, float factor, int minMean, unsigned int moveAllBelow,
-                                    unsigned int capacity) {
+// left (SHADOW_FLAG_LAST).
+__global__ void lanePartitionKernel(MeshState a, ChaseRing ring, const unsigned long long* sums, float factor, float exclusiveFactor, int minMean,
+                                    unsigned int moveAllBelow, unsigned int capacity, unsigned int salt) {
     const unsigned int n1 = a.ctl->traceCount[0], n2 = a.ctl->shadeCount[0];
     const float mean = sums[1] ? (float)((double)sums[0] / (double)sums[1]) : 0.0f;
     const bool moveAll = n1 + n2 <= moveAllBelow;
-    const bool allowed = moveAll || (mean >= (float)minMean && sums[2] < (unsigned long long)capacity);
-    const float threshold = factor * mean;
+    const bool started = mean >= (float)minMean;
+    const unsigned long long held = sums[2], under = sums[3];
+    const unsigned long long room = held < (unsigned long long)capacity ? (unsigned long long)capacity - held : 0ull;
+    const unsigned int admit = under <= room ? 0x1000000u : (unsigned int)((double)room / (double)under * 16777216.0); // of 2^24
+    const float threshold = factor * mean, thresholdX = exclusiveFactor * mean;
     const unsigned int stride = gridDim.x * blockDim.x;
     for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n1 + n2; base += stride) {
         const unsigned int i = base + laneId();
         const bool valid = i < n1 + n2;
         const bool isTrace = i < n1;
         unsigned int entry = 0;
-        bool lag = false;
+        bool lag = false, lagX = false;
         if (valid) {
             entry = isTrace ? a.traceQ[0][i] : a.shadeQ[0][i - n1];
-            lag = allowed && (moveAll || (float)__float_as_int(a.atten[entry & ENTRY_SLOT_MASK].w) < threshold);
+            const unsigned int slot = entry & ENTRY_SLOT_MASK;
+            const float sample = (float)__float_as_int(a.atten[slot].w);
+            lagX = started && sample < thresholdX;
+            lag = moveAll || lagX || (started && sample < threshold && (wangHash(slot ^ salt) & 0xFFFFFFu) < admit);
         }
         const bool isShadowEntry = isTrace && (entry & ENTRY_SHADOW) != 0u;
         // a shadow entry is all that is left of a slot whose last sample has ended: then IT takes the slot into the ring
         const bool lastShadow = valid && lag && isShadowEntry && (__float_as_uint(a.shL[entry & ENTRY_SLOT_MASK].w) & SHADOW_FLAG_LAST) != 0u;
         const bool toRing = valid && lag && (!isShadowEntry || lastShadow);
+        const unsigned int ringEntry = lastShadow ? ((entry & ENTRY_SLOT_MASK) | CHASE_ENTRY_DRAIN) : (isTrace ? entry : (entry | CHASE_ENTRY_SHADE));
         unsigned int pos;
-        pos = warpAppend(toRing, &ring.ctl[2]);
-        if (toRing) ring.entries[pos] = lastShadow ? ((entry & ENTRY_SLOT_MASK) | CHASE_ENTRY_DRAIN) : (isTrace ? entry : (entry | CHASE_ENTRY_SHADE));
+        pos = warpAppend(toRing && !lagX, &ring.ctl[2]);
+        if (toRing && !lagX) ring.entries[0][pos] = ringEntry;
+        pos = warpAppend(toRing && lagX, &ring.ctl[8 + 2]);
+        if (toRing && lagX) ring.entries[1][pos] = ringEntry;
         pos = warpAppend(valid && isTrace && !lag, &a.ctl->traceCount[1]);
         if (valid && isTrace && !lag) a.traceQ[1][pos] = entry;
         pos = warpAppend(valid && !isTrace && !lag, &a.ctl->shadeCount[1]);
@@ -865,15 +886,13 @@ __global__ void laneCopyBackKernel(MeshState a) {
 
 // Makes the split visible: the wavefront continues with the spare queues' contents, the chaser sees the new ring entries
 // (everything the earlier kernels of this stream wrote precedes the `tail` store).
-__global__ void laneCommitKernel(MeshControl* ctl, ChaseRing ring, int close) {
+__global__ void laneCommitKernel(MeshControl* ctl, ChaseRing ring, unsigned long long* sums) {
+    sums[4] = (unsigned long long)__float_as_uint(sums[1] ? (float)((double)sums[0] / (double)sums[1]) : 0.0f);
     ctl->traceCount[0] = ctl->traceCount[1];
     ctl->shadeCount[0] = ctl->shadeCount[1];
     ctl->traceCount[1] = 0;
     ctl->shadeCount[1] = 0;
     __threadfence();
     *(volatile unsigned int*)&ring.ctl[1] = ring.ctl[2];
-    if (close) {
-        __threadfence();
-        *(volatile unsigned int*)&ring.ctl[3] = 1u;
-    }
+    *(volatile unsigned int*)&ring.ctl[8 + 1] = ring.ctl[8 + 2];
 }

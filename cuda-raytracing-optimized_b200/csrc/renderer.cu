@@ -108,9 +108,11 @@ static T* devAlloc(size_t count) {
 }
 
 // Streams, events and pinned host buffers, created once per process (per device).
+#define CHASE_STREAMS 16
 struct HostCache {
     int device = -1;
     cudaStream_t stream = nullptr, streamFast = nullptr;
+    cudaStream_t chaseStreams[CHASE_STREAMS] = {}; // high priority: one wave of chaseKernel each, round robin
     cudaEvent_t evLane = nullptr, evStart = nullptr, evStop = nullptr;
     void* hostCtl = nullptr;      // pinned
     void* hostCtlFast = nullptr;  // pinned
@@ -124,6 +126,7 @@ static void releaseCaches() {
         cudaFreeHost(g_cache.hostCtl); cudaFreeHost(g_cache.hostCtlFast); cudaFreeHost(g_cache.fb);
         cudaEventDestroy(g_cache.evLane); cudaEventDestroy(g_cache.evStart); cudaEventDestroy(g_cache.evStop);
         cudaStreamDestroy(g_cache.streamFast); cudaStreamDestroy(g_cache.stream);
+        for (auto& cs : g_cache.chaseStreams) cudaStreamDestroy(cs);
     }
     g_cache = HostCache();
     arenaFreeAll();
@@ -194,8 +197,9 @@ static void allocMeshPipeline(RendererContext& c, unsigned int numSlots) {
         s.shadeQ[k] = devAlloc<unsigned int>(numSlots);
     }
     s.ctl = devAlloc<MeshControl>(1);
-    c.ring.entries = devAlloc<unsigned int>(numSlots);
-    c.ring.ctl = devAlloc<unsigned int>(8);
+    c.ring.entries[0] = devAlloc<unsigned int>(numSlots);
+    c.ring.entries[1] = devAlloc<unsigned int>(numSlots);
+    c.ring.ctl = devAlloc<unsigned int>(16);
     c.ring.counters = devAlloc<unsigned long long>(4);
 }
 
@@ -234,6 +238,7 @@ static void initCommon(RendererContext& c, const camera& cam, vec3** fb, int nx,
             int prLow = 0, prHigh = 0;
             CRT_CHECK(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
             CRT_CHECK(cudaStreamCreateWithPriority(&g_cache.streamFast, cudaStreamNonBlocking, prHigh));
+            for (auto& cs : g_cache.chaseStreams) CRT_CHECK(cudaStreamCreateWithPriority(&cs, cudaStreamNonBlocking, prHigh));
             CRT_CHECK(cudaEventCreateWithFlags(&g_cache.evLane, cudaEventDisableTiming));
             CRT_CHECK(cudaEventCreate(&g_cache.evStart));
             CRT_CHECK(cudaEventCreate(&g_cache.evStop));
@@ -250,7 +255,7 @@ static void initCommon(RendererContext& c, const camera& cam, vec3** fb, int nx,
     c.evStop = g_cache.evStop;
     c.hostCtlFast = (MeshControl*)g_cache.hostCtlFast;
     c.hostCtl = (WfControl*)g_cache.hostCtl;
-    c.laneSums = devAlloc<unsigned long long>(4);
+    c.laneSums = devAlloc<unsigned long long>(8);
     c.batchScratch = devAlloc<unsigned long long>(4);
     const size_t npix = (size_t)nx * ny;
     // The frame buffer the caller reads after runRenderer (kernels.cu:578-580 uses managed memory; main.cpp:105,119 only
@@ -461,13 +466,20 @@ void crtRunMesh(RendererContext& c, int ns) {
             // frame on its own stream. Between two batches of iterations the slots that fell behind are moved into the ring.
             auto envInt = [](const char* name, int dflt) { const char* v = std::getenv(name); return v ? std::atoi(v) : dflt; };
             const bool chase = lanes;
-            const int chaseBlocks = chase ? envInt("CRT_CHASE_BLOCKS", c.numSMs) : 0; // tuning knobs (defaults are the measured best)
-            const int blocksA = c.traceBlocks - (chase ? envInt("CRT_CHASE_RESERVE", c.numSMs) * (WF_BLOCK / TRACE_BLOCK) : 0);
-            const int shadeBlocksA = chase ? envInt("CRT_LANE_A_SHADE_BLOCKS", c.numSMs * 3) : c.numSMs * 4;
-            const int extraBlocks = envInt("CRT_CHASE_EXTRA", c.numSMs * 3);
-            const float lagFactor = (float)envInt("CRT_CHASE_LAG_PCT", 40) * 0.01f;
+            const int waveBlocks = envInt("CRT_CHASE_WAVE", c.numSMs * 4);        // tuning knobs (defaults are the measured best)
+            const int lastWaveBlocks = envInt("CRT_CHASE_LAST_WAVE", c.numSMs * 16);
+            const int reserve = chase ? envInt("CRT_CHASE_RESERVE", 0) : 0;            // trace blocks per SM the wavefront does not ask for
+            const int blocksA = c.traceBlocks - reserve * c.numSMs;
+            const int shadeBlocksA = envInt("CRT_LANE_A_SHADE_BLOCKS", c.numSMs * 4);
+            float lagFactor = (float)envInt("CRT_CHASE_LAG_PCT", 40) * 0.01f; // raised while the chaser has room (below)
+            const float lagFactorMax = (float)envInt("CRT_CHASE_LAG_MAX_PCT", 90) * 0.01f;
+            const float lagStep = (float)envInt("CRT_CHASE_LAG_STEP_PCT", 2) * 0.01f;
+            const unsigned int target = (unsigned int)envInt("CRT_CHASE_TARGET", 4000);
+            const float exclusiveFactor = (float)envInt("CRT_CHASE_EXCLUSIVE_PCT", 8) * 0.01f;
+            const unsigned int exclusiveEvery = (unsigned int)envInt("CRT_CHASE_EXCLUSIVE_EVERY", 4); // every n-th warp of a wave serves the exclusive ring ...
+            const unsigned int exclusivePairs = (1u << envInt("CRT_CHASE_EXCLUSIVE_SLOTS", 1)) - 1u;  // ... this many slots at a time
             const unsigned int moveAllBelow = (unsigned int)envInt("CRT_CHASE_MOVE_ALL", 24576);
-            const unsigned int capacity = (unsigned int)envInt("CRT_CHASE_CAPACITY", chaseBlocks * (CHASE_BLOCK / 32) * CHASE_SLOTS_PER_WARP);
+            const unsigned int capacity = (unsigned int)envInt("CRT_CHASE_CAPACITY", 16384);
             const long long key = ((long long)mp.samplesPerSlot << 24) ^ ((long long)slotsPerPixel << 8) ^ batch ^
                                   ((long long)c.counting << 60) ^ ((long long)c.maxDepth << 40) ^ ((long long)mp.streamBase << 48) ^
                                   ((long long)mp.traceBudget << 12) ^ ((long long)mp.traceMinActive << 4) ^ ((long long)chase << 59) ^
@@ -480,50 +492,58 @@ void crtRunMesh(RendererContext& c, int ns) {
             }
             const ChaseRing ring = c.ring;
             const ShadeScene scene = shadeScene(c);
-            auto launchChasers = [&](int blocks, cudaStream_t on) {
-                if (c.counting) chaseKernel<true><<<blocks, CHASE_BLOCK, 0, on>>>(mp, c.mesh, scene, c.cam, ring);
-                else chaseKernel<false><<<blocks, CHASE_BLOCK, 0, on>>>(mp, c.mesh, scene, c.cam, ring);
+            int wave = 0;
+            auto launchWave = [&](int blocks) { // after a hand-over: the wave starts once the commit kernel of `stream` has run
+                cudaStream_t on = g_cache.chaseStreams[wave++ % CHASE_STREAMS];
+                CRT_CHECK(cudaEventRecord(c.evLane, stream));
+                CRT_CHECK(cudaStreamWaitEvent(on, c.evLane, 0));
+                if (c.counting) chaseKernel<true><<<blocks, CHASE_BLOCK, 0, on>>>(mp, c.mesh, scene, c.cam, ring, exclusiveEvery, exclusivePairs);
+                else chaseKernel<false><<<blocks, CHASE_BLOCK, 0, on>>>(mp, c.mesh, scene, c.cam, ring, exclusiveEvery, exclusivePairs);
                 CRT_CHECK(cudaGetLastError());
                 launches += 1;
             };
             if (chase) {
-                CRT_CHECK(cudaMemsetAsync(ring.ctl, 0, 8 * sizeof(unsigned int), stream));
+                CRT_CHECK(cudaMemsetAsync(ring.ctl, 0, 16 * sizeof(unsigned int), stream));
                 CRT_CHECK(cudaMemsetAsync(ring.counters, 0, 4 * sizeof(unsigned long long), stream));
-                CRT_CHECK(cudaEventRecord(c.evLane, stream));
-                CRT_CHECK(cudaStreamWaitEvent(c.streamFast, c.evLane, 0));
-                launchChasers(chaseBlocks, c.streamFast);
+                CRT_CHECK(cudaMemsetAsync(c.laneSums, 0, 8 * sizeof(unsigned long long), stream));
             }
             const bool dumpLanes = std::getenv("CRT_DUMP_LANES") != nullptr;
             unsigned int* hostRing = (unsigned int*)c.hostCtlFast;
             const auto t0 = std::chrono::steady_clock::now();
+            bool last = false;
             while (true) {
-                if (chase) { // the wavefront is idle here: move lagging slots from its input queues to the ring
+                if (chase) { // the wavefront is idle here: move lagging slots from its input queues to the rings
                     CRT_CHECK(cudaMemsetAsync(c.laneSums, 0, 4 * sizeof(unsigned long long), stream));
-                    laneStatsKernel<<<c.numSMs * 2, WF_BLOCK, 0, stream>>>(mp, ring, c.laneSums);
-                    lanePartitionKernel<<<c.numSMs * 2, WF_BLOCK, 0, stream>>>(mp, ring, c.laneSums, lagFactor, 6, moveAllBelow, capacity);
+                    laneStatsKernel<<<c.numSMs * 2, WF_BLOCK, 0, stream>>>(mp, ring, c.laneSums, lagFactor);
+                    lanePartitionKernel<<<c.numSMs * 2, WF_BLOCK, 0, stream>>>(mp, ring, c.laneSums, lagFactor, exclusiveFactor, 6, moveAllBelow, capacity,
+                                                                             (unsigned int)wave * 0x9E3779B9u);
                     laneCopyBackKernel<<<c.numSMs * 2, WF_BLOCK, 0, stream>>>(mp);
-                    laneCommitKernel<<<1, 1, 0, stream>>>(mp.ctl, ring, 0);
+                    laneCommitKernel<<<1, 1, 0, stream>>>(mp.ctl, ring, c.laneSums);
                     launches += 4;
+                    launchWave(last ? lastWaveBlocks : waveBlocks);
                 }
+                if (last) break;
                 CRT_CHECK(cudaGraphLaunch(c.graphExec, stream));
                 launches += (unsigned long long)batch * MESH_KERNELS_PER_ITERATION;
                 CRT_CHECK(cudaMemcpyAsync(host, mp.ctl, sizeof(MeshControl), cudaMemcpyDeviceToHost, stream));
-                if (dumpLanes && chase) CRT_CHECK(cudaMemcpyAsync(hostRing, ring.ctl, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
+                if (chase) CRT_CHECK(cudaMemcpyAsync(hostRing, ring.ctl, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
                 CRT_CHECK(cudaStreamSynchronize(stream));
-                const bool work = host->traceCount[0] != 0 || host->shadeCount[0] != 0;
+                const unsigned int live = host->traceCount[0] + host->shadeCount[0];
                 if (dumpLanes) {
                     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-                    std::fprintf(stderr, "lanes t=%.2f ms  wavefront: trace %u shade %u iters %llu   chaser: claimed %u published %u finished %u\n", ms,
-                                 host->traceCount[0], host->shadeCount[0], host->iterations, chase ? hostRing[0] : 0u, chase ? hostRing[1] : 0u,
-                                 chase ? hostRing[4] : 0u);
+                    std::fprintf(stderr, "lanes t=%.2f ms  wavefront: trace %u shade %u iters %llu   chaser shared: %u/%u finished %u  exclusive: %u/%u finished %u  lag %.2f\n",
+                                 ms, host->traceCount[0], host->shadeCount[0], host->iterations, chase ? hostRing[0] : 0u, chase ? hostRing[1] : 0u,
+                                 chase ? hostRing[4] : 0u, chase ? hostRing[8] : 0u, chase ? hostRing[9] : 0u, chase ? hostRing[12] : 0u, lagFactor);
                 }
-                if (!work) break;
+                if (live == 0) break;
+                if (chase) { // the chaser has room: hand over slots that lag less (they would otherwise stretch the end of the frame)
+                    const unsigned int held = (hostRing[2] - hostRing[4]) + (hostRing[10] - hostRing[12]);
+                    if (held < target && lagFactor < lagFactorMax) lagFactor += lagStep;
+                }
+                last = chase && live <= moveAllBelow; // the next hand-over takes everything that is left: no iteration follows it
             }
-            if (chase) { // nothing is left in the wavefront: close the ring, give the chaser the rest of the GPU, wait for it
-                laneCommitKernel<<<1, 1, 0, stream>>>(mp.ctl, ring, 1);
-                launches += 1;
-                if (extraBlocks > 0) launchChasers(extraBlocks, stream);
-                CRT_CHECK(cudaStreamSynchronize(c.streamFast));
+            if (chase) { // wait for the chaser's waves, collect their ray counts
+                for (int k = 0; k < (wave < CHASE_STREAMS ? wave : CHASE_STREAMS); k++) CRT_CHECK(cudaStreamSynchronize(g_cache.chaseStreams[k]));
                 CRT_CHECK(cudaMemcpyAsync(hostRing, ring.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
                 CRT_CHECK(cudaStreamSynchronize(stream));
                 const unsigned long long* hc = (const unsigned long long*)hostRing;
@@ -533,7 +553,7 @@ void crtRunMesh(RendererContext& c, int ns) {
                 host->triTests += hc[3];
                 if (dumpLanes) {
                     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-                    std::fprintf(stderr, "lanes t=%.2f ms  chaser done: %llu extend + %llu shadow rays\n", ms, hc[0], hc[1]);
+                    std::fprintf(stderr, "lanes t=%.2f ms  chaser done: %llu extend + %llu shadow rays in %d waves\n", ms, hc[0], hc[1], wave);
                 }
             }
         }
