@@ -470,7 +470,7 @@ void crtRunMesh(RendererContext& c, int ns) {
             const int lastWaveBlocks = envInt("CRT_CHASE_LAST_WAVE", c.numSMs * 16);
             const int reserve = chase ? envInt("CRT_CHASE_RESERVE", 0) : 0;            // trace blocks per SM the wavefront does not ask for
             const int blocksA = c.traceBlocks - reserve * c.numSMs;
-            const int shadeBlocksA = envInt("CRT_LANE_A_SHADE_BLOCKS", c.numSMs * 4);
+            const int shadeBlocksA = envInt("CRT_LANE_A_SHADE_BLOCKS", c.numSMs * 8);
             float lagFactor = (float)envInt("CRT_CHASE_LAG_PCT", 40) * 0.01f; // raised while the chaser has room (below)
             const float lagFactorMax = (float)envInt("CRT_CHASE_LAG_MAX_PCT", 90) * 0.01f;
             const float lagStep = (float)envInt("CRT_CHASE_LAG_STEP_PCT", 2) * 0.01f;

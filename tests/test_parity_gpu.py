@@ -196,6 +196,34 @@ def test_full_size_properties(crt):
     scene.close()
 
 
+def test_frame_does_not_depend_on_who_runs_a_slot(crt, medium_scene, monkeypatch):
+    """The wavefront alone, the chaser alone (every slot handed over before the first iteration) and mixes with slots handed
+    over in every state (fresh / parked extend ray, pending / parked shadow ray, deferred shade, last FINAL shadow ray) give
+    the same bits: the schedule decides only WHEN a slot's next bounce is computed, never what it computes."""
+    nx, ny, ns, depth = 400, 300, 16, 64
+
+    def render(env):
+        for k in ("CRT_EXPRESS_LANE", "CRT_CHASE_MOVE_ALL", "CRT_CHASE_CAPACITY", "CRT_CHASE_LAG_PCT", "CRT_CHASE_TARGET", "CRT_CHASE_EXCLUSIVE_PCT"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        crt.set_options(mega_batch=2)  # hand-overs every 2 iterations
+        with crt.Frame(medium_scene, nx, ny, depth) as fr:
+            img = fr.run(ns)
+            st = crt.stats()
+        crt.set_options()
+        return img, st.raysExtend + st.raysShadow
+
+    wave, rays = render({"CRT_EXPRESS_LANE": "0"})
+    for env in ({"CRT_CHASE_MOVE_ALL": "100000000", "CRT_CHASE_CAPACITY": "100000000"},          # chaser alone
+                {"CRT_CHASE_MOVE_ALL": "0", "CRT_CHASE_LAG_PCT": "90", "CRT_CHASE_EXCLUSIVE_PCT": "50"},  # steady trickle of hand-overs
+                {"CRT_CHASE_MOVE_ALL": "60000", "CRT_CHASE_LAG_PCT": "60"},                          # big final hand-over mid-flight
+                {}):                                                                                 # defaults
+        img, r = render(env)
+        assert r == rays, (env, r, rays)
+        assert np.array_equal(img, wave), env
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(G), "..", "oracle", "_ref", "ref_driver")), reason="oracle/_ref not built")
 def test_side_by_side_with_reference_kernel(crt, oracle, medium_scene):
     """The reference's own render kernel (libref.so, separate process) and ours on the same box, same seeds, a config
