@@ -35,6 +35,7 @@ EXTEND_BYTES_PER_RAY = 56   # queue entry 4 + {origin,rng} 16 + {dir,flags} 16 r
 SHADOW_BYTES_PER_RAY = 85   # entry 4 + {origin} 16 + {dir,dist} 16 + {contribution,flags} 16 read; colour 16 read + 16 written; pending 1
 RESUME_BYTES = 64           # a parked ray: state 8 + hit 16 + entry 4 written, then ray 32 + the same 28 read again
 BATCH_BYTES_PER_RAY = 52    # 32 in, 16 + 4 out
+TRACE_DRAM_BYTES_PER_LAUNCH = 350.5e6  # dram__bytes_read.sum + dram__bytes_write.sum of one bulk traceKernel launch (profiles/r01/d_trace_ncu_summary.txt)
 
 
 def shard_samples(ns_total, world):
@@ -268,39 +269,49 @@ def run_ours(args, rank, world, local_rank):
     value = total_rays / (ms_per_step * 1e3)
     clocks = clk.summary()
 
-    # ---- roofline of the dominant kernel (extendKernel): one extra profiled step + one counting step, untimed
+    # ---- roofline of the dominant kernel (traceKernel): one extra step in the timed configuration with CUDA events around every
+    # trace / shade launch (setRendererProfiling(2): same kernels, same chaser beside them, launched one by one instead of as a
+    # graph), and one counting step for the flop side; both untimed
     roof, extra = None, {}
     if rank == 0 and not spheres:
-        L.setRendererProfiling(1)
+        import ctypes as C
+        L.setRendererProfiling(2)
         L.runRenderer(ns, 8, 8)
         L.setRendererProfiling(0)
         ps = crt.stats()
+        ce, cs, cn, ct = C.c_ulonglong(), C.c_ulonglong(), C.c_ulonglong(), C.c_ulonglong()
+        L.getRendererChaserCounts(C.byref(ce), C.byref(cs), C.byref(cn), C.byref(ct))
+        wave_extend, wave_shadow = ps.raysExtend - ce.value, ps.raysShadow - cs.value  # the rays traceKernel traced
         L.setRendererCounting(1)
         L.runRenderer(ns, 8, 8)
         L.setRendererCounting(0)
-        import ctypes as C
         nv, tt = C.c_ulonglong(), C.c_ulonglong()
         L.getRendererTraversalCounts(C.byref(nv), C.byref(tt))
+        L.getRendererChaserCounts(C.byref(ce), C.byref(cs), C.byref(cn), C.byref(ct))
         iters = max(int(ps.iterations), 1)
         avg_ms = ps.msTrace / iters
         rays_all = ps.raysExtend + ps.raysShadow
-        bytes_per_launch = (EXTEND_BYTES_PER_RAY * ps.raysExtend + SHADOW_BYTES_PER_RAY * ps.raysShadow + RESUME_BYTES * ps.resumes) / iters
+        bytes_per_launch = (EXTEND_BYTES_PER_RAY * wave_extend + SHADOW_BYTES_PER_RAY * wave_shadow + RESUME_BYTES * ps.resumes) / iters
         achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
-        flops = 3.0 * rays_all + 36.0 * nv.value + 48.0 * tt.value
-        trav_ms = ps.msTrace
+        flops_wave = 3.0 * (wave_extend + wave_shadow) + 36.0 * (nv.value - cn.value) + 48.0 * (tt.value - ct.value)
+        flops_all = 3.0 * rays_all + 36.0 * nv.value + 48.0 * tt.value
         sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
         fp32_peak = sms * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
         roof = dict(bound="hbm", kernel="traceKernel<false>", achieved=achieved, peak=pk["hbm_gbs"], unit="GB/s", frac=achieved / pk["hbm_gbs"],
-                    traffic=None, peak_source=pk["src"], avg_launch_ms=avg_ms, launches=iters,
+                    traffic=TRACE_DRAM_BYTES_PER_LAUNCH, peak_source=pk["src"], avg_launch_ms=avg_ms, launches=iters,
                     bytes_per_ray=dict(extend=EXTEND_BYTES_PER_RAY, shadow=SHADOW_BYTES_PER_RAY, resumed=RESUME_BYTES),
-                    note="scene (19 MB) is L2-resident by design: the kernel is bound by L2 latency and FP32 issue, not HBM; see fp32",
-                    fp32=dict(achieved=flops / (trav_ms * 1e-3) / 1e12, peak=fp32_peak, unit="TFLOP/s",
-                              frac=flops / (trav_ms * 1e-3) / 1e12 / fp32_peak, kernels="traceKernel",
+                    note="scene (19 MB) is L2-resident by design: the kernel is bound by L1/L2 latency and instruction issue, not HBM; "
+                         "`traffic` = dram bytes of one bulk launch (1.66 M rays) from profiles/r01 (ncu --set full); see fp32",
+                    fp32=dict(achieved=flops_wave / (ps.msTrace * 1e-3) / 1e12, peak=fp32_peak, unit="TFLOP/s",
+                              frac=flops_wave / (ps.msTrace * 1e-3) / 1e12 / fp32_peak, kernels="traceKernel (its own rays over its own launch time)",
+                              whole_frame_frac=flops_all / (ms_per_step * 1e-3) / 1e12 / fp32_peak,
                               node_visits_per_ray=nv.value / max(rays_all, 1), tri_tests_per_ray=tt.value / max(rays_all, 1),
                               formula="3*rays + 36*dual-node visits + 48*triangle tests (SURVEY.md 8d)"))
         extra = dict(kernel_ms_profiled=dict(trace=ps.msTrace, shade=ps.msShade,
-                                             note="per-family CUDA events, one sync per iteration (serialised)"),
-                     wavefront_iterations=iters, resumed_rays=int(ps.resumes), deferred_shades=int(ps.deferred))
+                                             note="CUDA events around every traceKernel / meshShadeKernel launch of one frame in the timed "
+                                                  "configuration (chaser waves run beside them)"),
+                     wavefront_iterations=iters, resumed_rays=int(ps.resumes), deferred_shades=int(ps.deferred),
+                     chaser=dict(rays=int(ce.value + cs.value), share_of_rays=(ce.value + cs.value) / max(rays_all, 1)))
     fr.close()
 
     # ---- e2e: host buffers -> frame on the host, through the reference-facing entry points, every step

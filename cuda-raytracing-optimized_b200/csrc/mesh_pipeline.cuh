@@ -281,12 +281,25 @@ __global__ void __launch_bounds__(WF_BLOCK) meshStartKernel(MeshState st, Camera
 #endif
 #define TRACE_BLOCKS_PER_SM (1280 / TRACE_BLOCK) // 40 warps per SM, register cap 48: occupancy is what hides the L1/L2 latency of the node fetches
 
-template <bool COUNT>
-__global__ void __launch_bounds__(TRACE_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(MeshState st, MeshView mesh, int cur) {
+// A per-warp flag byte in shared memory, addressed from %tid inside the asm block: the address is recomputed at every
+// use instead of occupying a register (or a local-memory slot, which is what ptxas chose under the 48-register cap).
+__device__ __forceinline__ unsigned int warpFlagLoad(unsigned int sharedBase) {
+    unsigned int v;
+    asm volatile("{\n\t.reg .u32 t;\n\tmov.u32 t, %%tid.x;\n\tshr.u32 t, t, 5;\n\tadd.u32 t, t, %1;\n\tld.volatile.shared.u8 %0, [t];\n\t}" : "=r"(v) : "r"(sharedBase));
+    return v;
+}
+__device__ __forceinline__ void warpFlagSet(unsigned int sharedBase) {
+    asm volatile("{\n\t.reg .u32 t;\n\t.reg .u32 one;\n\tmov.u32 t, %%tid.x;\n\tshr.u32 t, t, 5;\n\tadd.u32 t, t, %0;\n\tmov.u32 one, 1;\n\tst.volatile.shared.u8 [t], one;\n\t}" ::"r"(sharedBase) : "memory");
+}
+
+// CUR (which of the two queue sets is the input) is a template parameter so that the queue pointers are reads of the kernel's
+// parameter bank and not six registers held across the traversal loop.
+template <bool COUNT, int CUR>
+__global__ void __launch_bounds__(TRACE_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(MeshState st, MeshView mesh) {
+    constexpr int cur = CUR;
     __shared__ RayCold coldAll[TRACE_BLOCK];
     RayCold& c = coldAll[threadIdx.x];
     MeshControl* ctl = st.ctl;
-    const unsigned int n = ctl->traceCount[cur];
     const unsigned int* __restrict__ queue = st.traceQ[cur];
     unsigned int* __restrict__ nextTrace = st.traceQ[cur ^ 1];
     unsigned int* __restrict__ shadeQ = st.shadeQ[cur];
@@ -295,19 +308,26 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(
     // rays are spread over all warps, so that no ray waits in lockstep for a longer one in the same warp.
     // (`take` is a launch constant, but under the 48-register cap ptxas spilled it to local memory; it lives in shared
     // memory instead, read through a volatile pointer where it is used: local-memory traffic of this kernel is zero.)
-    __shared__ unsigned int takeShared;
+    __shared__ unsigned int takeShared, countShared;
+    __shared__ unsigned char exhaustedShared[TRACE_BLOCK / 32]; // per warp: the queue has no more entries for this warp
     if (threadIdx.x == 0) {
+        const unsigned int count = ctl->traceCount[cur];
         const unsigned int totalWarps = gridDim.x * (TRACE_BLOCK / 32);
-        takeShared = min(32u, max(1u, (n + totalWarps - 1) / totalWarps));
+        countShared = count;
+        takeShared = min(32u, max(1u, (count + totalWarps - 1) / totalWarps));
     }
+    if (threadIdx.x < TRACE_BLOCK / 32) exhaustedShared[threadIdx.x] = 0;
     __syncthreads();
     const volatile unsigned int* takePtr = &takeShared;
+    const volatile unsigned int* countPtr = &countShared;
+    const unsigned int exhaustedBase = (unsigned int)__cvta_generic_to_shared(exhaustedShared);
+#define n (*countPtr)
+#define exhausted (warpFlagLoad(exhaustedBase) != 0u)
 #define take (*takePtr)
 #define tail (take < 32u)
 #define refillBelow (tail ? take : (unsigned int)st.traceMinActive)
 
     bool live = false;       // this lane holds a ray
-    bool exhausted = false;  // the queue has no more entries for this warp
     bool isShadow = false;
     RayHot r;
     TravHot s;
@@ -383,7 +403,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(
                 unsigned int base = 0;
                 if (lane == 0) base = atomicAdd(&ctl->traceCursor, count);
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                if (base + count >= n) exhausted = true; // warp-uniform: the tail of the queue has been handed out
+                if (base + count >= n) warpFlagSet(exhaustedBase); // warp-uniform: the tail of the queue has been handed out
                 const unsigned int rank = __popc(idle & below);
                 const unsigned int i = base + rank;
                 if (!live && rank < count && i < n) {
@@ -440,6 +460,8 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(
         }
     }
 }
+#undef n
+#undef exhausted
 #undef take
 #undef tail
 #undef refillBelow

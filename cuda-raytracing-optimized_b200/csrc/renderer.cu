@@ -375,8 +375,13 @@ static ShadeScene shadeScene(const RendererContext& c) {
 static void launchMeshIteration(RendererContext& c, const MeshState& mp, cudaStream_t stream, int cur, int traceBlocks, int shadeBlocks,
                                 cudaEvent_t* ev, int shadeThreads = WF_BLOCK) {
     if (ev) cudaEventRecord(ev[0], stream);
-    if (c.counting) traceKernel<true><<<traceBlocks, TRACE_BLOCK, 0, stream>>>(mp, c.mesh, cur);
-    else traceKernel<false><<<traceBlocks, TRACE_BLOCK, 0, stream>>>(mp, c.mesh, cur);
+    if (c.counting) {
+        if (cur) traceKernel<true, 1><<<traceBlocks, TRACE_BLOCK, 0, stream>>>(mp, c.mesh);
+        else traceKernel<true, 0><<<traceBlocks, TRACE_BLOCK, 0, stream>>>(mp, c.mesh);
+    } else {
+        if (cur) traceKernel<false, 1><<<traceBlocks, TRACE_BLOCK, 0, stream>>>(mp, c.mesh);
+        else traceKernel<false, 0><<<traceBlocks, TRACE_BLOCK, 0, stream>>>(mp, c.mesh);
+    }
     if (ev) cudaEventRecord(ev[1], stream);
     meshShadeKernel<<<shadeBlocks, shadeThreads, 0, stream>>>(mp, shadeScene(c), c.cam, cur);
     if (ev) cudaEventRecord(ev[2], stream);
@@ -415,12 +420,13 @@ void crtRunMesh(RendererContext& c, int ns) {
     mp.traceMinActive = c.opts.reserved[2] > 0 ? c.opts.reserved[2] : TRACE_MIN_ACTIVE;
     if (!c.traceBlocks) {
         int perSM = 0;
-        CRT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, traceKernel<false>, TRACE_BLOCK, 0));
+        CRT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, traceKernel<false, 0>, TRACE_BLOCK, 0));
         c.traceBlocks = c.numSMs * (perSM > 0 ? perSM : 1); // persistent: exactly one resident wave
     }
     cudaStream_t stream = c.stream;
 
     std::memset(&c.stats, 0, sizeof(c.stats));
+    c.chaserRays = c.chaserShadowRays = c.chaserNodeVisits = c.chaserTriTests = 0;
     c.stats.samples = (unsigned long long)npix * (unsigned long long)(ns > 0 ? ns : 0);
     CRT_CHECK(cudaEventRecord(c.evStart, stream));
     CRT_CHECK(cudaMemsetAsync(mp.accum, 0, (size_t)npix * sizeof(float4), stream));
@@ -436,8 +442,8 @@ void crtRunMesh(RendererContext& c, int ns) {
         int batch = c.opts.megaBatch > 0 ? c.opts.megaBatch : 16;
         batch = (batch + 1) & ~1; // even: the two queue sets swap roles every iteration
         const char* lanesEnv = std::getenv("CRT_EXPRESS_LANE");
-        const bool lanes = !g_profiling && !(lanesEnv && lanesEnv[0] == '0') && c.traceBlocks >= 2 * c.numSMs;
-        if (g_profiling) {
+        const bool lanes = g_profiling != 1 && !(lanesEnv && lanesEnv[0] == '0') && c.traceBlocks >= 2 * c.numSMs;
+        if (g_profiling == 1) {
             cudaEvent_t ev[3];
             for (auto& e : ev) CRT_CHECK(cudaEventCreate(&e));
             c.stats.profiled = 1;
@@ -508,6 +514,7 @@ void crtRunMesh(RendererContext& c, int ns) {
                 CRT_CHECK(cudaMemsetAsync(c.laneSums, 0, 8 * sizeof(unsigned long long), stream));
             }
             const bool dumpLanes = std::getenv("CRT_DUMP_LANES") != nullptr;
+            std::vector<cudaEvent_t> profEvents;
             unsigned int* hostRing = (unsigned int*)c.hostCtlFast;
             const auto t0 = std::chrono::steady_clock::now();
             bool last = false;
@@ -523,11 +530,29 @@ void crtRunMesh(RendererContext& c, int ns) {
                     launchWave(last ? lastWaveBlocks : waveBlocks);
                 }
                 if (last) break;
-                CRT_CHECK(cudaGraphLaunch(c.graphExec, stream));
+                if (g_profiling == 2) { // the timed configuration, launch by launch with events around every kernel (no graph, no extra sync)
+                    if (profEvents.empty()) {
+                        profEvents.resize(3 * (size_t)batch);
+                        for (auto& e : profEvents) CRT_CHECK(cudaEventCreate(&e));
+                        c.stats.profiled = 2;
+                    }
+                    for (int k = 0; k < batch; k++) launchMeshIteration(c, mp, stream, k & 1, blocksA, shadeBlocksA, &profEvents[3 * (size_t)k]);
+                } else {
+                    CRT_CHECK(cudaGraphLaunch(c.graphExec, stream));
+                }
                 launches += (unsigned long long)batch * MESH_KERNELS_PER_ITERATION;
                 CRT_CHECK(cudaMemcpyAsync(host, mp.ctl, sizeof(MeshControl), cudaMemcpyDeviceToHost, stream));
                 if (chase) CRT_CHECK(cudaMemcpyAsync(hostRing, ring.ctl, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
                 CRT_CHECK(cudaStreamSynchronize(stream));
+                if (g_profiling == 2) {
+                    for (int k = 0; k < batch; k++) {
+                        float msT = 0.0f, msS = 0.0f;
+                        cudaEventElapsedTime(&msT, profEvents[3 * (size_t)k], profEvents[3 * (size_t)k + 1]);
+                        cudaEventElapsedTime(&msS, profEvents[3 * (size_t)k + 1], profEvents[3 * (size_t)k + 2]);
+                        c.stats.msTrace += msT;
+                        c.stats.msShade += msS;
+                    }
+                }
                 const unsigned int live = host->traceCount[0] + host->shadeCount[0];
                 if (dumpLanes) {
                     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -542,6 +567,7 @@ void crtRunMesh(RendererContext& c, int ns) {
                 }
                 last = chase && live <= moveAllBelow; // the next hand-over takes everything that is left: no iteration follows it
             }
+            for (auto& e : profEvents) cudaEventDestroy(e);
             if (chase) { // wait for the chaser's waves, collect their ray counts
                 for (int k = 0; k < (wave < CHASE_STREAMS ? wave : CHASE_STREAMS); k++) CRT_CHECK(cudaStreamSynchronize(g_cache.chaseStreams[k]));
                 CRT_CHECK(cudaMemcpyAsync(hostRing, ring.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
@@ -551,6 +577,10 @@ void crtRunMesh(RendererContext& c, int ns) {
                 host->raysShadow += hc[1];
                 host->nodeVisits += hc[2];
                 host->triTests += hc[3];
+                c.chaserRays = hc[0];
+                c.chaserShadowRays = hc[1];
+                c.chaserNodeVisits = hc[2];
+                c.chaserTriTests = hc[3];
                 if (dumpLanes) {
                     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
                     std::fprintf(stderr, "lanes t=%.2f ms  chaser done: %llu extend + %llu shadow rays in %d waves\n", ms, hc[0], hc[1], wave);
@@ -638,6 +668,14 @@ extern "C" void setRendererCounting(int on) {
 extern "C" void getRendererTraversalCounts(unsigned long long* nodeVisits, unsigned long long* triTests) {
     if (nodeVisits) *nodeVisits = g_ctx.lastNodeVisits;
     if (triTests) *triTests = g_ctx.lastTriTests;
+}
+
+extern "C" void getRendererChaserCounts(unsigned long long* raysExtend, unsigned long long* raysShadow, unsigned long long* nodeVisits,
+                                        unsigned long long* triTests) {
+    if (raysExtend) *raysExtend = g_ctx.chaserRays;
+    if (raysShadow) *raysShadow = g_ctx.chaserShadowRays;
+    if (nodeVisits) *nodeVisits = g_ctx.chaserNodeVisits;
+    if (triTests) *triTests = g_ctx.chaserTriTests;
 }
 
 extern "C" void cleanupRenderer() {

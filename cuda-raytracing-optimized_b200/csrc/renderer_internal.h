@@ -62,6 +62,7 @@ struct RendererContext {
     int traceBlocks = 0; // persistent grid of traceKernel: one resident wave
     bool counting = false;
     unsigned long long lastNodeVisits = 0, lastTriTests = 0;
+    unsigned long long chaserRays = 0, chaserShadowRays = 0, chaserNodeVisits = 0, chaserTriTests = 0; // the chaser's share of the last frame
     renderer_stats stats = {};
 };
 

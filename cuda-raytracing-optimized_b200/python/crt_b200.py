@@ -122,7 +122,7 @@ DEVICE_SYMBOLS = [
     "initRenderer", "runRenderer", "cleanupRenderer", "setRendererOptions", "initRendererSpheres", "intersectBatch",
     "intersectBatchDevice", "generateRayBatchDevice", "rendererDeviceAlloc", "rendererDeviceFree", "rendererCopyToHost",
     "rendererCopyToDevice", "getRendererStats", "setRendererProfiling", "getRendererAccumDevice", "setRendererAccumDevice",
-    "finalizeFrame", "setRendererCounting", "getRendererTraversalCounts", "rendererDebugRead", "rendererReleaseCaches",
+    "finalizeFrame", "setRendererCounting", "getRendererTraversalCounts", "rendererDebugRead", "rendererReleaseCaches", "getRendererChaserCounts",
 ]
 
 
@@ -161,6 +161,7 @@ def device_lib():
         L.rendererDebugRead.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t]
         L.setRendererCounting.argtypes = [C.c_int]
         L.getRendererTraversalCounts.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+        L.getRendererChaserCounts.argtypes = [C.POINTER(C.c_ulonglong)] * 4
         _dev = L
     return _dev
 

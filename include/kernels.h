@@ -112,7 +112,9 @@ typedef struct renderer_stats {
 } renderer_stats;
 
 void getRendererStats(renderer_stats* out);
-// 1: time every kernel family with CUDA events (serialises the iteration; for roofline numbers).
+// 1: the wavefront alone, one synchronisation per iteration, CUDA events around each kernel family (diagnostics).
+// 2: the timed configuration (wavefront + chaser), launched kernel by kernel instead of as a graph with CUDA events around
+//    every trace and shade launch; msTrace / msShade are the sums, `iterations` the launch count (roofline numbers).
 void setRendererProfiling(int on);
 
 // Multi-GPU support: the per-pixel un-normalised radiance sums (float4 per
@@ -130,6 +132,9 @@ size_t rendererDebugRead(const char* name, void* dst, size_t maxBytes);
 // internal-node visits (two slab tests each) and triangle tests.  Never on in timed runs.
 void setRendererCounting(int on);
 void getRendererTraversalCounts(unsigned long long* nodeVisits, unsigned long long* triTests);
+// The part of the last frame that chaseKernel did (visits/tests only in counting builds); the rest was traced by traceKernel.
+void getRendererChaserCounts(unsigned long long* raysExtend, unsigned long long* raysShadow, unsigned long long* nodeVisits,
+                             unsigned long long* triTests);
 
 #ifdef __cplusplus
 }
