@@ -188,6 +188,7 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner must not share stdout with the JSON line
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     L = crt.device_lib()  # raises when the CUDA library is missing: no fallback
@@ -359,7 +360,7 @@ def run_ours(args, rank, world, local_rank):
                 rays_per_step=int(total_rays), msamples_per_s=nx * ny * ns_total / (ms_per_step * 1e3), wall_ms_per_step=wall_ms / args.steps,
                 clocks=clocks, e2e=dict(value=e2e_value, unit="Mrays/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                                         ms_per_step=e2e_ms, steps=e2e_steps,
-                                        note="initRenderer (scene upload from caller-owned host memory) + runRenderer + frame read, per step"),
+                                        note="initRenderer (scene upload from caller-owned host memory) + runRenderer + frame read + cleanupRenderer, per step"),
                 gpu_launches=launches, roofline=roof, cpu_baseline=cpu, **extra)
     print(json.dumps(line))
     if dist:
@@ -446,12 +447,19 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", str(29400 + os.getpid() % 500)] + sys.argv
         sys.exit(subprocess.call(cmd))
+    # Anything a library prints on stdout (NCCL's version banner, for one) must not mix with the ONE JSON line: file
+    # descriptor 1 points at stderr while the benchmark runs, print() goes to the saved original stdout.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         run_reference(args, rank, world)
     elif args.workload == "raybatch":
         run_raybatch(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
+    real_stdout.flush()
 
 
 if __name__ == "__main__":
