@@ -12,9 +12,11 @@
 //     (2 L1 requests per step instead of 3; an earlier 96-byte record with a pre-swapped copy per direction sign cost
 //     no selects but a third of the L1 lines held dead copies). The slab test's swap of t0/t1 when invD < 0
 //     (intersections.h:30) is a select after the two products;
-//   * triangles: 48-byte tiles {v0, e1 = v1-v0, e2 = v2-v0} in three float4
-//     (the subtractions are the ones triangleHit does first; precomputing them
-//     does not change a bit), +inf in v0.x marks an unused leaf slot.
+//   * triangles: packed per leaf. A leaf of N slots is N 32-byte blocks {v0.xyz, e1.xyz, e2.xy} followed by one tail block
+//     with the N values e2.z (padded to a multiple of 32 bytes): 192 bytes for N = 5 instead of 5 x 48, one 256-bit load
+//     plus one 32-bit load (all N of them hit one sector) per test instead of three 128-bit loads, and 9 registers per tile
+//     instead of 12. e1 = v1-v0 and e2 = v2-v0 are the subtractions triangleHit does first; precomputing them does not
+//     change a bit. +inf in v0.x marks an unused leaf slot.
 #pragma once
 
 #include <cfloat>
@@ -22,13 +24,12 @@
 #include "vecmath.cuh"
 
 #define RT_EPSILON 0.01f // kernels.cu:19
-#ifndef TRI_F4
-#define TRI_F4 3 // float4 per traversal tile: 3 = 48-byte tiles; 4 = 64-byte tiles fetched with one 256-bit + one 32-bit load
-#endif
+
 
 struct MeshView {
     const float4* __restrict__ nodes; // 4 float4 per internal node index (see travNodeStep / swizzleNodesKernel)
-    const float4* __restrict__ tris;  // 3 float4 per triangle slot
+    const float4* __restrict__ tris;  // packed leaves, leafBytes each (see above)
+    unsigned int leafBytes;           // 32 * N + 32 * ceil(N / 8)
     unsigned int firstLeaf;
     unsigned int primsPerLeaf;
     f3 boundsMin, boundsMax;

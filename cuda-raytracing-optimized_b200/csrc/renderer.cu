@@ -288,10 +288,15 @@ extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb,
     // triangles: upload the caller's 64-byte records once, re-tile on the device, drop the staging copy
     float* staging = (float*)arenaAlloc((size_t)(numSlots ? numSlots : 1) * sizeof(triangle));
     CRT_CHECK(cudaMemcpy(staging, m->tris, (size_t)numSlots * sizeof(triangle), cudaMemcpyHostToDevice));
-    c.triGeom = devAlloc<float4>(TRI_F4 * (size_t)numSlots + 8);
+    const unsigned int primsPerLeaf = sc.numPrimitivesPerLeaf > 0 ? (unsigned int)sc.numPrimitivesPerLeaf : 1u;
+    const unsigned int leafBytes = 32u * primsPerLeaf + 32u * ((primsPerLeaf + 7u) / 8u);
+    const size_t numLeaves = ((size_t)numSlots + primsPerLeaf - 1) / primsPerLeaf;
+    const size_t geomBytes = (numLeaves + 1) * leafBytes + 256; // (+1: the tail-mode prefetch of a leaf pair may touch the next leaf)
+    c.triGeom = (float4*)arenaAlloc(geomBytes);
+    CRT_CHECK(cudaMemset(c.triGeom, 0, geomBytes));
     c.triShade = devAlloc<float4>(3 * (size_t)numSlots);
     if (numSlots) {
-        retileTrianglesKernel<<<(numSlots + 255) / 256, 256>>>(staging, numSlots, c.triGeom, c.triShade);
+        retileTrianglesKernel<<<(numSlots + 255) / 256, 256>>>(staging, numSlots, primsPerLeaf, leafBytes, (float*)c.triGeom, c.triShade);
         CRT_CHECK(cudaGetLastError());
     }
     c.numTriSlots = numSlots;
@@ -314,6 +319,7 @@ extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb,
     c.mesh.tris = c.triGeom;
     c.mesh.firstLeaf = firstLeaf;
     c.mesh.primsPerLeaf = (unsigned int)sc.numPrimitivesPerLeaf;
+    c.mesh.leafBytes = leafBytes;
     c.mesh.boundsMin = toF3(m->bounds.min);
     c.mesh.boundsMax = toF3(m->bounds.max);
 

@@ -84,36 +84,19 @@ __device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
 // and 2*idx+1 are adjacent), or -- on the last internal level -- its triangles lie in the 2*N tiles that start at leaf
 // 2*idx - firstLeaf. Requesting those lines into L1 now overlaps the next step's memory latency with this step's slab
 // tests. Used when a launch has too few rays to hide latency with other warps (the tail of a frame).
-#ifndef CRT_V_LEAFPF
-#define CRT_V_LEAFPF 0
-#endif
-#ifndef CRT_V_NODEPF
-#define CRT_V_NODEPF 0
-#endif
-// The leaf a traversal has just arrived at: request its tiles now, the triangle tests start a scheduling round later.
-__device__ __forceinline__ void prefetchLeaf(const MeshView& m, unsigned int idx) {
-    const char* p = (const char*)(m.tris + TRI_F4 * ((idx - m.firstLeaf) * m.primsPerLeaf));
-    const unsigned int bytes = m.primsPerLeaf * (16u * TRI_F4);
-    for (unsigned int o = 0; o < bytes; o += 128u) prefetchL1(p + o);
-    prefetchL1(p + bytes - 16u);
-}
-
 template <bool PREFETCH>
 __device__ __forceinline__ void travNodeStep(const MeshView& m, const RayHot& r, TravHot& s) {
     const char* rec = (const char*)m.nodes + 64u * s.idx;
     float4 qx, qy;
     ldg256(rec, qx, qy);
     const float4 qz = __ldg((const float4*)(rec + 32));
-    if (!PREFETCH && CRT_V_NODEPF) {
-        if (2u * s.idx < m.firstLeaf) prefetchL1((const char*)m.nodes + 128u * s.idx);
-    }
     if (PREFETCH) {
         const unsigned int child = 2u * s.idx;
         if (child < m.firstLeaf) {
             prefetchL1((const char*)m.nodes + 64u * child);
         } else {
-            const float4* p = m.tris + TRI_F4 * ((child - m.firstLeaf) * m.primsPerLeaf);
-            const unsigned int bytes = 2u * m.primsPerLeaf * (16u * TRI_F4);
+            const char* p = (const char*)m.tris + (size_t)(child - m.firstLeaf) * m.leafBytes;
+            const unsigned int bytes = 2u * m.leafBytes;
             for (unsigned int o = 0; o < bytes; o += 128u) prefetchL1((const char*)p + o);
             prefetchL1((const char*)p + bytes - 16u);
         }
@@ -135,9 +118,6 @@ __device__ __forceinline__ void travNodeStep(const MeshView& m, const RayHot& r,
     } else {
         travPop(s);
     }
-    if (!PREFETCH && CRT_V_LEAFPF) {
-        if (s.idx >= m.firstLeaf) prefetchLeaf(m, s.idx);
-    }
 }
 
 // One leaf visit (kernels.cu:198-217). An any-hit ray that finds a triangle is finished: closest = 0.0f is what the
@@ -145,26 +125,19 @@ __device__ __forceinline__ void travNodeStep(const MeshView& m, const RayHot& r,
 __device__ __forceinline__ void travLeafStep(const MeshView& m, const RayHot& r, RayCold& c, float tMin, bool anyHit, TravHot& s,
                                              unsigned int& triTests) {
     const unsigned int first = (s.idx - m.firstLeaf) * m.primsPerLeaf;
-    if (!CRT_V_LEAFPF) {   // the leaf's tiles are contiguous (N * 48 bytes): request all of its lines before the first test
-        const char* p = (const char*)(m.tris + TRI_F4 * first);
-        const unsigned int bytes = m.primsPerLeaf * (16u * TRI_F4);
-        for (unsigned int o = 128u; o < bytes; o += 128u) prefetchL1(p + o);
-        prefetchL1(p + bytes - 16u);
+    const char* leaf = (const char*)m.tris + (size_t)(s.idx - m.firstLeaf) * m.leafBytes;
+    {   // the leaf is contiguous (leafBytes): request all of its lines before the first test
+        for (unsigned int o = 128u; o < m.leafBytes; o += 128u) prefetchL1(leaf + o);
+        prefetchL1(leaf + m.leafBytes - 16u);
     }
     RayPrep rp;
     rp.o = mk3(r.ox, r.oy, r.oz);
     rp.d = xyz(c.dir);
     for (unsigned int i = 0; i < m.primsPerLeaf; i++) {
-        // all 48 bytes of the tile are requested together (one round trip); unused slots are readable padding
-#if TRI_F4 == 4
+        // 8 of the tile's 9 floats with one 256-bit load, e2.z from the leaf's tail block (one sector for the whole leaf)
         float4 t0, t1, t2;
-        ldg256(m.tris + 4 * (first + i), t0, t1);
-        t2.x = __ldg((const float*)(m.tris + 4 * (first + i) + 2));
-#else
-        const float4 t0 = __ldg(m.tris + 3 * (first + i));
-        const float4 t1 = __ldg(m.tris + 3 * (first + i) + 1);
-        const float4 t2 = __ldg(m.tris + 3 * (first + i) + 2);
-#endif
+        ldg256(leaf + 32u * i, t0, t1);
+        t2.x = __ldg((const float*)(leaf + 32u * m.primsPerLeaf) + i);
         if (isinf(t0.x)) break;
         triTests++;
         float u, v;
@@ -182,9 +155,6 @@ __device__ __forceinline__ void travLeafStep(const MeshView& m, const RayHot& r,
         }
     }
     travPop(s);
-    if (CRT_V_LEAFPF) {
-        if (s.idx >= m.firstLeaf) prefetchLeaf(m, s.idx);
-    }
 }
 
 // One scheduling round of a warp (all 32 lanes call it together; it does not change any lane's own sequence of steps):
