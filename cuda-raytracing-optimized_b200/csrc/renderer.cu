@@ -6,7 +6,9 @@
 //   cleanupRenderer  kernels.cu:666-680
 // and keeps the reference's error behaviour (check_cuda, kernels.cu:30-37).
 // There is no CPU fallback: without a CUDA device every entry point exits(99).
+#include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

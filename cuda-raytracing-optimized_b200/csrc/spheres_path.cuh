@@ -47,6 +47,81 @@ __global__ void __launch_bounds__(WF_BLOCK) extendSpheresKernel(WfState st, cons
     }
 }
 
+// ---- sphere BVH ----------------------------------------------------------------------------------------------------
+// 488 tests per ray is what the README-era kernel did; the result of that loop is `min over spheres of r_s`, where r_s is
+// the sphere's first root in (t_min, inf) (sphereHit, intersections.h:85-104, tries the near root, then the far one), ties
+// going to the lowest index (the loop accepts on strict `<` in index order). That is a property of the set of spheres, not
+// of the loop, so any traversal that (a) never skips a sphere whose r_s could win and (b) breaks ties by index returns the
+// same bits. The spheres are put into a small BVH at init (host, median split, <= 4 per leaf, boxes padded by 1 % of the
+// radius + 1e-3: three orders of magnitude more than the rounding of r_s for these sizes); spheres too large for that
+// margin (radius > 100: the ground sphere, whose roots lose ~1e-3 to cancellation) stay in a list that every ray tests.
+// The tree is stored depth-first with skip links (no stack): node i's subtree is [i+1, skip_i).
+struct SphereBvh {
+    const float4* __restrict__ nodes;   // 2 per node: {bmin.xyz, skip}{bmax.xyz, first | count << 24 (0xFFFFFFFF = internal)}
+    const float4* __restrict__ spheres; // leaf order: {center.xyz, radius}
+    const unsigned int* __restrict__ ids; // leaf order -> index the caller gave the sphere
+    unsigned int numNodes;
+    unsigned int numAlways;             // spheres[0 .. numAlways) are tested by every ray
+};
+
+__device__ __forceinline__ void testSphere(const SphereBvh& b, unsigned int k, const f3& o, const f3& d, float& closest, unsigned int& id) {
+    const float4 sp = __ldg(b.spheres + k);
+    const float t = sphereHitT(xyz(sp), sp.w, o, d, RT_EPSILON, FLT_MAX); // r_s: does not depend on the current closest
+    if (t < FLT_MAX) {
+        const unsigned int s = __ldg(b.ids + k);
+        if (t < closest || (t == closest && s < id)) {
+            closest = t;
+            id = s;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(WF_BLOCK) extendSpheresBvhKernel(WfState st, const unsigned int* __restrict__ queue, SphereBvh bvh) {
+    WfControl* ctl = st.ctl;
+    const unsigned int n = ctl->countActive;
+    while (true) {
+        unsigned int base = 0;
+        if (laneId() == 0) base = atomicAdd(&ctl->cursorExtend, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        const unsigned int i = base + laneId();
+        if (i < n) {
+            const unsigned int slot = queue[i];
+            const float4 ro = st.rayO[slot];
+            const float4 rd = st.rayD[slot];
+            const f3 o = xyz(ro);
+            const f3 d = unit(xyz(rd));
+            const f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+            float closest = FLT_MAX;
+            unsigned int id = 0xFFFFFFFFu;
+            for (unsigned int k = 0; k < bvh.numAlways; k++) testSphere(bvh, k, o, d, closest, id);
+            unsigned int node = 0;
+            while (node < bvh.numNodes) {
+                const float4 lo = __ldg(bvh.nodes + 2 * node);
+                const float4 hi = __ldg(bvh.nodes + 2 * node + 1);
+                // conservative slab test: fminf/fmaxf drop the NaN of 0 * inf (an axis the ray is parallel to)
+                const float x0 = (lo.x - o.x) * inv.x, x1 = (hi.x - o.x) * inv.x;
+                const float y0 = (lo.y - o.y) * inv.y, y1 = (hi.y - o.y) * inv.y;
+                const float z0 = (lo.z - o.z) * inv.z, z1 = (hi.z - o.z) * inv.z;
+                const float tEnter = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+                const float tExit = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+                const bool hitBox = tEnter <= tExit * 1.00001f + 1e-5f && tEnter <= closest;
+                const unsigned int leaf = __float_as_uint(hi.w);
+                if (!hitBox) {
+                    node = __float_as_uint(lo.w); // skip the subtree
+                } else {
+                    if (leaf != 0xFFFFFFFFu) {
+                        const unsigned int first = leaf & 0xFFFFFFu, count = leaf >> 24;
+                        for (unsigned int k = 0; k < count; k++) testSphere(bvh, first + k, o, d, closest, id);
+                    }
+                    node = node + 1;
+                }
+            }
+            st.hit[slot] = make_float4(closest, 0.0f, 0.0f, __uint_as_float(id));
+        }
+    }
+}
+
 __global__ void __launch_bounds__(WF_BLOCK) shadeSpheresKernel(WfState st, const float4* __restrict__ mats, int maxDepth,
                                                                const unsigned int* __restrict__ queue, unsigned int* __restrict__ nextQueue) {
     WfControl* ctl = st.ctl;
@@ -126,6 +201,75 @@ __global__ void __launch_bounds__(WF_BLOCK) shadeSpheresKernel(WfState st, const
     }
 }
 
+// Host side of the sphere BVH (layout: SphereBvh above). Median split of the centroids along the longest axis.
+static SphereBvh g_sphereBvh;
+
+static void buildSphereBvh(RendererContext& c, const std::vector<float4>& sp, int n) {
+    std::vector<unsigned int> always, rest;
+    for (int i = 0; i < n; i++) (sp[i].w > 100.0f ? always : rest).push_back((unsigned int)i);
+    std::vector<float4> nodes, leafSpheres;
+    std::vector<unsigned int> leafIds;
+    for (unsigned int i : always) { leafSpheres.push_back(sp[i]); leafIds.push_back(i); }
+    struct Builder {
+        const std::vector<float4>& sp;
+        std::vector<float4>& nodes;
+        std::vector<float4>& leafSpheres;
+        std::vector<unsigned int>& leafIds;
+        void build(std::vector<unsigned int>& idx, size_t lo, size_t hi) {
+            float bmin[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, bmax[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            float cmin[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, cmax[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            for (size_t k = lo; k < hi; k++) {
+                const float4 s = sp[idx[k]];
+                const float ce[3] = {s.x, s.y, s.z};
+                for (int a = 0; a < 3; a++) {
+                    const float pad = s.w * 1.01f + 1e-3f + 1e-5f * std::fabs(ce[a]);
+                    bmin[a] = std::min(bmin[a], ce[a] - pad);
+                    bmax[a] = std::max(bmax[a], ce[a] + pad);
+                    cmin[a] = std::min(cmin[a], ce[a]);
+                    cmax[a] = std::max(cmax[a], ce[a]);
+                }
+            }
+            const size_t me = nodes.size() / 2;
+            nodes.push_back(make_float4(bmin[0], bmin[1], bmin[2], 0.0f));
+            nodes.push_back(make_float4(bmax[0], bmax[1], bmax[2], 0.0f));
+            unsigned int leafWord = 0xFFFFFFFFu;
+            if (hi - lo <= 4) {
+                leafWord = (unsigned int)leafSpheres.size() | ((unsigned int)(hi - lo) << 24);
+                for (size_t k = lo; k < hi; k++) { leafSpheres.push_back(sp[idx[k]]); leafIds.push_back(idx[k]); }
+            } else {
+                int axis = 0;
+                for (int a = 1; a < 3; a++) if (cmax[a] - cmin[a] > cmax[axis] - cmin[axis]) axis = a;
+                const size_t mid = (lo + hi) / 2;
+                std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](unsigned int p, unsigned int q) {
+                    const float a = axis == 0 ? sp[p].x : axis == 1 ? sp[p].y : sp[p].z;
+                    const float b = axis == 0 ? sp[q].x : axis == 1 ? sp[q].y : sp[q].z;
+                    return a < b || (a == b && p < q);
+                });
+                build(idx, lo, mid);
+                build(idx, mid, hi);
+            }
+            const unsigned int skip = (unsigned int)(nodes.size() / 2);
+            std::memcpy(&nodes[2 * me].w, &skip, 4);
+            std::memcpy(&nodes[2 * me + 1].w, &leafWord, 4);
+        }
+    } builder{sp, nodes, leafSpheres, leafIds};
+    if (!rest.empty()) builder.build(rest, 0, rest.size());
+    if (leafSpheres.empty()) { leafSpheres.push_back(make_float4(0, 0, 0, 0)); leafIds.push_back(0); }
+    if (nodes.empty()) { nodes.push_back(make_float4(0, 0, 0, 0)); nodes.push_back(make_float4(0, 0, 0, 0)); }
+    float4* dNodes = (float4*)arenaAlloc(nodes.size() * sizeof(float4));
+    float4* dSpheres = (float4*)arenaAlloc(leafSpheres.size() * sizeof(float4));
+    unsigned int* dIds = (unsigned int*)arenaAlloc(leafIds.size() * sizeof(unsigned int));
+    CRT_CHECK(cudaMemcpy(dNodes, nodes.data(), nodes.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CRT_CHECK(cudaMemcpy(dSpheres, leafSpheres.data(), leafSpheres.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CRT_CHECK(cudaMemcpy(dIds, leafIds.data(), leafIds.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
+    g_sphereBvh.nodes = dNodes;
+    g_sphereBvh.spheres = dSpheres;
+    g_sphereBvh.ids = dIds;
+    g_sphereBvh.numNodes = rest.empty() ? 0u : (unsigned int)(nodes.size() / 2);
+    g_sphereBvh.numAlways = (unsigned int)always.size();
+    (void)c;
+}
+
 extern "C" void initRendererSpheres(const sphere* spheres, const material* materials, int n, const camera cam, vec3** fb, int nx,
                                     int ny, int maxDepth) {
     RendererContext& c = g_ctx;
@@ -150,14 +294,18 @@ extern "C" void initRendererSpheres(const sphere* spheres, const material* mater
         mats[2 * i + 1] = b;
     }
     CRT_CHECK(cudaMemcpyToSymbol(c_spheres, sp.data(), (size_t)n * sizeof(float4)));
+    buildSphereBvh(c, sp, n);
     c.materials = (float4*)arenaAlloc(mats.size() * sizeof(float4));
     CRT_CHECK(cudaMemcpy(c.materials, mats.data(), mats.size() * sizeof(float4), cudaMemcpyHostToDevice));
 }
 
+static bool g_spheresBrute = false; // CRT_SPHERES_BRUTE=1: all spheres from __constant__ for every ray (tests compare the two)
+
 static void launchSphereIteration(RendererContext& c, cudaStream_t stream, unsigned int* qCur, unsigned int* qNext, int samplesPerSlot,
                                   int slotsPerPixel) {
     const int grid = c.numSMs * 8;
-    extendSpheresKernel<<<grid, WF_BLOCK, 0, stream>>>(c.wf, qCur, c.numSpheres);
+    if (g_spheresBrute) extendSpheresKernel<<<grid, WF_BLOCK, 0, stream>>>(c.wf, qCur, c.numSpheres); // the README-era loop, kept as the BVH's checker
+    else extendSpheresBvhKernel<<<grid, WF_BLOCK, 0, stream>>>(c.wf, qCur, g_sphereBvh);
     shadeSpheresKernel<<<grid, WF_BLOCK, 0, stream>>>(c.wf, c.materials, c.maxDepth, qCur, qNext);
     raygenKernel<false><<<grid, WF_BLOCK, 0, stream>>>(c.wf, c.cam, qNext, c.nx, c.ny, samplesPerSlot, slotsPerPixel, c.opts.sampleStream);
     advanceKernel<<<1, 1, 0, stream>>>(c.wf.ctl);
@@ -168,6 +316,10 @@ void crtRunSpheres(RendererContext& c, int ns) {
     int slotsPerPixel = c.opts.reserved[0] > 0 ? c.opts.reserved[0] : 1;
     if (ns % slotsPerPixel != 0) slotsPerPixel = 1;
     const int samplesPerSlot = ns / slotsPerPixel;
+    {
+        const char* v = std::getenv("CRT_SPHERES_BRUTE");
+        g_spheresBrute = v && v[0] == '1';
+    }
     allocWavefront(c, npix * (unsigned int)slotsPerPixel);
     cudaStream_t stream = c.stream;
     std::memset(&c.stats, 0, sizeof(c.stats));
@@ -185,7 +337,7 @@ void crtRunSpheres(RendererContext& c, int ns) {
         int batch = c.opts.megaBatch > 0 ? c.opts.megaBatch : 16;
         batch = (batch + 1) & ~1;
         const long long key = ((long long)samplesPerSlot << 24) ^ ((long long)slotsPerPixel << 8) ^ batch ^ (1LL << 61) ^
-                              ((long long)c.maxDepth << 40);
+                              ((long long)c.maxDepth << 40) ^ ((long long)g_spheresBrute << 58);
         if (!c.graphExec || c.graphKey != key) {
             if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
             cudaGraph_t graph;

@@ -66,6 +66,22 @@ def test_spheres_vs_golden_reference_derived_frame(crt):
     assert within >= 0.999 and psnr >= 50.0 and exact >= 0.98, (within, psnr, exact)
 
 
+def test_sphere_bvh_equals_the_brute_force_loop(crt, monkeypatch):
+    """The sphere BVH returns, ray by ray, what the loop over all spheres returns (closest root, ties to the lowest index):
+    whole frames are bit-identical, ray counts equal."""
+    nx, ny, ns = 300, 200, 8
+    monkeypatch.setenv("CRT_SPHERES_BRUTE", "1")
+    with crt.Frame(crt.rtiow_scene(1), nx, ny, 50) as fr:
+        brute = fr.run(ns)
+        rays_brute = crt.stats().raysExtend
+    monkeypatch.delenv("CRT_SPHERES_BRUTE")
+    with crt.Frame(crt.rtiow_scene(1), nx, ny, 50) as fr:
+        bvh = fr.run(ns)
+        rays_bvh = crt.stats().raysExtend
+    assert rays_bvh == rays_brute and rays_bvh > nx * ny * ns
+    assert np.array_equal(bvh, brute)
+
+
 def test_ray_batch_vs_golden_hitmesh(crt, small_scene):
     z = np.load(os.path.join(G, "rays_8192.npz"))
     with crt.Frame(small_scene, 8, 8, 1):
