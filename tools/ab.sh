@@ -1,6 +1,7 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python tools/parity_report.py --detail 0.25 --tex 64 --nx 1200 --ny 800 --ns 100 --rays 65536 --steps 2 --spheres 2>&1 | grep SPHERES | cut -c1-600
-CRT_SPHERES_BRUTE=1 python bench.py --workload rtiow --steps 2 --warmup 3 2>/dev/null | cut -c1-700
-python bench.py --workload rtiow --steps 2 --warmup 3 2>/dev/null | cut -c1-900
-python bench.py --workload rtiow --impl reference --steps 2 --warmup 1 2>/dev/null | cut -c1-500
+timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python tools/render_once.py --nx 240 --ny 160 --ns 12 --detail 0.25 --tex 64 --steps 1 2>&1 | tail -8
+echo "memcheck rc=$?"
+timeout 600 compute-sanitizer --tool racecheck --error-exitcode 7 python tools/render_once.py --nx 160 --ny 100 --ns 8 --detail 0.25 --tex 64 --steps 1 2>&1 | tail -8
+echo "racecheck rc=$?"
+timeout 600 compute-sanitizer --tool initcheck --error-exitcode 7 python tools/render_once.py --nx 160 --ny 100 --ns 8 --detail 0.25 --tex 64 --steps 1 2>&1 | tail -12
+echo "initcheck rc=$?"
