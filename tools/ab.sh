@@ -1,7 +1,8 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 7 python tools/render_once.py --nx 240 --ny 160 --ns 12 --detail 0.25 --tex 64 --steps 1 2>&1 | tail -8
-echo "memcheck rc=$?"
-timeout 600 compute-sanitizer --tool racecheck --error-exitcode 7 python tools/render_once.py --nx 160 --ny 100 --ns 8 --detail 0.25 --tex 64 --steps 1 2>&1 | tail -8
-echo "racecheck rc=$?"
-timeout 600 compute-sanitizer --tool initcheck --error-exitcode 7 python tools/render_once.py --nx 160 --ny 100 --ns 8 --detail 0.25 --tex 64 --steps 1 2>&1 | tail -12
-echo "initcheck rc=$?"
+for v in "" _top6 _top8 _top9; do
+  lib=build/libcrt_b200$v.so
+  echo "=== $lib batch"; CRT_B200_LIB=$lib python tools/batch_halves.py
+  echo "=== $lib nochase"; CRT_EXPRESS_LANE=0 CRT_B200_LIB=$lib python tools/render_once.py --steps 1 | tail -1 | cut -c1-60
+  echo "=== $lib frame"; CRT_B200_LIB=$lib python tools/render_once.py --steps 2 | tail -1 | cut -c1-60
+done
+CRT_B200_LIB=build/libcrt_b200_top8.so timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
