@@ -449,8 +449,8 @@ void crtRunMesh(RendererContext& c, int ns) {
 
         int batch = c.opts.megaBatch > 0 ? c.opts.megaBatch : 16;
         batch = (batch + 1) & ~1; // even: the two queue sets swap roles every iteration
-        const char* lanesEnv = std::getenv("CRT_EXPRESS_LANE");
-        const bool lanes = g_profiling != 1 && !(lanesEnv && lanesEnv[0] == '0') && c.traceBlocks >= 2 * c.numSMs;
+        const char* chaserEnv = std::getenv("CRT_CHASER"); // CRT_CHASER=0: the wavefront alone (diagnostics, tests)
+        const bool lanes = g_profiling != 1 && !(chaserEnv && chaserEnv[0] == '0') && c.traceBlocks >= 2 * c.numSMs;
         if (g_profiling == 1) {
             cudaEvent_t ev[3];
             for (auto& e : ev) CRT_CHECK(cudaEventCreate(&e));

@@ -66,6 +66,26 @@ def test_spheres_vs_golden_reference_derived_frame(crt):
     assert within >= 0.999 and psnr >= 50.0 and exact >= 0.98, (within, psnr, exact)
 
 
+def test_frames_survive_cache_release_and_size_changes(crt, small_scene, medium_scene):
+    """cleanupRenderer keeps the device arena / streams / pinned buffers for the next frame; a bigger frame, a smaller
+    frame, another scene and an explicit rendererReleaseCaches() in between must not change a bit."""
+    L = crt.device_lib()
+
+    def render(scene, nx, ny, ns):
+        with crt.Frame(scene, nx, ny, 16) as fr:
+            return fr.run(ns)
+
+    a = render(small_scene, 96, 64, 4)
+    b = render(medium_scene, 320, 200, 4)   # grows the arena
+    assert np.array_equal(render(small_scene, 96, 64, 4), a)   # shrinks again: same bits
+    L.rendererReleaseCaches()
+    assert np.array_equal(render(medium_scene, 320, 200, 4), b)
+    with crt.Frame(small_scene, 96, 64, 16) as fr:
+        L.rendererReleaseCaches()           # no-op while a frame is live
+        assert np.array_equal(fr.run(4), a)
+    L.rendererReleaseCaches()
+
+
 def test_sphere_bvh_equals_the_brute_force_loop(crt, monkeypatch):
     """The sphere BVH returns, ray by ray, what the loop over all spheres returns (closest root, ties to the lowest index):
     whole frames are bit-identical, ray counts equal."""
@@ -219,7 +239,7 @@ def test_frame_does_not_depend_on_who_runs_a_slot(crt, medium_scene, monkeypatch
     nx, ny, ns, depth = 400, 300, 16, 64
 
     def render(env):
-        for k in ("CRT_EXPRESS_LANE", "CRT_CHASE_MOVE_ALL", "CRT_CHASE_CAPACITY", "CRT_CHASE_LAG_PCT", "CRT_CHASE_TARGET", "CRT_CHASE_EXCLUSIVE_PCT"):
+        for k in ("CRT_CHASER", "CRT_CHASE_MOVE_ALL", "CRT_CHASE_CAPACITY", "CRT_CHASE_LAG_PCT", "CRT_CHASE_TARGET", "CRT_CHASE_EXCLUSIVE_PCT"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -230,7 +250,7 @@ def test_frame_does_not_depend_on_who_runs_a_slot(crt, medium_scene, monkeypatch
         crt.set_options()
         return img, st.raysExtend + st.raysShadow
 
-    wave, rays = render({"CRT_EXPRESS_LANE": "0"})
+    wave, rays = render({"CRT_CHASER": "0"})
     for env in ({"CRT_CHASE_MOVE_ALL": "100000000", "CRT_CHASE_CAPACITY": "100000000"},          # chaser alone
                 {"CRT_CHASE_MOVE_ALL": "0", "CRT_CHASE_LAG_PCT": "90", "CRT_CHASE_EXCLUSIVE_PCT": "50"},  # steady trickle of hand-overs
                 {"CRT_CHASE_MOVE_ALL": "60000", "CRT_CHASE_LAG_PCT": "60"},                          # big final hand-over mid-flight

@@ -17,7 +17,7 @@ scene = crt.Scene.staircase(1.0, 1024, 5)
 
 
 def render(env):
-    for k in ("CRT_EXPRESS_LANE", "CRT_CHASE_MOVE_ALL", "CRT_CHASE_CAPACITY"):
+    for k in ("CRT_CHASER", "CRT_CHASE_MOVE_ALL", "CRT_CHASE_CAPACITY"):
         os.environ.pop(k, None)
     os.environ.update(env)
     with crt.Frame(scene, nx, ny, 64) as fr:
@@ -26,7 +26,7 @@ def render(env):
     return img, st.raysExtend + st.raysShadow, st.msTotal
 
 
-a, ra, ta = render({"CRT_EXPRESS_LANE": "0"})
+a, ra, ta = render({"CRT_CHASER": "0"})
 b, rb, tb = render({"CRT_CHASE_MOVE_ALL": "100000000", "CRT_CHASE_CAPACITY": "100000000"})
 c1, rc1, tc1 = render({})
 c2, rc2, tc2 = render({})

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """GPU-box diagnostic: renders the benchmark frame with libcrt_b200.so only (no reference run) and prints device time,
-ray counts and iteration counts. Environment knobs of the library (CRT_DUMP_LANES, CRT_EXPRESS_LANE, ...) apply."""
+ray counts and iteration counts. Environment knobs of the library (CRT_DUMP_LANES, CRT_CHASER, ...) apply."""
 import argparse
 import json
 import os
