@@ -61,6 +61,7 @@ struct MeshState {
     float4* shC;    // FINAL only: {finished sample's colour, -}
     uint2* travS;   // parked any-hit traversal
     unsigned char* pending;
+    unsigned int* rngOut;  // the slot's RNG state after its last sample of this run (continueRenderer / checkpoints start from it)
     unsigned int* traceQ[2];
     unsigned int* shadeQ[2];
     float4* accum;
@@ -250,12 +251,15 @@ __device__ __forceinline__ ShadeResult shadePath(const MeshState& st, const Shad
         if (sample < st.samplesPerSlot) {
             startSample(st, cam, slot, rng, sample, p);
             out.traceNext = true;
+        } else {
+            st.rngOut[slot] = rng; // where the pixel's stream stands: a later continueRenderer() goes on from here
         }
     }
     return out;
 }
 
-__global__ void __launch_bounds__(WF_BLOCK) meshStartKernel(MeshState st, CameraDev cam) {
+// resume = 0: seed every slot (kernels.cu:541-542). resume = 1: continue the streams where the previous run left them.
+__global__ void __launch_bounds__(WF_BLOCK) meshStartKernel(MeshState st, CameraDev cam, int resume) {
     const unsigned int stride = gridDim.x * blockDim.x;
     for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < st.numSlots; base += stride) {
         const unsigned int slot = base + laneId();
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(WF_BLOCK) meshStartKernel(MeshState st, Camera
             const unsigned int stream = st.streamBase * (unsigned int)st.slotsPerPixel + slot / st.npix;
             st.pending[slot] = 0;
             PathRegs p;
-            startSample(st, cam, slot, pathSeed(pixel + stream * st.npix), 0, p); // kernels.cu:541-542 is stream 0
+            startSample(st, cam, slot, resume ? st.rngOut[slot] : pathSeed(pixel + stream * st.npix), 0, p); // kernels.cu:541-542 is stream 0
             storePath(st, slot, p, true);
         }
         const unsigned int pos = warpAppend(alive, &st.ctl->traceCount[0]);
@@ -274,7 +278,7 @@ __global__ void __launch_bounds__(WF_BLOCK) meshStartKernel(MeshState st, Camera
 }
 
 // ------------------------------------------------------------------- trace --
-#define TRACE_BUDGET 96        // default steps per ray per launch before it is parked
+#define TRACE_BUDGET 128       // default steps per ray per launch before it is parked
 #define TRACE_MIN_ACTIVE 20    // default: refill when fewer lanes than this hold a ray
 #ifndef TRACE_BLOCK
 #define TRACE_BLOCK 256

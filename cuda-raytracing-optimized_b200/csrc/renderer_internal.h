@@ -59,6 +59,7 @@ struct RendererContext {
     cudaGraphExec_t graphExec = nullptr;
     long long graphKey = -1;
 
+    int samplesDone = 0; // samples per pixel in the sums (runRenderer sets, continueRenderer adds)
     int traceBlocks = 0; // persistent grid of traceKernel: one resident wave
     bool counting = false;
     unsigned long long lastNodeVisits = 0, lastTriTests = 0;
@@ -69,5 +70,5 @@ struct RendererContext {
 extern RendererContext g_ctx;
 extern renderer_options g_opts;
 
-void crtRunMesh(RendererContext& c, int ns);
+void crtRunMesh(RendererContext& c, int ns, bool resume);
 void crtRunSpheres(RendererContext& c, int ns);

@@ -122,7 +122,8 @@ DEVICE_SYMBOLS = [
     "initRenderer", "runRenderer", "cleanupRenderer", "setRendererOptions", "initRendererSpheres", "intersectBatch",
     "intersectBatchDevice", "generateRayBatchDevice", "rendererDeviceAlloc", "rendererDeviceFree", "rendererCopyToHost",
     "rendererCopyToDevice", "getRendererStats", "setRendererProfiling", "getRendererAccumDevice", "setRendererAccumDevice",
-    "finalizeFrame", "setRendererCounting", "getRendererTraversalCounts", "rendererDebugRead", "rendererReleaseCaches", "getRendererChaserCounts",
+    "finalizeFrame", "setRendererCounting", "getRendererTraversalCounts", "rendererDebugRead", "rendererReleaseCaches", "getRendererChaserCounts", "continueRenderer", "getRendererSamplesDone",
+    "saveRendererCheckpoint", "loadRendererCheckpoint",
 ]
 
 
@@ -162,6 +163,9 @@ def device_lib():
         L.setRendererCounting.argtypes = [C.c_int]
         L.getRendererTraversalCounts.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
         L.getRendererChaserCounts.argtypes = [C.POINTER(C.c_ulonglong)] * 4
+        L.continueRenderer.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.saveRendererCheckpoint.argtypes = [C.c_char_p]
+        L.loadRendererCheckpoint.argtypes = [C.c_char_p]
         _dev = L
     return _dev
 
@@ -285,6 +289,11 @@ class Frame:
 
     def run(self, ns, copy=True):
         device_lib().runRenderer(ns, 8, 8)
+        return self.frame(copy)
+
+    def continue_run(self, ns_more, copy=True):
+        if device_lib().continueRenderer(ns_more, 8, 8) != 0:
+            raise RuntimeError("continueRenderer: nothing to continue")
         return self.frame(copy)
 
     def frame(self, copy=True):

@@ -124,6 +124,16 @@ void* getRendererAccumDevice();   // device pointer, nx*ny float4
 void setRendererAccumDevice(void* dAccum); // render into a caller-owned device buffer (e.g. a torch tensor) instead
 void finalizeFrame(int nsTotal);  // fb = accum / nsTotal (blocking)
 
+// Progressive rendering (mesh scenes, one slot per pixel). A pixel's samples are ONE RNG stream (reference
+// kernels.cu:542-548), so a frame can be continued exactly: runRenderer(a) followed by continueRenderer(b) leaves in fb the
+// bits runRenderer(a + b) would. saveRendererCheckpoint writes the running sums and the stream positions
+// ("CRTCKP01", nx, ny, samples done, stream, nx*ny float4, nx*ny uint32); loadRendererCheckpoint restores them after an
+// initRenderer of the same scene / size / sample stream (the reference's wish list, TODO.txt:70). Return 0 on success.
+int continueRenderer(int nsMore, int tx, int ty);
+int getRendererSamplesDone();
+int saveRendererCheckpoint(const char* path);
+int loadRendererCheckpoint(const char* path);
+
 // Diagnostic hook for tests: copy one per-slot array of the mesh pipeline ("rayO","rayD","atten","pcol","hit","shO","shD",
 // "shL","shC","accum"; float4 per slot / pixel) to the host. Returns the number of bytes copied (0 = unknown name).
 size_t rendererDebugRead(const char* name, void* dst, size_t maxBytes);

@@ -86,6 +86,29 @@ def test_frames_survive_cache_release_and_size_changes(crt, small_scene, medium_
     L.rendererReleaseCaches()
 
 
+def test_progressive_rendering_and_checkpoint_are_exact(crt, medium_scene, tmp_path):
+    """runRenderer(a) + continueRenderer(b) == runRenderer(a + b), bit for bit -- also through a checkpoint file and a fresh
+    initRenderer (a pixel's samples are one RNG stream, so the split is invisible)."""
+    nx, ny, depth = 320, 200, 64
+    L = crt.device_lib()
+    with crt.Frame(medium_scene, nx, ny, depth) as fr:
+        whole = fr.run(12)
+        part = fr.run(5)
+        assert L.getRendererSamplesDone() == 5
+        both = fr.continue_run(7)
+        assert L.getRendererSamplesDone() == 12
+        assert not np.array_equal(part, whole) and np.array_equal(both, whole)
+        fr.run(5)
+        ck = str(tmp_path / "frame.ckpt").encode()
+        assert L.saveRendererCheckpoint(ck) == 0
+    with crt.Frame(medium_scene, nx, ny, depth) as fr:      # a fresh renderer
+        assert L.continueRenderer(7, 8, 8) != 0             # nothing to continue yet
+        assert L.loadRendererCheckpoint(ck) == 0
+        assert np.array_equal(fr.continue_run(7), whole)
+    with crt.Frame(medium_scene, nx + 8, ny, depth):
+        assert L.loadRendererCheckpoint(ck) != 0            # another frame size
+
+
 def test_sphere_bvh_equals_the_brute_force_loop(crt, monkeypatch):
     """The sphere BVH returns, ray by ray, what the loop over all spheres returns (closest root, ties to the lowest index):
     whole frames are bit-identical, ray counts equal."""
