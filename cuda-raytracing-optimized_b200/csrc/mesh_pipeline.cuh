@@ -61,6 +61,7 @@ struct MeshState {
     float4* shC;    // FINAL only: {finished sample's colour, -}
     uint2* travS;   // parked any-hit traversal
     unsigned char* pending;
+    unsigned char* ready;  // 1 while the slot has an entry in the shade queue (its hit record waits to be shaded)
     unsigned int* rngOut;  // the slot's RNG state after its last sample of this run (continueRenderer / checkpoints start from it)
     unsigned int* traceQ[2];
     unsigned int* shadeQ[2];
@@ -268,6 +269,7 @@ __global__ void __launch_bounds__(WF_BLOCK) meshStartKernel(MeshState st, Camera
             const unsigned int pixel = slot % st.npix;
             const unsigned int stream = st.streamBase * (unsigned int)st.slotsPerPixel + slot / st.npix;
             st.pending[slot] = 0;
+            st.ready[slot] = 0;
             PathRegs p;
             startSample(st, cam, slot, resume ? st.rngOut[slot] : pathSeed(pixel + stream * st.npix), 0, p); // kernels.cu:541-542 is stream 0
             storePath(st, slot, p, true);
@@ -397,7 +399,10 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(
             baseShade = __shfl_sync(0xFFFFFFFFu, baseShade, 0);
             basePark = __shfl_sync(0xFFFFFFFFu, basePark, 0);
             const unsigned int below = (1u << lane) - 1u;
-            if (toShade) shadeQ[baseShade + __popc(mShade & below)] = slot;
+            if (toShade) {
+                shadeQ[baseShade + __popc(mShade & below)] = slot;
+                st.ready[slot] = 1;
+            }
             if (park) nextTrace[basePark + __popc(mPark & below)] = entry | ENTRY_RESUME;
 
             // ---- refill idle lanes, one atomic per warp
@@ -471,9 +476,19 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(
 #undef refillBelow
 
 // ------------------------------------------------------------------- shade --
+#ifndef SHADE_DENSE_FRACTION
+#define SHADE_DENSE_FRACTION 4 // sweep all slots in slot order when more than 1/4 of them wait to be shaded
+#endif
+// Two ways to find the work. SPARSE: walk the shade queue (entries in the order rays happened to finish: every state access
+// is a gather). DENSE, when most slots have an entry anyway (the bulk of a frame): sweep the slots in slot order and shade
+// those whose `ready` flag is set -- the same set, but state loads and stores are coalesced, neighbouring lanes are
+// neighbouring pixels (same materials, same texture lines), and the trace queue it writes comes out in slot order, so the
+// next trace launch gets coalesced refills and rays of neighbouring pixels in one warp.
 __global__ void __launch_bounds__(WF_BLOCK, 4) meshShadeKernel(MeshState st, ShadeScene sc, CameraDev cam, int cur) {
     MeshControl* ctl = st.ctl;
-    const unsigned int n = ctl->shadeCount[cur];
+    const unsigned int queued = ctl->shadeCount[cur];
+    const bool dense = queued > st.numSlots / SHADE_DENSE_FRACTION;
+    const unsigned int n = dense ? st.numSlots : queued;
     const unsigned int* __restrict__ queue = st.shadeQ[cur];
     unsigned int* __restrict__ nextTrace = st.traceQ[cur ^ 1];
     unsigned int* __restrict__ nextShade = st.shadeQ[cur ^ 1];
@@ -483,8 +498,8 @@ __global__ void __launch_bounds__(WF_BLOCK, 4) meshShadeKernel(MeshState st, Sha
         const unsigned int i = base + laneId();
         bool traceNext = false, castsShadow = false, defer = false;
         unsigned int slot = 0;
-        if (i < n) {
-            slot = queue[i];
+        if (i < n && (!dense || st.ready[i])) {
+            slot = dense ? i : queue[i];
             if (st.pending[slot]) {
                 defer = true; // its shadow ray is still in flight: keep bounce order, come back next iteration
             } else {
@@ -504,6 +519,7 @@ __global__ void __launch_bounds__(WF_BLOCK, 4) meshShadeKernel(MeshState st, Sha
                 traceNext = r.traceNext;
                 castsShadow = r.castsShadow;
                 if (traceNext) storePath(st, slot, p, !r.continued);
+                st.ready[slot] = 0;
             }
         }
         const unsigned int posDefer = warpAppend(defer, &ctl->shadeCount[cur ^ 1]);
@@ -895,6 +911,7 @@ __global__ void lanePartitionKernel(MeshState a, ChaseRing ring, const unsigned 
         if (toRing && !lagX) ring.entries[0][pos] = ringEntry;
         pos = warpAppend(toRing && lagX, &ring.ctl[8 + 2]);
         if (toRing && lagX) ring.entries[1][pos] = ringEntry;
+        if (toRing && !isTrace) a.ready[entry & ENTRY_SLOT_MASK] = 0; // the wavefront's dense shade sweep must not see the slot any more
         pos = warpAppend(valid && isTrace && !lag, &a.ctl->traceCount[1]);
         if (valid && isTrace && !lag) a.traceQ[1][pos] = entry;
         pos = warpAppend(valid && !isTrace && !lag, &a.ctl->shadeCount[1]);

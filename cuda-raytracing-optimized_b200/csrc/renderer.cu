@@ -194,6 +194,7 @@ static void allocMeshPipeline(RendererContext& c, unsigned int numSlots) {
     s.shC = devAlloc<float4>(numSlots);
     s.travS = devAlloc<uint2>(numSlots);
     s.pending = devAlloc<unsigned char>(numSlots);
+    s.ready = devAlloc<unsigned char>(numSlots);
     s.rngOut = devAlloc<unsigned int>(numSlots);
     for (int k = 0; k < 2; k++) {
         s.traceQ[k] = devAlloc<unsigned int>(2 * (size_t)numSlots); // at most one extend and one shadow entry per slot
