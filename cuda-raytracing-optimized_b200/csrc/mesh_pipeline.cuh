@@ -72,10 +72,23 @@ struct MeshState {
     int nx, ny;
     int samplesPerSlot;
     int slotsPerPixel;
+    unsigned int tilesX;   // > 0: slots enumerate the frame in 8x4 pixel tiles (tilesX tiles per row); 0: row by row
     unsigned int streamBase;
     int traceBudget;    // steps per ray per launch before it is parked
     int traceMinActive; // refill a warp when fewer lanes than this still traverse
 };
+
+// The pixel a slot renders. Slots are numbered tile by tile (8 wide, 4 high) when the frame divides into such tiles, so that
+// the 32 lanes of a warp -- consecutive slots wherever queues are in slot order -- are a compact patch of the image: their
+// rays start together, hit the same materials and texture lines, walk the same part of the tree. Which slot renders a
+// pixel changes nothing in the pixel (its RNG stream is seeded by the pixel's own index, kernels.cu:541-542).
+__device__ __forceinline__ unsigned int slotPixel(const MeshState& st, unsigned int slot) {
+    const unsigned int s = slot % st.npix;
+    if (st.tilesX == 0u) return s;
+    const unsigned int tile = s >> 5, o = s & 31u;
+    const unsigned int ty = tile / st.tilesX, tx = tile - ty * st.tilesX;
+    return (ty * 4u + (o >> 3)) * (unsigned int)st.nx + tx * 8u + (o & 7u);
+}
 
 __device__ __forceinline__ void accumulatePixel(const MeshState& st, unsigned int pixel, float r, float g, float b) {
     if (st.slotsPerPixel == 1) { // one slot per pixel: plain read-modify-write, in sample order (read from L2: the
@@ -100,7 +113,7 @@ struct PathRegs {
 
 // Starts sample `sample` of `slot`: kernels.cu:549-555.
 __device__ __forceinline__ void startSample(const MeshState& st, const CameraDev& cam, unsigned int slot, unsigned int rng, int sample, PathRegs& p) {
-    const unsigned int pixel = slot % st.npix;
+    const unsigned int pixel = slotPixel(st, slot);
     const int px = (int)(pixel % (unsigned int)st.nx), py = (int)(pixel / (unsigned int)st.nx);
     const float u = float(px + rnd(rng)) / float(st.nx);
     const float v = float(py + rnd(rng)) / float(st.ny);
@@ -141,7 +154,7 @@ struct ArraySink {
         if (flags & SHADOW_FLAG_FINAL) st.shC[slot] = mk4(carried, 0.0f);
         st.pending[slot] = 1;
     }
-    __device__ __forceinline__ void retire(const f3& c) { accumulatePixel(st, slot % st.npix, c.x, c.y, c.z); }
+    __device__ __forceinline__ void retire(const f3& c) { accumulatePixel(st, slotPixel(st, slot), c.x, c.y, c.z); }
 };
 
 // Everything between two hit() calls of color() (kernels.cu:402-531) for one path whose closest-hit record is `h`
@@ -266,7 +279,7 @@ __global__ void __launch_bounds__(WF_BLOCK) meshStartKernel(MeshState st, Camera
         const unsigned int slot = base + laneId();
         const bool alive = slot < st.numSlots;
         if (alive) {
-            const unsigned int pixel = slot % st.npix;
+            const unsigned int pixel = slotPixel(st, slot);
             const unsigned int stream = st.streamBase * (unsigned int)st.slotsPerPixel + slot / st.npix;
             st.pending[slot] = 0;
             st.ready[slot] = 0;
@@ -365,7 +378,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(
                     if (__float_as_uint(l.w) & SHADOW_FLAG_FINAL) {
                         float4 col = st.shC[slot];
                         if (unoccluded) { col.x += l.x; col.y += l.y; col.z += l.z; }
-                        accumulatePixel(st, slot % st.npix, col.x, col.y, col.z); // col += p.color (kernels.cu:558)
+                        accumulatePixel(st, slotPixel(st, slot), col.x, col.y, col.z); // col += p.color (kernels.cu:558)
                     } else if (unoccluded) {
                         float4 col = st.pcol[slot];
                         col.x += l.x; col.y += l.y; col.z += l.z;
@@ -608,7 +621,7 @@ struct ChaseSink {
         partner->lFlags = mk4(contribution, __uint_as_float(flags));
         partner->carried = mk4(carried, 0.0f);
     }
-    __device__ __forceinline__ void retire(const f3& c) { accumulatePixel(st, slot % st.npix, c.x, c.y, c.z); }
+    __device__ __forceinline__ void retire(const f3& c) { accumulatePixel(st, slotPixel(st, slot), c.x, c.y, c.z); }
 };
 
 __device__ __forceinline__ unsigned int ldVolatile(const unsigned int* p) { return *(const volatile unsigned int*)p; }
@@ -756,7 +769,7 @@ __global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(Mes
                 if (__float_as_uint(l.w) & SHADOW_FLAG_FINAL) {
                     float4 col = shadow.carried;
                     if (lit) { col.x += l.x; col.y += l.y; col.z += l.z; }
-                    accumulatePixel(st, slot % st.npix, col.x, col.y, col.z); // col += p.color (kernels.cu:558)
+                    accumulatePixel(st, slotPixel(st, slot), col.x, col.y, col.z); // col += p.color (kernels.cu:558)
                 } else if (lit) {
                     float4 col = path.color;
                     col.x += l.x; col.y += l.y; col.z += l.z;

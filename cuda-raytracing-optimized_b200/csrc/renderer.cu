@@ -426,6 +426,10 @@ void crtRunMesh(RendererContext& c, int ns, bool resume) {
     mp.samplesPerSlot = ns / slotsPerPixel;
     mp.slotsPerPixel = slotsPerPixel;
     mp.streamBase = c.opts.sampleStream;
+    {
+        const char* v = std::getenv("CRT_TILED_SLOTS"); // CRT_TILED_SLOTS=0: slots row by row (diagnostics)
+        mp.tilesX = (c.nx % 8 == 0 && c.ny % 4 == 0 && !(v && v[0] == '0')) ? (unsigned int)c.nx / 8u : 0u;
+    }
     mp.traceBudget = c.opts.reserved[1] > 0 ? c.opts.reserved[1] : TRACE_BUDGET;
     mp.traceMinActive = c.opts.reserved[2] > 0 ? c.opts.reserved[2] : TRACE_MIN_ACTIVE;
     if (!c.traceBlocks) {
@@ -649,6 +653,14 @@ extern "C" int continueRenderer(int nsMore, int tx, int ty) {
 
 extern "C" int getRendererSamplesDone() { return g_ctx.initialised ? g_ctx.samplesDone : 0; }
 
+static unsigned int hostSlotPixel(const MeshState& st, unsigned int slot) { // slotPixel() of mesh_pipeline.cuh on the host
+    const unsigned int s = slot % st.npix;
+    if (st.tilesX == 0u) return s;
+    const unsigned int tile = s >> 5, o = s & 31u;
+    const unsigned int ty = tile / st.tilesX, tx = tile - ty * st.tilesX;
+    return (ty * 4u + (o >> 3)) * (unsigned int)st.nx + tx * 8u + (o & 7u);
+}
+
 struct CheckpointHeader {
     char magic[8]; // "CRTCKP01"
     int nx, ny, samplesDone;
@@ -663,6 +675,11 @@ extern "C" int saveRendererCheckpoint(const char* path) {
     std::vector<unsigned int> rng(npix);
     CRT_CHECK(cudaMemcpy(sums.data(), c.wf.accum, npix * sizeof(float4), cudaMemcpyDeviceToHost));
     CRT_CHECK(cudaMemcpy(rng.data(), c.mp.rngOut, npix * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    if (c.mp.tilesX) { // the file is in pixel order, rngOut in slot order
+        std::vector<unsigned int> byPixel(npix);
+        for (size_t sidx = 0; sidx < npix; sidx++) byPixel[hostSlotPixel(c.mp, (unsigned int)sidx)] = rng[sidx];
+        rng.swap(byPixel);
+    }
     CheckpointHeader h;
     std::memcpy(h.magic, "CRTCKP01", 8);
     h.nx = c.nx; h.ny = c.ny; h.samplesDone = c.samplesDone; h.stream = c.opts.sampleStream;
@@ -691,6 +708,17 @@ extern "C" int loadRendererCheckpoint(const char* path) {
     if (!ok) return -3;
     allocMeshPipeline(c, (unsigned int)npix);
     c.mp.slotsPerPixel = 1;
+    c.mp.npix = (unsigned int)npix;
+    c.mp.nx = c.nx;
+    {
+        const char* v = std::getenv("CRT_TILED_SLOTS");
+        c.mp.tilesX = (c.nx % 8 == 0 && c.ny % 4 == 0 && !(v && v[0] == '0')) ? (unsigned int)c.nx / 8u : 0u;
+    }
+    if (c.mp.tilesX) {
+        std::vector<unsigned int> bySlot(npix);
+        for (size_t sidx = 0; sidx < npix; sidx++) bySlot[sidx] = rng[hostSlotPixel(c.mp, (unsigned int)sidx)];
+        rng.swap(bySlot);
+    }
     CRT_CHECK(cudaMemcpy(c.wf.accum, sums.data(), npix * sizeof(float4), cudaMemcpyHostToDevice));
     CRT_CHECK(cudaMemcpy(c.mp.rngOut, rng.data(), npix * sizeof(unsigned int), cudaMemcpyHostToDevice));
     c.samplesDone = h.samplesDone;
