@@ -35,7 +35,7 @@ EXTEND_BYTES_PER_RAY = 56   # queue entry 4 + {origin,rng} 16 + {dir,flags} 16 r
 SHADOW_BYTES_PER_RAY = 85   # entry 4 + {origin} 16 + {dir,dist} 16 + {contribution,flags} 16 read; colour 16 read + 16 written; pending 1
 RESUME_BYTES = 64           # a parked ray: state 8 + hit 16 + entry 4 written, then ray 32 + the same 28 read again
 BATCH_BYTES_PER_RAY = 52    # 32 in, 16 + 4 out
-TRACE_DRAM_BYTES_PER_LAUNCH = 409.5e6  # dram__bytes_read.sum + dram__bytes_write.sum of one bulk traceKernel launch (profiles/r01/d_trace_ncu_summary.txt)
+TRACE_DRAM_BYTES_PER_LAUNCH = 179.7e6  # dram__bytes_read.sum + dram__bytes_write.sum of one bulk traceKernel launch (profiles/r01/d_trace_ncu_summary.txt)
 
 
 def shard_samples(ns_total, world):

@@ -17,7 +17,9 @@
 
 #include "intersect.cuh"
 
-#define TRACE_NODE_QUORUM 16 // node steps run while this many lanes (or half of the rays the warp holds) stand on nodes
+#ifndef TRACE_NODE_QUORUM
+#define TRACE_NODE_QUORUM 16
+#endif // node steps run while this many lanes (or half of the rays the warp holds) stand on nodes
 
 // A ray while it is being traversed. The fields the node loop touches every step stay in registers (RayHot, TravHot);
 // the rest -- direction (needed by the triangle test only), the hit record and the queue entry -- lives in shared memory,
