@@ -111,6 +111,121 @@ __device__ __forceinline__ void coatBsdf(Scatter& out, const SurfacePoint& i, co
         diffuseBsdf(out, i, diffuseAlbedo, rng);
 }
 
+// ---- the rest of the reference's BSDF library (material.h) and its scene presets (scene_materials.h:22-93) -------------
+// None of these is reachable from the staircase material table (material_scatter only dispatches DIFFUSE / METAL / GLASS);
+// they are the reference's material "API surface" (SURVEY.md 8f rank 2). Checked against the reference's own device
+// functions through oracle/ref_shim.cu (scatterBatch below, tests/test_parity_gpu.py::test_bsdf_library_vs_reference).
+// checker_layer (material.h:33-36)
+__device__ __forceinline__ bool checkerLayer(const f3& p, float frequency) {
+    const float sines = sinf(frequency * p.x) * sinf(frequency * p.y) * sinf(frequency * p.z);
+    return sines < 0;
+}
+
+// scatter_checker (material.h:39-44)
+__device__ __forceinline__ void scatterChecker(Scatter& out, const SurfacePoint& i, const f3& p, float frequency, const f3& albedo1,
+                                               const f3& albedo2, unsigned int& rng) {
+    if (checkerLayer(p, frequency)) diffuseBsdf(out, i, albedo1, rng);
+    else diffuseBsdf(out, i, albedo2, rng);
+}
+
+// subsurface_bsdf (material.h:94-113): free-flight distance inside the medium, isotropic scattering
+__device__ __forceinline__ void subsurfaceBsdf(Scatter& out, const SurfacePoint& i, const f3& wo, const f3& absorption, float scatteringDistance,
+                                               unsigned int& rng) {
+    bool scattered = false;
+    if (i.inside) {
+        const float d = -logf(rnd(rng)) / scatteringDistance;
+        if (d < i.t) {
+            scattered = true;
+            out.t = d;
+        }
+        const f3 e = -absorption * out.t;
+        out.throughput = mk3(expf(e.x), expf(e.y), expf(e.z));
+    }
+    if (scattered) {
+        out.wi = randomInUnitSphere(rng);
+    } else {
+        out.wi = wo; // ray doesn't change direction
+        out.refracted = true;
+    }
+    out.specular = true;
+}
+
+// subsurface_dielectric_bsdf (material.h:115-143)
+__device__ __forceinline__ void subsurfaceDielectricBsdf(Scatter& out, const SurfacePoint& i, const f3& wo, float layerIor, const f3& glossyTint,
+                                                         float glossyFuzz, const f3& absorption, float scatteringDistance, unsigned int& rng) {
+    bool scattered = false;
+    if (i.inside) {
+        const float d = -logf(rnd(rng)) / scatteringDistance;
+        if (d < i.t) {
+            scattered = true;
+            out.t = d;
+        }
+        const f3 e = -absorption * out.t;
+        out.throughput = mk3(expf(e.x), expf(e.y), expf(e.z));
+    }
+    if (scattered) {
+        out.wi = randomInUnitSphere(rng);
+        out.specular = true;
+    } else {
+        // the dielectric interface: fresnel_layer, then glossy reflection or refraction (the arithmetic of dielectricBsdf
+        // above, which cannot be called here because it would overwrite the throughput when inside)
+        const f3& n = i.normal;
+        const float p1 = __fmul_rn(wo.x, n.x), p2 = __fmul_rn(wo.z, n.z);
+        const float etaiOverEtat = i.inside ? layerIor : (1.0f / layerIor);
+        const float cosTheta = fminf(__fsub_rn(__fmaf_rn(-wo.y, n.y, -p1), p2), 1.0f);
+        const float sinTheta = sqrtf(__fmaf_rn(-cosTheta, cosTheta, 1.0f));
+        if (__fmul_rn(etaiOverEtat, sinTheta) > 1.0f || rnd(rng) < schlick(cosTheta, etaiOverEtat)) {
+            glossyBsdf(out, i, wo, __fadd_rn(p2, __fmaf_rn(wo.y, n.y, p1)), glossyTint, glossyFuzz, rng);
+        } else {
+            const f3 par = mk3(__fmul_rn(etaiOverEtat, __fmaf_rn(cosTheta, n.x, wo.x)), __fmul_rn(etaiOverEtat, __fmaf_rn(cosTheta, n.y, wo.y)),
+                               __fmul_rn(etaiOverEtat, __fmaf_rn(cosTheta, n.z, wo.z)));
+            const float sq = sqlen(par);
+            f3 perp = mk3(0.0f, 0.0f, 0.0f);
+            if (!(sq >= 1.0f)) {
+                const float k = -sqrtf(__fsub_rn(1.0f, sq));
+                perp = mk3(__fmul_rn(k, n.x), __fmul_rn(k, n.y), __fmul_rn(k, n.z));
+            }
+            out.wi = unit(mk3(__fadd_rn(par.x, perp.x), __fadd_rn(par.y, perp.y), __fadd_rn(par.z, perp.z)));
+            out.refracted = true;
+        }
+        out.specular = true;
+    }
+}
+
+// hexColor (scene_materials.h:6-11): the division is by the double literal 255.0 in the reference
+__device__ __forceinline__ f3 hexColor(int hexValue) {
+    const float r = (float)((hexValue >> 16) & 0xFF), g = (float)((hexValue >> 8) & 0xFF), b = (float)(hexValue & 0xFF);
+    return mk3(r / 255.0f, g / 255.0f, b / 255.0f);
+}
+
+// The presets of scene_materials.h:22-93, by number (the order they appear in that file).
+enum ScenePreset {
+    PRESET_FLOOR_COAT = 0, PRESET_FLOOR_DIFFUSE = 1, PRESET_FLOOR_CHECKER = 2, PRESET_MODEL_COAT = 3, PRESET_MODEL_DIFFUSE = 4,
+    PRESET_MODEL_GLOSSY = 5, PRESET_MODEL_GLASS = 6, PRESET_MODEL_TINTEDGLASS = 7, PRESET_MODEL_SSS = 8, PRESET_SUBSURFACE = 9,
+    PRESET_COUNT = 10
+};
+
+__device__ __forceinline__ void presetScatter(int preset, Scatter& out, const SurfacePoint& i, const f3& p, const f3& wo, unsigned int& rng) {
+    const f3 white = mk3(1.0f, 1.0f, 1.0f);
+    const f3 model = mk3(0.0972942f, 0.0482054f, 0.000273194f);
+    switch (preset) {
+        case PRESET_FLOOR_COAT: coatBsdf(out, i, wo, 1.5f, white, 0.0f, hexColor(0x511845), rng); break;           // :22-28
+        case PRESET_FLOOR_DIFFUSE: diffuseBsdf(out, i, hexColor(0x511845), rng); break;                            // :30-33
+        case PRESET_FLOOR_CHECKER: scatterChecker(out, i, p, 0.2f, hexColor(0x511845), hexColor(0xff5733), rng); break; // :35-44
+        case PRESET_MODEL_COAT: coatBsdf(out, i, wo, 1.1f, white, 0.0f, model, rng); break;                        // :46-52
+        case PRESET_MODEL_DIFFUSE: diffuseBsdf(out, i, model, rng); break;                                        // :54-57
+        case PRESET_MODEL_GLOSSY: glossyBsdf(out, i, wo, dot(wo, i.normal), white, 0.0f, rng); break;              // :59-63
+        case PRESET_MODEL_GLASS: dielectricBsdf(out, i, wo, 1.1f, white, 0.0f, mk3(0.0f, 0.0f, 0.0f), rng); break; // :65-71
+        case PRESET_MODEL_TINTEDGLASS: {                                                                           // :73-81
+            const f3 absorption = mk3(-logf(model.x) / 10.0f, -logf(model.y) / 10.0f, -logf(model.z) / 10.0f);
+            dielectricBsdf(out, i, wo, 1.1f, white, 0.0f, absorption, rng);
+            break;
+        }
+        case PRESET_MODEL_SSS: subsurfaceDielectricBsdf(out, i, wo, 1.333f, white, 0.0f, mk3(0.9f, 0.3f, 0.02f), 2.0f, rng); break; // :83-93
+        default: subsurfaceBsdf(out, i, wo, mk3(0.9f, 0.3f, 0.02f), 2.0f, rng); break;                              // material.h:94 with the SSS constants
+    }
+}
+
 // material types: helper_structs.h:127-131
 #define MAT_DIFFUSE 0
 #define MAT_METAL 1

@@ -5,6 +5,7 @@
 // dual-node traversal runs.  Per ray the kernel moves 32 B in and 20 B out.
 #pragma once
 
+#include "bsdf.cuh"
 #include "device_scene.cuh"
 #include "rng.cuh"
 #include "traverse.cuh"
@@ -102,4 +103,28 @@ __global__ void generateRayBatchKernel(float4* __restrict__ rayO, float4* __rest
     }
     rayO[i] = mk4(o, tMin);
     rayD[i] = mk4(d, tMax);
+}
+
+// ---- BSDF probe: one preset of scene_materials.h on a batch of surface points (tests) ----------------
+// in:  3 float4 per item {normal.xyz, t} {p.xyz, inside (0/1)} {wo.xyz, rng state bits}
+// out: 3 float4 per item {wi.xyz, t} {throughput.xyz, specular | refracted << 1 (as int bits)} {rng state bits after, 0, 0, 0}
+__global__ void scatterBatchKernel(int preset, long long n, const float4* __restrict__ in, float4* __restrict__ out) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float4 a = in[3 * k], b = in[3 * k + 1], c = in[3 * k + 2];
+    SurfacePoint i;
+    i.normal = xyz(a);
+    i.t = a.w;
+    i.inside = b.w != 0.0f;
+    unsigned int rng = __float_as_uint(c.w);
+    Scatter s; // scatter_info's constructor, helper_structs.h:45
+    s.wi = mk3(0.0f, 0.0f, 0.0f);
+    s.specular = false;
+    s.throughput = mk3(1.0f, 1.0f, 1.0f);
+    s.refracted = false;
+    s.t = i.t;
+    presetScatter(preset, s, i, xyz(b), xyz(c), rng);
+    out[3 * k] = mk4(s.wi, s.t);
+    out[3 * k + 1] = mk4(s.throughput, __int_as_float((s.specular ? 1 : 0) | (s.refracted ? 2 : 0)));
+    out[3 * k + 2] = make_float4(__uint_as_float(rng), 0.0f, 0.0f, 0.0f);
 }

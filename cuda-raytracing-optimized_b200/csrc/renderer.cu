@@ -876,6 +876,22 @@ extern "C" void intersectBatch(const float* origins, const float* dirs, long lon
     cudaFree(dO); cudaFree(dD); cudaFree(dH); cudaFree(dM);
 }
 
+// Host pointers in and out (12 floats per item each way, layout at scatterBatchKernel). Needs no scene.
+extern "C" int scatterBatch(int preset, long long n, const float* in, float* out) {
+    if (preset < 0 || preset >= PRESET_COUNT || n < 0) return -1;
+    if (n == 0) return 0;
+    float4 *dIn = nullptr, *dOut = nullptr;
+    CRT_CHECK(cudaMalloc((void**)&dIn, (size_t)n * 3 * sizeof(float4)));
+    CRT_CHECK(cudaMalloc((void**)&dOut, (size_t)n * 3 * sizeof(float4)));
+    CRT_CHECK(cudaMemcpy(dIn, in, (size_t)n * 3 * sizeof(float4), cudaMemcpyHostToDevice));
+    scatterBatchKernel<<<(unsigned int)((n + 127) / 128), 128>>>(preset, n, dIn, dOut);
+    CRT_CHECK(cudaGetLastError());
+    CRT_CHECK(cudaMemcpy(out, dOut, (size_t)n * 3 * sizeof(float4), cudaMemcpyDeviceToHost));
+    cudaFree(dIn);
+    cudaFree(dOut);
+    return 0;
+}
+
 extern "C" void* rendererDeviceAlloc(size_t bytes) {
     void* p = nullptr;
     CRT_CHECK(cudaMalloc(&p, bytes ? bytes : 16));

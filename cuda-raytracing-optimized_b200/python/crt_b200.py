@@ -123,7 +123,7 @@ DEVICE_SYMBOLS = [
     "intersectBatchDevice", "generateRayBatchDevice", "rendererDeviceAlloc", "rendererDeviceFree", "rendererCopyToHost",
     "rendererCopyToDevice", "getRendererStats", "setRendererProfiling", "getRendererAccumDevice", "setRendererAccumDevice",
     "finalizeFrame", "setRendererCounting", "getRendererTraversalCounts", "rendererDebugRead", "rendererReleaseCaches", "getRendererChaserCounts", "continueRenderer", "getRendererSamplesDone",
-    "saveRendererCheckpoint", "loadRendererCheckpoint",
+    "saveRendererCheckpoint", "loadRendererCheckpoint", "scatterBatch",
 ]
 
 
@@ -163,6 +163,7 @@ def device_lib():
         L.setRendererCounting.argtypes = [C.c_int]
         L.getRendererTraversalCounts.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
         L.getRendererChaserCounts.argtypes = [C.POINTER(C.c_ulonglong)] * 4
+        L.scatterBatch.argtypes = [C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]
         L.continueRenderer.argtypes = [C.c_int, C.c_int, C.c_int]
         L.saveRendererCheckpoint.argtypes = [C.c_char_p]
         L.loadRendererCheckpoint.argtypes = [C.c_char_p]

@@ -93,6 +93,14 @@ void generateRayBatchDevice(void* dRayO, void* dRayD, long long n, int filmW, in
 // driver.  No-op while a frame is live (between initRenderer and cleanupRenderer).
 void rendererReleaseCaches();
 
+// The reference's BSDF library beyond the three materials material_scatter dispatches (material.h:33-143) through its
+// scene presets (scene_materials.h:22-93, numbered in file order: 0 floor_coat, 1 floor_diffuse, 2 floor_checker,
+// 3 model_coat, 4 model_diffuse, 5 model_glossy, 6 model_glass, 7 model_tintedglass, 8 model_sss; 9 = subsurface_bsdf with
+// the sss constants), evaluated on a batch of surface points.  in: 12 floats per item {normal.xyz, t, p.xyz, inside,
+// wo.xyz, rng state bits}; out: 12 floats {wi.xyz, t, throughput.xyz, specular | refracted << 1 (int bits), rng state bits
+// after, 0, 0, 0}.  HOST pointers; returns 0, or -1 for an unknown preset.
+int scatterBatch(int preset, long long n, const float* in, float* out);
+
 void* rendererDeviceAlloc(size_t bytes);
 void rendererDeviceFree(void* p);
 void rendererCopyToHost(void* dst, const void* dSrc, size_t bytes);

@@ -128,3 +128,15 @@ def ref_intersect_batch(scene_spec, tex_size, ppl, ray_o, ray_d, any_hit, workdi
     hit = raw[8:8 + 16 * n].view(np.float32).reshape(n, 4)
     mesh = raw[8 + 16 * n:8 + 20 * n].view(np.int32)
     return hit, mesh, info
+
+
+def ref_scatter_batch(preset, items, workdir):
+    """The reference's own BSDF preset `preset` (scene_materials.h, through oracle/ref_shim.cu) on `items` (n, 12) float32."""
+    n = items.shape[0]
+    fin, fout = os.path.join(workdir, "scatter_in.bin"), os.path.join(workdir, "scatter_out.bin")
+    with open(fin, "wb") as f:
+        f.write(np.int64(n).tobytes())
+        f.write(np.ascontiguousarray(items, dtype=np.float32).tobytes())
+    _run([os.path.join(REF_DIR, "ref_shim_driver"), "scatter", str(preset), fin, fout])
+    raw = np.fromfile(fout, dtype=np.uint8)
+    return raw[8:8 + 48 * n].view(np.float32).reshape(n, 12).copy()

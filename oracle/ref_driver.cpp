@@ -29,6 +29,7 @@ void crtRtiowCamera(int nx, int ny, camera* out);
 int crtWriteRef(const char* path, int nx, int ny, const vec3* fb);
 #ifdef WITH_SHIM
 float refIntersectBatch(const float* rayO, const float* rayD, long long n, int isShadow, float* outHit, int* outMesh);
+int refScatterBatch(int preset, long long n, const float* in, float* out);
 void refSpheresInit(const sphere* spheres, const material* materials, int n, const camera cam, vec3** fb, int nx, int ny, int maxDepth);
 void refSpheresRun(int ns, int tx, int ty);
 void refSpheresCleanup();
@@ -132,6 +133,20 @@ int main(int argc, char** argv) {
         std::printf("]}\n");
         if (std::strcmp(argv[9], "-") != 0 && crtWriteRef(argv[9], nx, ny, fb) != 0) return 1;
         refSpheresCleanup();
+        return 0;
+    }
+    if (mode == "scatter" && argc == 5) { // scatter <preset> <in.bin> <out.bin>: int64 n, then n x 12 floats each way
+        std::ifstream in(argv[3], std::ios::binary);
+        long long n = 0;
+        in.read((char*)&n, 8);
+        std::vector<float> a(12 * (size_t)n), b(12 * (size_t)n);
+        in.read((char*)a.data(), a.size() * 4);
+        if (!in) { std::fprintf(stderr, "short read on %s\n", argv[3]); return 1; }
+        if (refScatterBatch(std::atoi(argv[2]), n, a.data(), b.data()) != 0) return 1;
+        std::ofstream out(argv[4], std::ios::binary);
+        out.write((const char*)&n, 8);
+        out.write((const char*)b.data(), b.size() * 4);
+        std::printf("{\"mode\": \"scatter\", \"n\": %lld}\n", n);
         return 0;
     }
     if (mode == "batch" && argc == 8) {
