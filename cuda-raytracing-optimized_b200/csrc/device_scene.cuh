@@ -49,7 +49,8 @@ struct WfControl {
     unsigned int countRegen;
     unsigned int cursorExtend; // dynamic fetch cursors
     unsigned int cursorShadow;
-    unsigned int pad0, pad1;
+    unsigned int blocksDone;   // shadeSpheresKernel's last block advances the iteration
+    unsigned int pad1;
     unsigned long long raysExtend;
     unsigned long long raysShadow;
     unsigned long long iterations;

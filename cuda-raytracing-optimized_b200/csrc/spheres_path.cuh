@@ -9,6 +9,8 @@
 // attenuation * gradient(rayDir.y) and ends the path.  No light, no shadow rays.
 // oracle/ref_spheres.cu is the same definition as a thread-per-pixel megakernel built from the
 // reference's own headers; tests compare the two.
+// An iteration is two launches: extendSpheresBvhKernel (closest sphere) and shadeSpheresKernel (scatter, retire, next camera
+// ray, queue swap).
 // Included at the end of renderer.cu (one translation unit: the kernels of wavefront_kernels.cuh are shared).
 #pragma once
 
@@ -122,14 +124,19 @@ __global__ void __launch_bounds__(WF_BLOCK) extendSpheresBvhKernel(WfState st, c
     }
 }
 
+// Shade + retire + regenerate + advance in one launch (an iteration is extend, then this): when a path ends its colour goes
+// into the pixel (col += p.color, kernels.cu:558, in sample order: one slot per pixel) and the slot's next sample starts
+// right here (kernels.cu:549-555) instead of in a separate raygen pass; the last block to finish swaps the queues.
 __global__ void __launch_bounds__(WF_BLOCK) shadeSpheresKernel(WfState st, const float4* __restrict__ mats, int maxDepth,
-                                                               const unsigned int* __restrict__ queue, unsigned int* __restrict__ nextQueue) {
+                                                               const unsigned int* __restrict__ queue, unsigned int* __restrict__ nextQueue,
+                                                               CameraDev cam, int nx, int ny, int samplesPerSlot, int slotsPerPixel) {
     WfControl* ctl = st.ctl;
     const unsigned int n = ctl->countActive;
+    const unsigned int npix = (unsigned int)nx * (unsigned int)ny;
     const unsigned int stride = gridDim.x * blockDim.x;
     for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
         const unsigned int i = base + laneId();
-        bool continues = false, ended = false;
+        bool continues = false;
         unsigned int slot = 0;
         if (i < n) {
             slot = queue[i];
@@ -143,15 +150,13 @@ __global__ void __launch_bounds__(WF_BLOCK) shadeSpheresKernel(WfState st, const
             unsigned int bounce = flags & PATH_BOUNCE_MASK;
             const float4 att4 = st.atten[slot];
             f3 att = xyz(att4);
+            float4 pc = st.pcol[slot];
             if (!(h.x < FLT_MAX)) {
                 // sky gradient, kernels.cu:419-421
                 const float t = 0.5f * (dir.y + 1.0f);
                 const f3 c = (1.0f - t) * mk3(1.0f, 1.0f, 1.0f) + t * mk3(0.5f, 0.7f, 1.0f);
-                float4 pc = st.pcol[slot];
                 const f3 add = att * c;
                 pc.x += add.x; pc.y += add.y; pc.z += add.z;
-                st.pcol[slot] = pc;
-                ended = true;
             } else {
                 const unsigned int id = __float_as_uint(h.w);
                 const float4 sp = c_spheres[id];
@@ -185,19 +190,58 @@ __global__ void __launch_bounds__(WF_BLOCK) shadeSpheresKernel(WfState st, const
                     bounce = (bounce + 1u) & PATH_BOUNCE_MASK;
                     if (!((int)bounce < maxDepth)) continues = false;
                 }
-                ended = !continues;
                 flags = bounce | (scat.specular ? PATH_FLAG_SPECULAR : 0u) | (inside ? PATH_FLAG_INSIDE : 0u);
+            }
+            if (continues) {
                 st.rayO[slot] = mk4(origin, __uint_as_float(rng));
-                if (continues) {
-                    st.rayD[slot] = mk4(dir, __uint_as_float(flags));
-                    st.atten[slot] = mk4(att, att4.w);
+                st.rayD[slot] = mk4(dir, __uint_as_float(flags));
+                st.atten[slot] = mk4(att, att4.w);
+            } else {
+                // the sample is finished: col += p.color (kernels.cu:558), then the slot's next sample
+                const unsigned int pixel = slot % npix;
+                if (slotsPerPixel == 1) {
+                    float4 a = st.accum[pixel];
+                    a.x += pc.x; a.y += pc.y; a.z += pc.z;
+                    st.accum[pixel] = a;
+                } else {
+                    atomicAdd(&st.accum[pixel].x, pc.x);
+                    atomicAdd(&st.accum[pixel].y, pc.y);
+                    atomicAdd(&st.accum[pixel].z, pc.z);
+                }
+                const int sample = __float_as_int(att4.w) + 1;
+                if (sample < samplesPerSlot) {
+                    const int px = (int)(pixel % (unsigned int)nx), py = (int)(pixel / (unsigned int)nx);
+                    const float u = float(px + rnd(rng)) / float(nx);
+                    const float v = float(py + rnd(rng)) / float(ny);
+                    f3 o, d;
+                    cameraRay(cam, u, v, rng, o, d);
+                    st.rayO[slot] = mk4(o, __uint_as_float(rng));
+                    st.rayD[slot] = mk4(d, __uint_as_float(0u)); // bounce 0, specular = inside = false (kernels.cu:554-555)
+                    st.atten[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(sample));
+                    st.pcol[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    continues = true;
                 }
             }
         }
         const unsigned int posNext = warpAppend(continues, &ctl->countNext);
         if (continues) nextQueue[posNext] = slot;
-        const unsigned int posRegen = warpAppend(ended, &ctl->countRegen);
-        if (ended) st.regen[posRegen] = slot;
+    }
+
+    // the last block to finish advances the iteration (what advanceKernel did)
+    __shared__ bool isLast;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        isLast = atomicAdd(&ctl->blocksDone, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (isLast && threadIdx.x == 0) {
+        ctl->raysExtend += ctl->countActive;
+        if (ctl->countActive) ctl->iterations += 1;
+        ctl->countActive = ctl->countNext;
+        ctl->countNext = 0;
+        ctl->cursorExtend = 0;
+        ctl->blocksDone = 0;
     }
 }
 
@@ -306,9 +350,7 @@ static void launchSphereIteration(RendererContext& c, cudaStream_t stream, unsig
     const int grid = c.numSMs * 8;
     if (g_spheresBrute) extendSpheresKernel<<<grid, WF_BLOCK, 0, stream>>>(c.wf, qCur, c.numSpheres); // the README-era loop, kept as the BVH's checker
     else extendSpheresBvhKernel<<<grid, WF_BLOCK, 0, stream>>>(c.wf, qCur, g_sphereBvh);
-    shadeSpheresKernel<<<grid, WF_BLOCK, 0, stream>>>(c.wf, c.materials, c.maxDepth, qCur, qNext);
-    raygenKernel<false><<<grid, WF_BLOCK, 0, stream>>>(c.wf, c.cam, qNext, c.nx, c.ny, samplesPerSlot, slotsPerPixel, c.opts.sampleStream);
-    advanceKernel<<<1, 1, 0, stream>>>(c.wf.ctl);
+    shadeSpheresKernel<<<grid, WF_BLOCK, 0, stream>>>(c.wf, c.materials, c.maxDepth, qCur, qNext, c.cam, c.nx, c.ny, samplesPerSlot, slotsPerPixel);
 }
 
 void crtRunSpheres(RendererContext& c, int ns) {
@@ -354,7 +396,7 @@ void crtRunSpheres(RendererContext& c, int ns) {
         }
         while (true) {
             CRT_CHECK(cudaGraphLaunch(c.graphExec, stream));
-            launches += (unsigned long long)batch * 4;
+            launches += (unsigned long long)batch * 2;
             CRT_CHECK(cudaMemcpyAsync(c.hostCtl, c.wf.ctl, sizeof(WfControl), cudaMemcpyDeviceToHost, stream));
             CRT_CHECK(cudaStreamSynchronize(stream));
             if (c.hostCtl->countActive == 0) break;
