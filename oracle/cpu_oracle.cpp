@@ -376,6 +376,76 @@ void material_scatter(Scatter& out, const Inter& i, V3 wo, const material& mat, 
     else dielectric_bsdf(out, i, wo, mat.param, color, 0.0f, v3(0, 0, 0), rng);
 }
 
+// ---- the rest of material.h and the presets of scene_materials.h:22-93 (unused by the staircase table) ----
+bool checker_layer(V3 p, float frequency) { // material.h:33-36
+    const float sines = std::sin(frequency * p.x) * std::sin(frequency * p.y) * std::sin(frequency * p.z);
+    return sines < 0;
+}
+void coat_bsdf(Scatter& out, const Inter& i, V3 wo, float layer_ior, V3 glossy_tint, float glossy_fuzz, V3 diffuse_albedo,
+               uint32_t& rng) { // material.h:62-70
+    if (fresnel_layer(i, wo, layer_ior, rng)) glossy_bsdf(out, i, wo, glossy_tint, glossy_fuzz, rng);
+    else diffuse_bsdf(out, i, diffuse_albedo, rng);
+}
+void subsurface_bsdf(Scatter& out, const Inter& i, V3 wo, V3 absorption, float scatteringDistance, uint32_t& rng) { // material.h:94-113
+    bool scattered = false;
+    if (i.inside) {
+        const float d = -std::log(rnd(rng)) / scatteringDistance;
+        if (d < i.t) { scattered = true; out.t = d; }
+        const V3 e = -absorption * out.t;
+        out.throughput = v3(std::exp(e.x), std::exp(e.y), std::exp(e.z));
+    }
+    if (scattered) {
+        out.wi = random_in_unit_sphere(rng);
+    } else {
+        out.wi = wo;
+        out.refracted = true;
+    }
+    out.specular = true;
+}
+void subsurface_dielectric_bsdf(Scatter& out, const Inter& i, V3 wo, float layer_ior, V3 glossy_tint, float glossy_fuzz, V3 absorption,
+                                float scatteringDistance, uint32_t& rng) { // material.h:115-143
+    bool scattered = false;
+    if (i.inside) {
+        const float d = -std::log(rnd(rng)) / scatteringDistance;
+        if (d < i.t) { scattered = true; out.t = d; }
+        const V3 e = -absorption * out.t;
+        out.throughput = v3(std::exp(e.x), std::exp(e.y), std::exp(e.z));
+    }
+    if (scattered) {
+        out.wi = random_in_unit_sphere(rng);
+    } else if (fresnel_layer(i, wo, layer_ior, rng)) {
+        glossy_bsdf(out, i, wo, glossy_tint, glossy_fuzz, rng);
+    } else {
+        const float etai_over_etat = i.inside ? layer_ior : (1.0f / layer_ior);
+        out.wi = unit(refract(wo, i.normal, etai_over_etat));
+        out.refracted = true;
+    }
+    out.specular = true;
+}
+V3 hexColor(int hexValue) { // scene_materials.h:6-11
+    const float r = (float)((hexValue >> 16) & 0xFF), g = (float)((hexValue >> 8) & 0xFF), b = (float)(hexValue & 0xFF);
+    return v3((float)(r / 255.0), (float)(g / 255.0), (float)(b / 255.0));
+}
+void preset_scatter(int preset, Scatter& out, const Inter& i, V3 p, V3 wo, uint32_t& rng) { // scene_materials.h:22-93, in file order
+    const V3 white = v3(1, 1, 1), model = v3(0.0972942f, 0.0482054f, 0.000273194f);
+    switch (preset) {
+        case 0: coat_bsdf(out, i, wo, 1.5f, white, 0.0f, hexColor(0x511845), rng); break;
+        case 1: diffuse_bsdf(out, i, hexColor(0x511845), rng); break;
+        case 2: diffuse_bsdf(out, i, checker_layer(p, 0.2f) ? hexColor(0x511845) : hexColor(0xff5733), rng); break;
+        case 3: coat_bsdf(out, i, wo, 1.1f, white, 0.0f, model, rng); break;
+        case 4: diffuse_bsdf(out, i, model, rng); break;
+        case 5: glossy_bsdf(out, i, wo, white, 0.0f, rng); break;
+        case 6: dielectric_bsdf(out, i, wo, 1.1f, white, 0.0f, v3(0, 0, 0), rng); break;
+        case 7: {
+            const V3 absorption = v3(-std::log(model.x) / 10.0f, -std::log(model.y) / 10.0f, -std::log(model.z) / 10.0f);
+            dielectric_bsdf(out, i, wo, 1.1f, white, 0.0f, absorption, rng);
+            break;
+        }
+        case 8: subsurface_dielectric_bsdf(out, i, wo, 1.333f, white, 0.0f, v3(0.9f, 0.3f, 0.02f), 2.0f, rng); break;
+        default: subsurface_bsdf(out, i, wo, v3(0.9f, 0.3f, 0.02f), 2.0f, rng); break;
+    }
+}
+
 bool generateShadowRay(const Ctx& c, Path& p, const Inter& inters, float& lightDist) { // kernels.cu:363-393
     const V3 sw = unit(c.lightCenter - p.origin);
     const V3 su = unit(cross(std::fabs(sw.x) > 0.01f ? v3(0, 1, 0) : v3(1, 0, 0), sw));
@@ -512,6 +582,39 @@ Ctx makeCtx(const kernel_scene* sc, const camera* cam, int nx, int ny, int ns, i
 } // namespace
 
 extern "C" {
+
+// The BSDF presets on a batch of surface points; item layout as scatterBatch (include/kernels.h): in 12 floats
+// {normal.xyz, t, p.xyz, inside, wo.xyz, rng bits}, out 12 floats {wi.xyz, t, throughput.xyz, flags, rng bits after, 0, 0, 0}.
+int oracleScatterBatch(int preset, long long n, const float* in, float* out) {
+    if (preset < 0 || preset > 9) return -1;
+    for (long long k = 0; k < n; k++) {
+        const float* a = in + 12 * k;
+        Inter i;
+        i.objId = TRIMESH;
+        i.meshID = 0;
+        i.normal = v3(a[0], a[1], a[2]);
+        i.t = a[3];
+        i.inside = a[7] != 0.0f;
+        i.texCoords[0] = i.texCoords[1] = 0.0f;
+        uint32_t rng;
+        std::memcpy(&rng, &a[11], 4);
+        Scatter s;
+        s.wi = v3(0, 0, 0);
+        s.specular = false;
+        s.throughput = v3(1, 1, 1);
+        s.refracted = false;
+        s.t = i.t;
+        preset_scatter(preset, s, i, v3(a[4], a[5], a[6]), v3(a[8], a[9], a[10]), rng);
+        float* o = out + 12 * k;
+        o[0] = s.wi.x; o[1] = s.wi.y; o[2] = s.wi.z; o[3] = s.t;
+        o[4] = s.throughput.x; o[5] = s.throughput.y; o[6] = s.throughput.z;
+        const int flags = (s.specular ? 1 : 0) | (s.refracted ? 2 : 0);
+        std::memcpy(&o[7], &flags, 4);
+        std::memcpy(&o[8], &rng, 4);
+        o[9] = o[10] = o[11] = 0.0f;
+    }
+    return 0;
+}
 
 // render(), kernels.cu:535-569, for rows rowBegin, rowBegin+rowStride, ... < rowEnd (other rows of fb are left untouched). counters (may be NULL): primary, secondary, shadow, nodeVisits, triTests.
 void oracleRender(const kernel_scene* sc, const camera* cam, int nx, int ny, int ns, int maxDepth, unsigned int sampleStream,

@@ -49,6 +49,7 @@ def lib():
         L.oracleBoxDist.restype = C.c_float
         L.oracleBoxDist.argtypes = [C.c_float * 3, C.c_float * 3, C.c_float * 3, C.c_float * 3, C.c_float]
         L.oracleNumThreads.restype = C.c_int
+        L.oracleScatterBatch.argtypes = [C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -140,3 +141,11 @@ def ref_scatter_batch(preset, items, workdir):
     _run([os.path.join(REF_DIR, "ref_shim_driver"), "scatter", str(preset), fin, fout])
     raw = np.fromfile(fout, dtype=np.uint8)
     return raw[8:8 + 48 * n].view(np.float32).reshape(n, 12).copy()
+
+
+def scatter_batch(preset, items):
+    """CPU restatement of the BSDF presets (cpu_oracle.cpp preset_scatter) on `items` (n, 12) float32."""
+    items = np.ascontiguousarray(items, dtype=np.float32)
+    out = np.zeros_like(items)
+    assert lib().oracleScatterBatch(preset, items.shape[0], items.ctypes.data, out.ctypes.data) == 0
+    return out

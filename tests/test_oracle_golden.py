@@ -132,3 +132,22 @@ def test_oracle_depth_zero_and_counts(oracle, small_scene):
     assert (img == 0).all() and cnt["primary"] == 0
     img, cnt = oracle.render(small_scene, 16, 12, 2, 5, count=True)
     assert cnt["primary"] == 16 * 12 * 2 and cnt["secondary"] <= 4 * cnt["primary"] and cnt["shadow"] <= cnt["primary"] + cnt["secondary"]
+
+
+def test_cpu_oracle_bsdf_presets_vs_golden_reference_outputs(oracle):
+    """The CPU restatement of the reference's whole BSDF library (material.h behind the presets of scene_materials.h:22-93)
+    against outputs of the reference's own device functions (tests/golden/bsdf_presets.npz, minted on a B200 through
+    oracle/ref_shim.cu). Integer results (RNG state after the call = number of draws, specular/refracted flags) and the
+    subsurface free-flight distance decisions must agree on every item where the decision is not a float tie; directions and
+    throughputs to 2e-5 (the GPU fuses multiply-adds and uses its own expf/logf/powf, the oracle does neither)."""
+    z = np.load(os.path.join(G, "bsdf_presets.npz"))
+    items = z["items"]
+    for preset in range(10):
+        ref = z["ref_%d" % preset]
+        got = oracle.scatter_batch(preset, items)
+        same = (got[:, 8].view(np.uint32) == ref[:, 8].view(np.uint32)) & (got[:, 7].view(np.int32) == ref[:, 7].view(np.int32))
+        assert same.mean() >= 0.99, (preset, same.mean())   # a Fresnel / free-flight comparison can flip on the last bit
+        ok = same
+        assert np.allclose(got[ok, 0:3], ref[ok, 0:3], rtol=2e-5, atol=2e-5), preset
+        assert np.allclose(got[ok, 3], ref[ok, 3], rtol=2e-5, atol=1e-6), preset
+        assert np.allclose(got[ok, 4:7], ref[ok, 4:7], rtol=2e-5, atol=1e-6), preset
