@@ -101,7 +101,8 @@ class ClockSampler:
 def workload_params(args):
     if args.workload == "staircase":
         return dict(workload="staircase mesh %dx%d %dspp/GPU depth %d (BASELINE config 3)" % (args.nx, args.ny, args.spp, args.depth),
-                    scene="procedural staircase detail %.2f, %d^2 textures, 5 prims/leaf" % (args.detail, args.tex))
+                    scene="procedural staircase detail %.2f, %d^2 textures, 5 prims/leaf%s" %
+                          (args.detail, args.tex, ", BVH built with SAH splits (same BVH_00.04 layout)" if args.bvh == "sah" else ""))
     if args.workload == "rtiow":
         return dict(workload="RTIOW 488 spheres %dx%d %dspp/GPU depth 50 (BASELINE config 2)" % (args.nx, args.ny, args.spp),
                     scene="host LCG seed 1, spheres in __constant__")
@@ -138,8 +139,13 @@ def run_reference(args, rank, world):
     ns = args.spp * world  # the whole job of the other arm, on the one GPU the reference can use
     cfg = dict(workload_params(args), gpus_used=1, total_spp=ns, l2="state + textures (>230 MB) exceed L2; rewritten every step")
     if args.workload == "staircase":
-        _, info = oracle.ref_render(args.detail, args.tex, 5, args.nx, args.ny, ns, args.depth, "-", warmup=args.warmup, steps=args.steps)
-        e2e = oracle._run([os.path.join(oracle.REF_DIR, "ref_driver"), "render_e2e", str(args.detail), str(args.tex), "5", str(args.nx),
+        spec = args.detail
+        if args.bvh == "sah":  # the reference reads the SAH-built tree from a BVH_00.04 file, like any scene of its own
+            import tempfile
+            spec = os.path.join(tempfile.mkdtemp(), "staircase_sah.bvh")
+            assert oracle.crt.Scene.staircase(args.detail, args.tex, 5, sah=True).save_bvh(spec) == 0
+        _, info = oracle.ref_render(spec, args.tex, 5, args.nx, args.ny, ns, args.depth, "-", warmup=args.warmup, steps=args.steps)
+        e2e = oracle._run([os.path.join(oracle.REF_DIR, "ref_driver"), "render_e2e", str(spec), str(args.tex), "5", str(args.nx),
                            str(args.ny), str(ns), str(args.depth), "1", str(min(args.steps, 3)), "-"])
         kind = "reference"
     elif args.workload == "rtiow":
@@ -195,7 +201,7 @@ def run_ours(args, rank, world, local_rank):
     pk = peaks()
     spheres = args.workload == "rtiow"
     depth = 50 if spheres else args.depth
-    scene = crt.rtiow_scene(1) if spheres else crt.Scene.staircase(args.detail, args.tex, 5)
+    scene = crt.rtiow_scene(1) if spheres else crt.Scene.staircase(args.detail, args.tex, 5, sah=args.bvh == "sah")
     nx, ny, ns = args.nx, args.ny, args.spp
     ns_total = ns * world
     h2d = (488 * 40) if spheres else scene_bytes(scene)
@@ -439,6 +445,9 @@ def main():
     ap.add_argument("--tex", type=int, default=1024)
     ap.add_argument("--rays", type=int, default=1 << 26)
     ap.add_argument("--slots", type=int, default=0, help="path slots per pixel (0/1 = reference RNG streams)")
+    ap.add_argument("--bvh", default="median", choices=["median", "sah"],
+                    help="how the host builds the scene's BVH_00.04 tree: the reference author's median split (default) or the "
+                         "surface-area heuristic inside the same layout (both arms get the same file)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -8,7 +8,11 @@
 //   * leaf k owns triangle slots [k*N, k*N+N), N = numPrimitivesPerLeaf; unused
 //     slots are marked with v[0].x = +inf (kernels.cu:202);
 //   * split = median of the centroids along the longest axis of the node box,
-//     lower side to the left child (TODO.txt:235-238, helper_structs.h:106).
+//     lower side to the left child (TODO.txt:235-238, helper_structs.h:106);
+//   * BUILD_SAH (opt-in): the tree must stay complete, so a child can take at most
+//     (leaves under it) x N triangles; among the sweep positions that respect that
+//     for both children, on all three axes, the one with the least
+//     area(L)*|L| + area(R)*|R| is taken (the author's own next step, TODO.txt:574).
 // The sort uses a total order (key, then original index) so the tree is the
 // same on every machine.
 #include "bvh_builder.h"
@@ -31,6 +35,57 @@ struct Builder {
     int leafLevel;
     int primsPerLeaf;
     int firstLeaf;
+    BuildMode mode = BUILD_MEDIAN;
+    std::vector<float> areaL; // SAH sweep scratch
+
+    static float halfArea(const bvh_node& b) {
+        const float dx = b.b.e[0] - b.a.e[0], dy = b.b.e[1] - b.a.e[1], dz = b.b.e[2] - b.a.e[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+
+    void sortAxis(int lo, int hi, int axis) {
+        const std::vector<float>& c = cent[axis];
+        std::sort(order.begin() + lo, order.begin() + hi, [&c](int x, int y) {
+            if (c[x] != c[y]) return c[x] < c[y];
+            return x < y;
+        });
+    }
+
+    // Least-cost (axis, position) among the splits both children have room for; leaves `order[lo, hi)` sorted on that axis.
+    int sahSplit(int lo, int hi, int level) {
+        const int n = hi - lo;
+        const long long cap = (long long)(1LL << (leafLevel - level - 1)) * primsPerLeaf; // triangles a child can hold
+        const int kMin = (int)std::max<long long>(1, n - cap), kMax = (int)std::min<long long>(n - 1, cap);
+        const float inf = std::numeric_limits<float>::infinity();
+        float bestCost = inf;
+        int bestAxis = -1, bestK = (n + 1) / 2;
+        areaL.resize((size_t)n + 1);
+        for (int axis = 0; axis < 3; axis++) {
+            sortAxis(lo, hi, axis);
+            bvh_node box;
+            box.a = vec3(inf, inf, inf);
+            box.b = vec3(-inf, -inf, -inf);
+            for (int i = 0; i < n; i++) { // areaL[k] = area of the first k triangles
+                grow(box, src[order[lo + i]]);
+                areaL[i + 1] = halfArea(box);
+            }
+            box.a = vec3(inf, inf, inf);
+            box.b = vec3(-inf, -inf, -inf);
+            for (int k = n - 1; k >= kMin; k--) { // right side = triangles k .. n-1
+                grow(box, src[order[lo + k]]);
+                if (k > kMax) continue;
+                const float cost = areaL[k] * (float)k + halfArea(box) * (float)(n - k);
+                if (cost < bestCost || (cost == bestCost && (axis < bestAxis || (axis == bestAxis && k < bestK)))) {
+                    bestCost = cost;
+                    bestAxis = axis;
+                    bestK = k;
+                }
+            }
+        }
+        if (bestAxis < 0) { bestAxis = 0; bestK = std::min(std::max((n + 1) / 2, kMin), kMax); }
+        if (bestAxis != 2) sortAxis(lo, hi, bestAxis);
+        return lo + bestK;
+    }
 
     Builder(const std::vector<triangle>& s, BuiltMesh& o) : src(s), out(o) {}
 
@@ -58,6 +113,12 @@ struct Builder {
         }
 
         const int n = hi - lo;
+        if (mode == BUILD_SAH && n >= 2) {
+            const int mid = sahSplit(lo, hi, level);
+            build(2 * node, lo, mid, level + 1);
+            build(2 * node + 1, mid, hi, level + 1);
+            return;
+        }
         int axis = 0;
         if (n > 0) {
             float ext[3] = {box.b.e[0] - box.a.e[0], box.b.e[1] - box.a.e[1], box.b.e[2] - box.a.e[2]};
@@ -77,7 +138,7 @@ struct Builder {
 
 } // namespace
 
-bool buildBvh(const std::vector<triangle>& tris, int primsPerLeaf, BuiltMesh& out) {
+bool buildBvh(const std::vector<triangle>& tris, int primsPerLeaf, BuiltMesh& out, BuildMode mode) {
     if (primsPerLeaf < 1) return false;
     const int n = (int)tris.size();
     int level = 0;
@@ -97,6 +158,7 @@ bool buildBvh(const std::vector<triangle>& tris, int primsPerLeaf, BuiltMesh& ou
     b.leafLevel = level;
     b.primsPerLeaf = primsPerLeaf;
     b.firstLeaf = numLeaves;
+    b.mode = mode;
     b.order.resize(n);
     for (int i = 0; i < n; i++) b.order[i] = i;
     for (int a = 0; a < 3; a++) {

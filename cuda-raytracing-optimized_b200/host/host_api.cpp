@@ -406,15 +406,19 @@ struct crt_scene {
 
 extern "C" {
 
-crt_scene* crtSceneCreateStaircase(float detail, int texSize, int primsPerLeaf) {
-    if (!(detail > 0.0f) || texSize < 1 || primsPerLeaf < 1) return nullptr;
+crt_scene* crtSceneCreateStaircaseEx(float detail, int texSize, int primsPerLeaf, int buildMode) {
+    if (!(detail > 0.0f) || texSize < 1 || primsPerLeaf < 1 || buildMode < 0 || buildMode > 1) return nullptr;
     MeshGen g;
     g.detail = detail;
     buildStaircase(g);
     crt_scene* s = new crt_scene();
-    if (!crt::buildBvh(g.tris, primsPerLeaf, s->built)) { delete s; return nullptr; }
+    if (!crt::buildBvh(g.tris, primsPerLeaf, s->built, buildMode ? crt::BUILD_SAH : crt::BUILD_MEDIAN)) { delete s; return nullptr; }
     s->finish(texSize);
     return s;
+}
+
+crt_scene* crtSceneCreateStaircase(float detail, int texSize, int primsPerLeaf) {
+    return crtSceneCreateStaircaseEx(detail, texSize, primsPerLeaf, 0);
 }
 
 crt_scene* crtSceneLoadBVH(const char* path, int texSize) {

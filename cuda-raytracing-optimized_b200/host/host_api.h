@@ -27,6 +27,9 @@ typedef struct crt_scene crt_scene; // opaque; owns tris, bvh, materials, textur
 // detail: 1.0 ~ 258k triangles (2^16 leaves x 5 slots, 17 levels). Smaller = coarser
 // tessellation of the same rooms/objects (for tests). texSize: texture edge in texels.
 crt_scene* crtSceneCreateStaircase(float detail, int texSize, int primsPerLeaf);
+// The same scene with the BVH built by the surface-area heuristic inside the same complete-tree layout (buildMode 1;
+// 0 = the reference author's median split, what crtSceneCreateStaircase does). Same file format, same hits.
+crt_scene* crtSceneCreateStaircaseEx(float detail, int texSize, int primsPerLeaf, int buildMode);
 // Mesh from a BVH_00.04 file + the procedural textures/material table.
 crt_scene* crtSceneLoadBVH(const char* path, int texSize);
 // Scene from caller triangles (copied); builds the BVH. materials/textures = staircase tables.

@@ -91,6 +91,8 @@ def host_lib():
         L = C.CDLL(path)
         L.crtSceneCreateStaircase.restype = C.c_void_p
         L.crtSceneCreateStaircase.argtypes = [C.c_float, C.c_int, C.c_int]
+        L.crtSceneCreateStaircaseEx.restype = C.c_void_p
+        L.crtSceneCreateStaircaseEx.argtypes = [C.c_float, C.c_int, C.c_int, C.c_int]
         L.crtSceneLoadBVH.restype = C.c_void_p
         L.crtSceneLoadBVH.argtypes = [C.c_char_p, C.c_int]
         L.crtSceneFromTriangles.restype = C.c_void_p
@@ -181,7 +183,9 @@ class Scene:
         self.ks = host_lib().crtSceneKernelScene(handle).contents
 
     @classmethod
-    def staircase(cls, detail=1.0, tex_size=1024, prims_per_leaf=5):
+    def staircase(cls, detail=1.0, tex_size=1024, prims_per_leaf=5, sah=False):
+        if sah:  # same mesh, BVH split by the surface-area heuristic inside the same complete-tree layout
+            return cls(host_lib().crtSceneCreateStaircaseEx(detail, tex_size, prims_per_leaf, 1))
         return cls(host_lib().crtSceneCreateStaircase(detail, tex_size, prims_per_leaf))
 
     @classmethod

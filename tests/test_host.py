@@ -73,6 +73,20 @@ def test_bvh_builder_invariants(small_scene):
     assert mesh_ids[~np.isinf(tris[:, 0])].max() < 20
 
 
+def test_sah_builder_same_layout_same_triangles(crt, small_scene):
+    """BUILD_SAH: the same complete-tree BVH_00.04 layout, every triangle stored exactly once, all the tree
+    invariants of the traversal -- only the split positions differ."""
+    sah = crt.Scene.staircase(0.1, 32, 5, sah=True)
+    assert sah.num_nodes == small_scene.num_nodes and sah.num_slots == small_scene.num_slots
+    assert sah.num_real_triangles == small_scene.num_real_triangles and sah.hash() != small_scene.hash()
+    tris, nodes = sah.triangles().copy(), sah.nodes().copy()
+    _check_tree(nodes, tris, 5)
+    real = lambda t: sorted(map(tuple, t[~np.isinf(t[:, 0])].view(np.uint32).tolist()))
+    assert real(tris) == real(small_scene.triangles().copy())
+    assert np.array_equal(sah.bounds()[0], small_scene.bounds()[0]) and np.array_equal(sah.bounds()[1], small_scene.bounds()[1])
+    sah.close()
+
+
 @pytest.mark.parametrize("n,ppl", [(0, 5), (1, 5), (5, 5), (6, 5), (37, 1), (100, 3)])
 def test_bvh_builder_ragged_inputs(crt, n, ppl):
     rng = np.random.default_rng(n * 31 + ppl)

@@ -151,3 +151,15 @@ def test_cpu_oracle_bsdf_presets_vs_golden_reference_outputs(oracle):
         assert np.allclose(got[ok, 0:3], ref[ok, 0:3], rtol=2e-5, atol=2e-5), preset
         assert np.allclose(got[ok, 3], ref[ok, 3], rtol=2e-5, atol=1e-6), preset
         assert np.allclose(got[ok, 4:7], ref[ok, 4:7], rtol=2e-5, atol=1e-6), preset
+
+
+def test_sah_tree_gives_the_same_frame_with_fewer_visits(oracle, crt, golden_scene):
+    """The SAH-built tree (same layout, same triangles) is a pure acceleration change: the CPU oracle renders the same frame
+    bit for bit and the same hit records, visiting fewer nodes and testing fewer triangles."""
+    sah = crt.Scene.staircase(0.1, 32, 5, sah=True)
+    a, ca = oracle.render(golden_scene, META["nx"], META["ny"], 4, 16, count=True)
+    b, cb = oracle.render(sah, META["nx"], META["ny"], 4, 16, count=True)
+    assert np.array_equal(a, b)
+    assert (ca["primary"], ca["secondary"], ca["shadow"]) == (cb["primary"], cb["secondary"], cb["shadow"])
+    assert cb["nodeVisits"] < 0.9 * ca["nodeVisits"] and cb["triTests"] < 0.8 * ca["triTests"]
+    sah.close()

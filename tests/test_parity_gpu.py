@@ -339,6 +339,22 @@ def test_side_by_side_with_reference_kernel(crt, oracle, medium_scene):
     assert np.array_equal(drop, img)
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(G), "..", "oracle", "_ref", "ref_driver")), reason="oracle/_ref not built")
+def test_side_by_side_on_a_sah_built_tree(crt, oracle, tmp_path):
+    """The opt-in SAH builder writes the same BVH_00.04 layout: the reference kernel reads the file like any scene of its own,
+    and on the same tree both kernels visit in the same order -- identical frames, as with the median tree."""
+    nx, ny, ns, depth = 200, 150, 12, 64
+    scene = crt.Scene.staircase(0.25, 64, 5, sah=True)
+    path = str(tmp_path / "sah.bvh")
+    assert scene.save_bvh(path) == 0
+    ref, _ = oracle.ref_render(path, 64, 5, nx, ny, ns, depth, str(tmp_path / "r.ref"))
+    with crt.Frame(scene, nx, ny, depth) as fr:
+        img = fr.run(ns)
+    within, psnr, exact = frame_stats(img, ref)
+    assert within >= 0.999 and psnr >= 50.0 and exact == 1.0, (within, psnr, exact)
+    scene.close()
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(G), "..", "oracle", "_ref", "ref_shim_driver")), reason="oracle/_ref not built")
 def test_large_ray_batch_side_by_side(crt, oracle, medium_scene):
     n = 1 << 20

@@ -23,10 +23,11 @@ def main():
     ap.add_argument("--slots", type=int, default=0)
     ap.add_argument("--budget", type=int, default=0)
     ap.add_argument("--min-active", type=int, default=0)
+    ap.add_argument("--sah", action="store_true", help="BVH split by the surface-area heuristic (same layout, same hits)")
     ap.add_argument("--profile", action="store_true", help="per-kernel-family CUDA events (serialised iterations)")
     args = ap.parse_args()
     crt.set_options(slots_per_pixel=args.slots, trace_budget=args.budget, trace_min_active=args.min_active)
-    scene = crt.Scene.staircase(args.detail, args.tex, 5)
+    scene = crt.Scene.staircase(args.detail, args.tex, 5, sah=args.sah)
     with crt.Frame(scene, args.nx, args.ny, args.depth) as fr:
         fr.run(args.ns, copy=False)
         if args.profile:
