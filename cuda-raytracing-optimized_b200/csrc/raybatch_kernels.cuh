@@ -9,12 +9,17 @@
 #include "device_scene.cuh"
 #include "rng.cuh"
 #include "traverse.cuh"
+#include "wide_traverse.cuh"
 
 template <bool COUNT>
 __global__ void __launch_bounds__(256, 5) intersectBatchKernel(MeshView mesh, const float4* __restrict__ triShade,
                                                             const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                             unsigned long long n, float4* __restrict__ outHit, int* __restrict__ outMesh,
-                                                            unsigned long long* cursor, unsigned long long* counts) {
+                                                            unsigned long long* cursor, unsigned long long* counts,
+                                                            const unsigned int* __restrict__ indices, const unsigned long long* nDevice, int anyHit) {
+    // anyHit: hitMesh(.., isShadow = true): t = 0.0f when anything lies in (tMin, tMax), FLT_MAX otherwise (kernels.cu:207)
+    // indices != nullptr: the rays to trace are rayO[indices[k]], k < *nDevice (the rays the wide walk could not certify)
+    if (nDevice) n = *nDevice;
     __shared__ RayCold coldAll[256];
     __shared__ float tMinAll[256];
     RayCold& c = coldAll[threadIdx.x];
@@ -37,9 +42,9 @@ __global__ void __launch_bounds__(256, 5) intersectBatchKernel(MeshView mesh, co
             if (base + __popc(mask) >= n) exhausted = true;
             const unsigned long long i = base + __popc(mask & ((1u << lane) - 1u));
             if (!live && i < n) {
-                index = i;
-                const float4 ro = __ldg(rayO + i);
-                const float4 rd = __ldg(rayD + i);
+                index = indices ? (unsigned long long)indices[i] : i;
+                const float4 ro = __ldg(rayO + index);
+                const float4 rd = __ldg(rayD + index);
                 prepRay(r, c, xyz(ro), unit(xyz(rd)), rd.w);
                 tMinAll[threadIdx.x] = ro.w;
                 c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), 0.0f);
@@ -53,13 +58,17 @@ __global__ void __launch_bounds__(256, 5) intersectBatchKernel(MeshView mesh, co
             liveMask = __ballot_sync(0xFFFFFFFFu, live);
         }
         if (liveMask == 0u) break;
-        travRound<false>(mesh, r, c, tMinAll[threadIdx.x], false, live, s, steps, max(1, min(TRACE_NODE_QUORUM, __popc(liveMask) >> 1)), nodeVisits, triTests);
+        travRound<false>(mesh, r, c, tMinAll[threadIdx.x], anyHit != 0, live, s, steps, max(1, min(TRACE_NODE_QUORUM, __popc(liveMask) >> 1)), nodeVisits, triTests);
         if (live && s.idx == 0u) {
             float t = s.closest;
             unsigned int triId = __float_as_uint(c.rec.z);
             float u = c.rec.x, v = c.rec.y;
             int meshID = -1;
-            if (t < c.dir.w) {
+            if (anyHit && t < c.dir.w) {
+                t = 0.0f;
+                triId = 0xFFFFFFFFu;
+                u = v = 0.0f;
+            } else if (t < c.dir.w) {
                 meshID = __float_as_int(__ldg(triShade + 3 * triId).w);
             } else {
                 t = FLT_MAX;
@@ -68,6 +77,97 @@ __global__ void __launch_bounds__(256, 5) intersectBatchKernel(MeshView mesh, co
             }
             outHit[index] = make_float4(t, u, v, __uint_as_float(triId));
             outMesh[index] = meshID;
+            live = false;
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&counts[0], (unsigned long long)nodeVisits);
+        atomicAdd(&counts[1], (unsigned long long)triTests);
+    }
+}
+
+// The same query through the renderer's own wide tree (wide_traverse.cuh). Rays whose result the certificate does not
+// cover are not answered here: their indices go to `redo` and the order-exact kernel above answers them.
+// Dynamic shared memory: wide.stackDepth * 256 uint2.
+template <bool COUNT, bool CERTIFY>
+__global__ void __launch_bounds__(256, 4) wideIntersectBatchKernel(MeshView mesh, WideView wide, const float4* __restrict__ triShade,
+                                                                   const float4* __restrict__ rayO, const float4* __restrict__ rayD,
+                                                                   unsigned long long n, float4* __restrict__ outHit, int* __restrict__ outMesh,
+                                                                   unsigned long long* cursor, unsigned long long* counts, unsigned int* __restrict__ redo,
+                                                                   unsigned long long* redoCount, int anyHit) {
+    extern __shared__ uint2 wideStackAll[];
+    __shared__ RayCold coldAll[256];
+    __shared__ float tMinAll[256];
+    RayCold& c = coldAll[threadIdx.x];
+    uint2* stack = wideStackAll + threadIdx.x;
+    const unsigned int lane = threadIdx.x & 31u;
+    bool live = false, exhausted = false;
+    unsigned long long index = 0;
+    WideRay r;
+    WideTrav s;
+    unsigned int nodeVisits = 0, triTests = 0;
+    r.ox = r.oy = r.oz = r.ix = r.iy = r.iz = 0.0f; r.oct = 0u;
+    s.ngx = s.ngy = s.tgx = s.tgy = 0u; s.sp = -1; s.closest = 0.0f;
+    while (true) {
+        unsigned int liveMask = __ballot_sync(0xFFFFFFFFu, live);
+        if (!exhausted && __popc(liveMask) < 20) { // refill idle lanes, one atomic per warp
+            const unsigned int mask = ~liveMask;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(cursor, (unsigned long long)__popc(mask));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (base + __popc(mask) >= n) exhausted = true;
+            const unsigned long long i = base + __popc(mask & ((1u << lane) - 1u));
+            if (!live && i < n) {
+                index = i;
+                const float4 ro = __ldg(rayO + i);
+                const float4 rd = __ldg(rayD + i);
+                const f3 d = unit(xyz(rd)); // the ray constructor normalises (ray.h:9)
+                c.dir = mk4(d, rd.w);
+                tMinAll[threadIdx.x] = ro.w;
+                c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), 0.0f);
+                if (!wideSetup(wide, r, xyz(ro), d, anyHit != 0)) {
+                    redo[atomicAdd(redoCount, 1ull)] = (unsigned int)i;
+                } else {
+                    RayHot rh;
+                    rh.ox = ro.x; rh.oy = ro.y; rh.oz = ro.z;
+                    rh.ix = 1.0f / d.x; rh.iy = 1.0f / d.y; rh.iz = 1.0f / d.z;
+                    if (!rayHitsBounds(mesh, rh, rd.w)) { // hitMesh: scene bounds first (kernels.cu:297)
+                        outHit[i] = make_float4(FLT_MAX, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
+                        outMesh[i] = -1;
+                    } else {
+                        wideStart(s, rd.w);
+                        live = true;
+                    }
+                }
+            }
+            liveMask = __ballot_sync(0xFFFFFFFFu, live);
+        }
+        if (liveMask == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+        wideRound(wide, r, c, tMinAll[threadIdx.x], live, s, stack, 256u, max(1, min(TRACE_NODE_QUORUM, __popc(liveMask) >> 1)), nodeVisits, triTests);
+        if (live && s.sp < 0) {
+            float t = s.closest;
+            unsigned int triId = __float_as_uint(c.rec.z);
+            float u = c.rec.x, v = c.rec.y;
+            int meshID = -1;
+            bool certified = true;
+            if (triId != 0xFFFFFFFFu && t < c.dir.w) {
+                if (CERTIFY) certified = wideCertify(mesh, r, xyz(c.dir), c.dir.w, t, triId);
+                if (anyHit) { t = 0.0f; triId = 0xFFFFFFFFu; u = v = 0.0f; }
+                else meshID = __float_as_int(__ldg(triShade + 3 * triId).w);
+            } else {
+                t = FLT_MAX;
+                triId = 0xFFFFFFFFu;
+                u = v = 0.0f;
+            }
+            if (certified) {
+                outHit[index] = make_float4(t, u, v, __uint_as_float(triId));
+                outMesh[index] = meshID;
+            } else {
+                redo[atomicAdd(redoCount, 1ull)] = (unsigned int)index;
+            }
             live = false;
         }
     }

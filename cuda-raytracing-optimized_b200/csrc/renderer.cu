@@ -13,12 +13,15 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.h"
 #include "raybatch_kernels.cuh"
 #include "renderer_internal.h"
 #include "wavefront_kernels.cuh"
+#include "wide_bvh.h"
+#include "wide_traverse.cuh"
 
 void crtCheckCuda(cudaError_t result, const char* func, const char* file, int line) {
     if (result) {
@@ -31,6 +34,7 @@ void crtCheckCuda(cudaError_t result, const char* func, const char* file, int li
 RendererContext g_ctx;
 renderer_options g_opts = {-1, 0u, 0, 0, 0, {0, 0, 0}};
 static int g_profiling = 0;
+static int g_traversal = -1; // setRendererTraversal(); -1 = CRT_TRAVERSAL from the environment, else TRAVERSAL_WIDE
 
 static f3 toF3(const vec3& v) { return mk3(v.e[0], v.e[1], v.e[2]); }
 
@@ -214,6 +218,16 @@ extern "C" void setRendererOptions(const renderer_options* opt) {
 
 extern "C" void setRendererProfiling(int on) { g_profiling = on; }
 
+extern "C" void setRendererTraversal(int mode) { g_traversal = mode; }
+
+static int traversalMode() {
+    if (g_traversal >= 0) return g_traversal;
+    const char* v = std::getenv("CRT_TRAVERSAL"); // exact | wide | uncertified (diagnostics, A/B runs)
+    if (v && v[0] == 'e') return TRAVERSAL_EXACT;
+    if (v && v[0] == 'u') return TRAVERSAL_WIDE_UNCERTIFIED;
+    return TRAVERSAL_WIDE;
+}
+
 static void initCommon(RendererContext& c, const camera& cam, vec3** fb, int nx, int ny, int maxDepth) {
     if (g_opts.device >= 0) CRT_CHECK(cudaSetDevice(g_opts.device));
     int dev = 0;
@@ -260,7 +274,7 @@ static void initCommon(RendererContext& c, const camera& cam, vec3** fb, int nx,
     c.hostCtlFast = (MeshControl*)g_cache.hostCtlFast;
     c.hostCtl = (WfControl*)g_cache.hostCtl;
     c.laneSums = devAlloc<unsigned long long>(8);
-    c.batchScratch = devAlloc<unsigned long long>(4);
+    c.batchScratch = devAlloc<unsigned long long>(8);
     const size_t npix = (size_t)nx * ny;
     // The frame buffer the caller reads after runRenderer (kernels.cu:578-580 uses managed memory; main.cpp:105,119 only
     // ever dereferences it on the host): pinned, device-mapped host memory that finalizeKernel writes directly, so the frame
@@ -289,6 +303,13 @@ extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb,
 
     const mesh* m = sc.m;
     const unsigned int numSlots = m->numTris;
+    // our own tree is built on host threads from the caller's triangles while this thread uploads the scene
+    c.traversal = traversalMode();
+    WideBvhHost wideHost;
+    bool wideBuilt = false;
+    std::thread wideBuilder;
+    if (c.traversal != TRAVERSAL_EXACT && numSlots > 0)
+        wideBuilder = std::thread([&] { wideBuilt = buildWideBvh(m->tris, numSlots, 0, wideHost); });
     // triangles: upload the caller's 64-byte records once, re-tile on the device, drop the staging copy
     float* staging = (float*)arenaAlloc((size_t)(numSlots ? numSlots : 1) * sizeof(triangle));
     CRT_CHECK(cudaMemcpy(staging, m->tris, (size_t)numSlots * sizeof(triangle), cudaMemcpyHostToDevice));
@@ -363,6 +384,42 @@ extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb,
     CRT_CHECK(cudaMemcpy(c.texHeight, texH.data(), texH.size() * sizeof(int), cudaMemcpyHostToDevice));
 
     pt.mark("init: materials+textures");
+
+    // the wide tree: nodes and triangle order from the host build, leaf triangles re-tiled on the device
+    c.wide = WideView{};
+    if (wideBuilder.joinable()) wideBuilder.join();
+    pt.mark("init: wide tree (host build, overlapped)");
+    c.wideStats = wideHost.stats;
+    if (wideBuilt && wideHost.stats.maxDepth <= 24 && sc.numPrimitivesPerLeaf > 0 && firstLeaf > 0) {
+        const size_t nn = wideHost.nodes.size(), nt = wideHost.triOrig.size();
+        uint4* dNodes = (uint4*)arenaAlloc(nn * sizeof(WideNode));
+        unsigned int* dOrig = devAlloc<unsigned int>(nt);
+        float4* dTriA = devAlloc<float4>(2 * nt);
+        float2* dTriB = devAlloc<float2>(nt);
+        unsigned int* dBad = devAlloc<unsigned int>(1);
+        CRT_CHECK(cudaMemcpy(dNodes, wideHost.nodes.data(), nn * sizeof(WideNode), cudaMemcpyHostToDevice));
+        CRT_CHECK(cudaMemcpy(dOrig, wideHost.triOrig.data(), nt * sizeof(unsigned int), cudaMemcpyHostToDevice));
+        CRT_CHECK(cudaMemset(dBad, 0, sizeof(unsigned int)));
+        wideTrianglesKernel<<<(unsigned int)((nt + 255) / 256), 256>>>(staging, dOrig, (unsigned int)nt, dTriA, dTriB);
+        checkRefTreeKernel<<<(unsigned int)((m->numBvhNodes + 255) / 256), 256>>>(nodeStaging, (unsigned int)m->numBvhNodes, dBad);
+        CRT_CHECK(cudaGetLastError());
+        unsigned int bad = 0;
+        CRT_CHECK(cudaMemcpy(&bad, dBad, sizeof(bad), cudaMemcpyDeviceToHost));
+        if (bad == 0) { // (else: the caller's boxes do not nest, the certificate's premise fails: exact traversal only)
+            c.wide.nodes = dNodes;
+            c.wide.triA = dTriA;
+            c.wide.triB = dTriB;
+            c.wide.rangeX = WIDE_ORIGIN_RANGE * wideHost.range[0];
+            c.wide.rangeY = WIDE_ORIGIN_RANGE * wideHost.range[1];
+            c.wide.rangeZ = WIDE_ORIGIN_RANGE * wideHost.range[2];
+            c.wide.stackDepth = (unsigned int)wideHost.stats.maxDepth;
+        }
+        if (pt.on)
+            std::fprintf(stderr, "[crt timing] wide tree: %u nodes, %u triangles, depth %d, build %.2f ms (binary %.2f, collapse %.2f) on %d threads, ref tree nests: %s\n",
+                         wideHost.stats.numNodes, wideHost.stats.numTris, wideHost.stats.maxDepth, wideHost.stats.msTotal, wideHost.stats.msBinary,
+                         wideHost.stats.msCollapse, wideHost.stats.threads, bad ? "NO" : "yes");
+    }
+    pt.mark("init: wide tree upload");
     // light: RenderContext default members, kernels.cu:93-94
     c.light.center = mk3(52.514355f, 715.686951f, -272.620972f);
     c.light.radius = 50.0f;
@@ -774,6 +831,21 @@ extern "C" void getRendererTraversalCounts(unsigned long long* nodeVisits, unsig
     if (triTests) *triTests = g_ctx.lastTriTests;
 }
 
+extern "C" void getRendererWideInfo(renderer_wide_info* out) {
+    if (!out) return;
+    const RendererContext& c = g_ctx;
+    out->active = c.initialised && c.wide.stackDepth > 0 && c.traversal != TRAVERSAL_EXACT;
+    out->traversal = c.traversal;
+    out->numNodes = c.wideStats.numNodes;
+    out->numTriangles = c.wideStats.numTris;
+    out->depth = c.wideStats.maxDepth;
+    out->buildThreads = c.wideStats.threads;
+    out->buildMs = (float)c.wideStats.msTotal;
+    out->sahCost = (float)c.wideStats.sahCost;
+    out->lastBatchRedo = c.lastBatchRedo;
+    out->lastFrameRedo = c.lastFrameRedo;
+}
+
 extern "C" void getRendererChaserCounts(unsigned long long* raysExtend, unsigned long long* raysShadow, unsigned long long* nodeVisits,
                                         unsigned long long* triTests) {
     if (raysExtend) *raysExtend = g_ctx.chaserRays;
@@ -794,6 +866,7 @@ extern "C" void cleanupRenderer() {
     c.texPtrHost.clear();
     arenaReset(); // every device pointer of the frame dies here; the memory stays with the process for the next frame
     const bool reset = c.opts.resetDeviceOnCleanup != 0;
+    if (c.batchRedo) cudaFree(c.batchRedo);
     c = RendererContext();
     pt.mark("cleanup");
     if (reset) { // kernels.cu:679
@@ -803,35 +876,62 @@ extern "C" void cleanupRenderer() {
 }
 
 // ------------------------------------------------------------- ray batches --
+extern "C" float intersectBatchDeviceEx(const void* dRayO, const void* dRayD, long long n, void* dHit, int* dMeshId, int anyHit);
 extern "C" float intersectBatchDevice(const void* dRayO, const void* dRayD, long long n, void* dHit, int* dMeshId) {
+    return intersectBatchDeviceEx(dRayO, dRayD, n, dHit, dMeshId, 0);
+}
+
+extern "C" float intersectBatchDeviceEx(const void* dRayO, const void* dRayD, long long n, void* dHit, int* dMeshId, int anyHit) {
     RendererContext& c = g_ctx;
     if (!c.initialised || c.kind != SCENE_MESH) {
         std::fprintf(stderr, "intersectBatchDevice needs a mesh scene (initRenderer)\n");
         std::exit(99);
     }
-    unsigned long long* cursor = c.batchScratch;
-    unsigned long long* counts = c.batchScratch + 2;
-    CRT_CHECK(cudaMemsetAsync(cursor, 0, 2 * sizeof(unsigned long long), c.stream));
-    CRT_CHECK(cudaMemsetAsync(counts, 0, 2 * sizeof(unsigned long long), c.stream));
+    unsigned long long* cursor = c.batchScratch;      // [0] cursor of the first kernel, [1] of the second
+    unsigned long long* counts = c.batchScratch + 2;  // [2], [3] visits / tests, [4] rays left to the exact kernel
+    CRT_CHECK(cudaMemsetAsync(c.batchScratch, 0, 5 * sizeof(unsigned long long), c.stream));
+    const bool useWide = c.wide.stackDepth > 0 && c.traversal != TRAVERSAL_EXACT;
+    if (useWide && c.batchRedoCap < (size_t)n) {
+        if (c.batchRedo) CRT_CHECK(cudaFree(c.batchRedo)); // per-call scratch: plain allocation, not the frame's arena
+        CRT_CHECK(cudaMalloc((void**)&c.batchRedo, (size_t)n * sizeof(unsigned int)));
+        c.batchRedoCap = (size_t)n;
+    }
     const int blocks = c.numSMs * 8;
     CRT_CHECK(cudaEventRecord(c.evStart, c.stream));
-    if (c.counting)
-        intersectBatchKernel<true><<<blocks, WF_BLOCK, 0, c.stream>>>(c.mesh, c.triShade, (const float4*)dRayO, (const float4*)dRayD,
-                                                                    (unsigned long long)n, (float4*)dHit, dMeshId, cursor, counts);
-    else
-        intersectBatchKernel<false><<<blocks, WF_BLOCK, 0, c.stream>>>(c.mesh, c.triShade, (const float4*)dRayO, (const float4*)dRayD,
-                                                                     (unsigned long long)n, (float4*)dHit, dMeshId, cursor, counts);
+    const float4* rayO = (const float4*)dRayO;
+    const float4* rayD = (const float4*)dRayD;
+    if (useWide) {
+        const size_t smem = (size_t)c.wide.stackDepth * 256 * sizeof(uint2);
+        const bool certify = c.traversal != TRAVERSAL_WIDE_UNCERTIFIED;
+        auto launch = [&](auto kernel) {
+            CRT_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int perSM = 1;
+            CRT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, 256, smem));
+            kernel<<<c.numSMs * (perSM > 0 ? perSM : 1), 256, smem, c.stream>>>(c.mesh, c.wide, c.triShade, rayO, rayD, (unsigned long long)n, (float4*)dHit,
+                                                                                dMeshId, cursor, counts, c.batchRedo, c.batchScratch + 4, anyHit);
+        };
+        if (c.counting) { if (certify) launch(wideIntersectBatchKernel<true, true>); else launch(wideIntersectBatchKernel<true, false>); }
+        else { if (certify) launch(wideIntersectBatchKernel<false, true>); else launch(wideIntersectBatchKernel<false, false>); }
+        // the rays the certificate does not cover, in the reference's visiting order (device-side count: no host round trip)
+        intersectBatchKernel<false><<<c.numSMs, WF_BLOCK, 0, c.stream>>>(c.mesh, c.triShade, rayO, rayD, 0ull, (float4*)dHit, dMeshId, cursor + 1, counts,
+                                                                        c.batchRedo, c.batchScratch + 4, anyHit);
+    } else if (c.counting) {
+        intersectBatchKernel<true><<<blocks, WF_BLOCK, 0, c.stream>>>(c.mesh, c.triShade, rayO, rayD, (unsigned long long)n, (float4*)dHit, dMeshId, cursor,
+                                                                    counts, nullptr, nullptr, anyHit);
+    } else {
+        intersectBatchKernel<false><<<blocks, WF_BLOCK, 0, c.stream>>>(c.mesh, c.triShade, rayO, rayD, (unsigned long long)n, (float4*)dHit, dMeshId, cursor,
+                                                                     counts, nullptr, nullptr, anyHit);
+    }
     CRT_CHECK(cudaEventRecord(c.evStop, c.stream));
     CRT_CHECK(cudaGetLastError());
     CRT_CHECK(cudaStreamSynchronize(c.stream));
     float ms = 0.0f;
     CRT_CHECK(cudaEventElapsedTime(&ms, c.evStart, c.evStop));
-    if (c.counting) {
-        unsigned long long h[2];
-        CRT_CHECK(cudaMemcpy(h, counts, sizeof(h), cudaMemcpyDeviceToHost));
-        c.lastNodeVisits = h[0];
-        c.lastTriTests = h[1];
-    }
+    unsigned long long h[3];
+    CRT_CHECK(cudaMemcpy(h, counts, sizeof(h), cudaMemcpyDeviceToHost));
+    c.lastNodeVisits = h[0];
+    c.lastTriTests = h[1];
+    c.lastBatchRedo = h[2];
     return ms;
 }
 

@@ -9,11 +9,13 @@
 
 #include "device_scene.cuh"
 #include "mesh_pipeline.cuh"
+#include "wide_traverse.cuh"
 #include "kernels.h"
 
 #define CRT_CHECK(val) crtCheckCuda((val), #val, __FILE__, __LINE__)
 void crtCheckCuda(cudaError_t result, const char* func, const char* file, int line);
 
+enum TraversalMode { TRAVERSAL_WIDE = 0, TRAVERSAL_EXACT = 1, TRAVERSAL_WIDE_UNCERTIFIED = 2 };
 enum SceneKind { SCENE_NONE = 0, SCENE_MESH = 1, SCENE_SPHERES = 2 };
 
 struct RendererContext {
@@ -38,6 +40,12 @@ struct RendererContext {
     int numTextures = 0;
     unsigned int numTriSlots = 0;
     MeshView mesh;
+    // the renderer's own wide tree (wide_bvh.h); wide.stackDepth == 0: not built / not usable, exact traversal only
+    WideView wide = {};
+    unsigned int* batchRedo = nullptr; // ray indices the wide walk could not certify (intersectBatchDevice)
+    size_t batchRedoCap = 0;
+    WideBvhStats wideStats;
+    int traversal = 0;                 // TRAVERSAL_* in effect for this scene
 
     // sphere scene
     int numSpheres = 0;
@@ -62,7 +70,7 @@ struct RendererContext {
     int samplesDone = 0; // samples per pixel in the sums (runRenderer sets, continueRenderer adds)
     int traceBlocks = 0; // persistent grid of traceKernel: one resident wave
     bool counting = false;
-    unsigned long long lastNodeVisits = 0, lastTriTests = 0;
+    unsigned long long lastNodeVisits = 0, lastTriTests = 0, lastBatchRedo = 0, lastFrameRedo = 0;
     unsigned long long chaserRays = 0, chaserShadowRays = 0, chaserNodeVisits = 0, chaserTriTests = 0; // the chaser's share of the last frame
     renderer_stats stats = {};
 };

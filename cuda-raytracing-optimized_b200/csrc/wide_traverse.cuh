@@ -1,0 +1,258 @@
+// wide_traverse.cuh -- traversal of the renderer's own 8-wide quantised BVH (wide_bvh.h) plus the certificate that keeps the
+// result THE REFERENCE'S result.
+//
+// What the reference computes (hitBvh, kernels.cu:154-224) is "the smallest triangleHit() over the triangles its walk
+// reaches"; its tree decides the answer only through (i) which of two exactly tied triangles is met first and (ii) box
+// tests that cull, by a last-ulp rounding, a leaf whose triangle test would have passed. The fast walk below evaluates the
+// SAME triangle test (triHit, intersect.cuh) over a conservative tree, i.e. it finds the true minimum over all triangles,
+// and then proves that the reference finds the same triangle:
+//   * near-tie flag: box culling and triangle acceptance use closest * (1 + 1e-5), so every triangle within that margin of
+//     the winner is seen; if there is one, the ray is flagged;
+//   * leaf certificate: the reference tests the winner's leaf iff the leaf's box (and every ancestor's) passes
+//     hit_bbox_dist(box, ray, closest) < closest with ITS `closest` at that moment, which is >= min(t_max, 1.00001 * t_win)
+//     when no near-tie exists. Parent boxes contain their children's and the slab arithmetic (intersections.h:25-41) is
+//     monotonic in the box coordinates, so the leaf's box decides for all its ancestors: ONE reference-arithmetic box test
+//     per found hit. If it fails, the ray is flagged.
+//   * any-hit rays: `closest` stays t_max until the first hit, so the same test with t_max certifies "occluded".
+//   * a miss needs no certificate: the reference's answer is always one of the triangle tests that pass.
+// Flagged rays (measured: ~3 in 100 000) are re-traced by the order-exact kernel (traverse.cuh), which is also the checker
+// in the tests. The containment assumption about the caller's tree is verified on the device at initRenderer
+// (checkRefTreeKernel); if it does not hold, every ray takes the exact kernel.
+#pragma once
+
+#include "traverse.cuh"
+#include "wide_bvh.h"
+
+#define WIDE_TIE_MARGIN 1.00001f
+#define WIDE_FLAG_TIE 0x100u     // WideRay::oct: a second triangle within the margin of the current best was seen
+#define WIDE_FLAG_ANYHIT 0x200u
+
+struct WideView {
+    const uint4* __restrict__ nodes;   // 96-byte records (wide_bvh.h)
+    const float4* __restrict__ triA;   // per leaf triangle {v0.xyz, e1.x}{e1.yz, e2.xy}
+    const float2* __restrict__ triB;   //                   {e2.z, caller's slot index}
+    float rangeX, rangeY, rangeZ;      // |origin| limit of the fast path (WIDE_ORIGIN_RANGE x coordinate range)
+    unsigned int stackDepth;           // entries per thread (>= wide tree depth); 0 = no wide tree: exact kernel only
+};
+
+struct WideRay {
+    float ox, oy, oz;
+    float ix, iy, iz;    // 1 / direction with |direction| clamped to >= 1e-20 (no inf * 0 in t = m * A + B)
+    unsigned int oct;    // bits 0..2: 4 = d.x >= 0, 2 = d.y >= 0, 1 = d.z >= 0 ("octinv"); WIDE_FLAG_*
+};
+
+struct WideTrav {
+    unsigned int ngx, ngy;  // node group: child base | hits in priority order (bits 24..31) + imask (bits 0..7)
+    unsigned int tgx, tgy;  // triangle group: triangle base | mask of triangles still to test (24 bits)
+    int sp;                 // entries on the stack; -1 = traversal finished
+    float closest;
+};
+
+__device__ __forceinline__ void ldg256u(const void* p, uint4& a, uint4& b) {
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+        : "l"(p));
+}
+
+// byte j of `w` (0x80 | q) as the float 1 + q/128: one PRMT
+template <int J>
+__device__ __forceinline__ float planeFloat(unsigned int w) {
+    return __uint_as_float(__byte_perm(w, 0x3F000000u, 0x7044 | (J << 8)));
+}
+
+// Sets the ray up. Returns false when the fast path does not take it (origin outside the range the padding covers, or a
+// non-finite direction): the caller hands it to the exact kernel.
+__device__ __forceinline__ bool wideSetup(const WideView& w, WideRay& r, const f3& o, const f3& d, bool anyHit) {
+    r.ox = o.x; r.oy = o.y; r.oz = o.z;
+    const float dx = fabsf(d.x) < 1e-20f ? copysignf(1e-20f, d.x) : d.x;
+    const float dy = fabsf(d.y) < 1e-20f ? copysignf(1e-20f, d.y) : d.y;
+    const float dz = fabsf(d.z) < 1e-20f ? copysignf(1e-20f, d.z) : d.z;
+    r.ix = 1.0f / dx; r.iy = 1.0f / dy; r.iz = 1.0f / dz;
+    r.oct = (d.x < 0.0f ? 0u : 4u) | (d.y < 0.0f ? 0u : 2u) | (d.z < 0.0f ? 0u : 1u) | (anyHit ? WIDE_FLAG_ANYHIT : 0u);
+    const bool finite = (fabsf(d.x) <= 1.0f) && (fabsf(d.y) <= 1.0f) && (fabsf(d.z) <= 1.0f); // false for NaN
+    return finite && fabsf(o.x) <= w.rangeX && fabsf(o.y) <= w.rangeY && fabsf(o.z) <= w.rangeZ;
+}
+
+__device__ __forceinline__ void wideStart(WideTrav& s, float tMax) {
+    s.ngx = 0u;
+    s.ngy = 0x01000000u; // a virtual group whose only hit child is node 0 (imask 0: relative index 0)
+    s.tgx = 0u; s.tgy = 0u;
+    s.sp = 0;
+    s.closest = tMax;
+}
+
+__device__ __forceinline__ void widePop(WideTrav& s, const uint2* stack, unsigned int stride) {
+    if (s.sp > 0) {
+        s.sp--;
+        const uint2 g = stack[(unsigned int)s.sp * stride];
+        s.ngx = g.x; s.ngy = g.y;
+    } else {
+        s.sp = -1;
+    }
+}
+
+// one child: slab distances from the six plane bytes, hit test, one bit of the slot mask
+#define WIDE_CHILD(J, SLOT, NX, FX, NY, FY, NZ, FZ)                                                    \
+    {                                                                                                  \
+        const float tnx = __fmaf_rn(planeFloat<J>(NX), ax, bx), tfx = __fmaf_rn(planeFloat<J>(FX), ax, bx); \
+        const float tny = __fmaf_rn(planeFloat<J>(NY), ay, by), tfy = __fmaf_rn(planeFloat<J>(FY), ay, by); \
+        const float tnz = __fmaf_rn(planeFloat<J>(NZ), az, bz), tfz = __fmaf_rn(planeFloat<J>(FZ), az, bz); \
+        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));                                     \
+        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, limit));                                    \
+        if (tn <= tf) hits |= 1u << (SLOT);                                                            \
+    }
+
+// One wide-node step: take the nearest pending child of the node group, test its 8 children, form the new groups.
+__device__ __forceinline__ void wideNodeStep(const WideView& w, const WideRay& r, WideTrav& s, uint2* stack, unsigned int stride) {
+    const unsigned int bit = 31u - (unsigned int)__clz(s.ngy);
+    s.ngy &= ~(1u << bit);
+    if (s.ngy > 0x00FFFFFFu) {
+        stack[(unsigned int)s.sp * stride] = make_uint2(s.ngx, s.ngy);
+        s.sp++;
+    }
+    const unsigned int slot = (bit - 24u) ^ (r.oct & 7u);
+    const unsigned int idx = s.ngx + __popc(s.ngy & ((1u << slot) - 1u) & 0xFFu);
+    const char* rec = (const char*)w.nodes + 96ull * idx;
+    uint4 h0, h1, q0, q1, q2, q3;
+    ldg256u(rec, h0, h1);        // p.xyz, e|imask, childBase, triBase, meta lo, meta hi
+    ldg256u(rec + 32, q0, q1);   // qlo x, x', y, y' | z, z', qhi x, x'
+    ldg256u(rec + 64, q2, q3);   // qhi y, y', z, z' | scale xyz, spare
+    const float ax = __uint_as_float(q3.x) * r.ix, ay = __uint_as_float(q3.y) * r.iy, az = __uint_as_float(q3.z) * r.iz;
+    const float bx = __fmaf_rn(__uint_as_float(h0.x) - r.ox, r.ix, -ax);
+    const float by = __fmaf_rn(__uint_as_float(h0.y) - r.oy, r.iy, -ay);
+    const float bz = __fmaf_rn(__uint_as_float(h0.z) - r.oz, r.iz, -az);
+    const float limit = (r.oct & WIDE_FLAG_ANYHIT) ? s.closest : s.closest * WIDE_TIE_MARGIN;
+    const bool px = (r.oct & 4u) != 0u, py = (r.oct & 2u) != 0u, pz = (r.oct & 1u) != 0u;
+    // near / far plane words per axis and half (slots 0..3, 4..7)
+    const unsigned int nx0 = px ? q0.x : q1.z, nx1 = px ? q0.y : q1.w, fx0 = px ? q1.z : q0.x, fx1 = px ? q1.w : q0.y;
+    const unsigned int ny0 = py ? q0.z : q2.x, ny1 = py ? q0.w : q2.y, fy0 = py ? q2.x : q0.z, fy1 = py ? q2.y : q0.w;
+    const unsigned int nz0 = pz ? q1.x : q2.z, nz1 = pz ? q1.y : q2.w, fz0 = pz ? q2.z : q1.x, fz1 = pz ? q2.w : q1.y;
+    unsigned int hits = 0u;
+    WIDE_CHILD(0, 0, nx0, fx0, ny0, fy0, nz0, fz0)
+    WIDE_CHILD(1, 1, nx0, fx0, ny0, fy0, nz0, fz0)
+    WIDE_CHILD(2, 2, nx0, fx0, ny0, fy0, nz0, fz0)
+    WIDE_CHILD(3, 3, nx0, fx0, ny0, fy0, nz0, fz0)
+    WIDE_CHILD(0, 4, nx1, fx1, ny1, fy1, nz1, fz1)
+    WIDE_CHILD(1, 5, nx1, fx1, ny1, fy1, nz1, fz1)
+    WIDE_CHILD(2, 6, nx1, fx1, ny1, fy1, nz1, fz1)
+    WIDE_CHILD(3, 7, nx1, fx1, ny1, fy1, nz1, fz1)
+    const unsigned int imask = h0.w >> 24;
+    // inner hits -> priority order: bit (slot ^ octinv), three conditional swaps of an 8-bit mask
+    unsigned int prio = hits & imask;
+    if (r.oct & 1u) prio = ((prio & 0x55u) << 1) | ((prio >> 1) & 0x55u);
+    if (r.oct & 2u) prio = ((prio & 0x33u) << 2) | ((prio >> 2) & 0x33u);
+    if (r.oct & 4u) prio = ((prio & 0x0Fu) << 4) | ((prio >> 4) & 0x0Fu);
+    s.ngx = h1.x;
+    s.ngy = (prio << 24) | imask;
+    // leaf hits -> mask of the triangles to test (meta = count << 5 | offset)
+    unsigned int leafHits = hits & ~imask, tris = 0u;
+    while (leafHits) {
+        const unsigned int sl = (unsigned int)__ffs((int)leafHits) - 1u;
+        leafHits &= leafHits - 1u;
+        const unsigned int meta = ((sl < 4u ? h1.z : h1.w) >> (8u * (sl & 3u))) & 0xFFu;
+        tris |= ((1u << (meta >> 5)) - 1u) << (meta & 31u);
+    }
+    s.tgx = h1.y;
+    s.tgy = tris;
+    if (tris == 0u && s.ngy <= 0x00FFFFFFu) widePop(s, stack, stride);
+}
+
+// The triangles of the lane's triangle group (kernels.cu:200-216 with the near-tie margin). c.rec = {u, v, winner slot, user}.
+__device__ __forceinline__ void wideTriPhase(const WideView& w, WideRay& r, RayCold& c, float tMin, WideTrav& s, const uint2* stack,
+                                             unsigned int stride, unsigned int& triTests) {
+    RayPrep rp;
+    rp.o = mk3(r.ox, r.oy, r.oz);
+    rp.d = xyz(c.dir);
+    const bool anyHit = (r.oct & WIDE_FLAG_ANYHIT) != 0u;
+    while (s.tgy) {
+        const unsigned int k = s.tgx + (unsigned int)__ffs((int)s.tgy) - 1u;
+        s.tgy &= s.tgy - 1u;
+        float4 t0, t1;
+        ldg256(w.triA + 2ull * k, t0, t1);
+        const float2 t2 = __ldg(w.triB + k);
+        triTests++;
+        const float limit = anyHit ? s.closest : s.closest * WIDE_TIE_MARGIN;
+        float u, v;
+        const float hitT = triHit(mk3(t0.x, t0.y, t0.z), mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), rp, tMin, limit, u, v);
+        if (hitT < limit) {
+            if (anyHit) { // kernels.cu:207: the first hit ends an any-hit walk
+                s.closest = hitT;
+                c.rec.z = t2.y;
+                s.tgy = 0u;
+                s.sp = -1;
+                return;
+            }
+            if (hitT < s.closest) {
+                // new best; the previous one (and whatever was accepted before it) may lie within the margin of the new one
+                r.oct = (s.closest <= hitT * WIDE_TIE_MARGIN) ? (r.oct | WIDE_FLAG_TIE) : (r.oct & ~WIDE_FLAG_TIE);
+                s.closest = hitT;
+                c.rec.x = u;
+                c.rec.y = v;
+                c.rec.z = t2.y;
+            } else if (__float_as_uint(t2.y) != __float_as_uint(c.rec.z)) {
+                r.oct |= WIDE_FLAG_TIE;
+            }
+        }
+    }
+    if (s.ngy <= 0x00FFFFFFu) widePop(s, stack, stride);
+}
+
+// One scheduling round of a warp (all 32 lanes call it together), the policy of travRound (traverse.cuh): node steps are
+// issued while at least `quorum` lanes stand on nodes, then every lane that holds triangles tests them.
+// Invariant between calls: a lane that is not finished (sp >= 0) has triangles (tgy != 0) or a pending node (ngy hits).
+__device__ __forceinline__ void wideRound(const WideView& w, WideRay& r, RayCold& c, float tMin, bool on, WideTrav& s, uint2* stack,
+                                          unsigned int stride, int quorum, unsigned int& nodeVisits, unsigned int& triTests) {
+    while (true) {
+        const bool atNode = on && s.sp >= 0 && s.tgy == 0u;
+        if (__popc(__ballot_sync(0xFFFFFFFFu, atNode)) < quorum) break;
+        if (atNode) {
+            wideNodeStep(w, r, s, stack, stride);
+            nodeVisits++;
+        }
+    }
+    if (on && s.sp >= 0 && s.tgy != 0u) wideTriPhase(w, r, c, tMin, s, stack, stride, triTests);
+}
+
+// The certificate (header comment). `winner` = caller's slot index of the triangle the walk found, `d` the unit direction,
+// tMax the ray's own limit, `closest` the winner's t (closest-hit rays). True: the reference returns the same hit.
+__device__ __forceinline__ bool wideCertify(const MeshView& m, const WideRay& r, const f3& d, float tMax, float closest, unsigned int winner) {
+    if (r.oct & WIDE_FLAG_TIE) return false;
+    const unsigned int leaf = m.firstLeaf + winner / m.primsPerLeaf;
+    const float4* rec = m.nodes + 4ull * (leaf >> 1); // {Lmin, Lmax, Rmin, Rmax} per axis for the children of leaf >> 1
+    const float4 qx = __ldg(rec), qy = __ldg(rec + 1), qz = __ldg(rec + 2);
+    const bool right = (leaf & 1u) != 0u;
+    RayPrep p;
+    p.o = mk3(r.ox, r.oy, r.oz);
+    p.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); // the reference's own reciprocal (may be inf)
+    const float bound = (r.oct & WIDE_FLAG_ANYHIT) ? tMax : fminf(tMax, closest * WIDE_TIE_MARGIN);
+    const float entry = boxDist(mk3(right ? qx.z : qx.x, right ? qy.z : qy.x, right ? qz.z : qz.x),
+                                mk3(right ? qx.w : qx.y, right ? qy.w : qy.y, right ? qz.w : qz.y), p, bound);
+    return entry < bound;
+}
+
+// ---- scene preparation ---------------------------------------------------------------------------------------------------
+// Leaf triangles in the wide tree's order, from the caller's 64-byte records (the same subtractions triangleHit starts with).
+__global__ void wideTrianglesKernel(const float* __restrict__ src, const unsigned int* __restrict__ triOrig, unsigned int n, float4* __restrict__ triA,
+                                    float2* __restrict__ triB) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned int orig = triOrig[i];
+    const float* t = src + 16ull * orig;
+    const f3 v0 = mk3(t[0], t[1], t[2]), v1 = mk3(t[3], t[4], t[5]), v2 = mk3(t[6], t[7], t[8]);
+    const f3 e1 = v1 - v0, e2 = v2 - v0;
+    triA[2ull * i] = make_float4(v0.x, v0.y, v0.z, e1.x);
+    triA[2ull * i + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
+    triB[i] = make_float2(e2.z, __uint_as_float(orig));
+}
+
+// The certificate's premise about the CALLER's tree: every node's box contains its children's (bvh_node[] of numBvhNodes
+// entries, root = 1). bad[0] counts violations; a tree that fails is traversed by the exact kernel only.
+__global__ void checkRefTreeKernel(const float* __restrict__ nodes, unsigned int numNodes, unsigned int* bad) {
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x + 4u; // children of nodes >= 2 (the root box itself is never tested, kernels.cu:157-170)
+    if (i >= numNodes) return;
+    const float* c = nodes + 6ull * i;
+    const float* p = nodes + 6ull * (i >> 1);
+    bool ok = true;
+    for (int a = 0; a < 3; a++) ok = ok && (!(c[a] <= c[3 + a]) || (p[a] <= c[a] && c[3 + a] <= p[3 + a])); // (an empty child box constrains nothing)
+    if (!ok) atomicAdd(bad, 1u);
+}

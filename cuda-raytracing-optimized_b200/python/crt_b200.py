@@ -68,6 +68,12 @@ class RendererOptions(C.Structure):
                 ("resetDeviceOnCleanup", C.c_int), ("megaBatch", C.c_int), ("reserved", C.c_int * 3)]
 
 
+class RendererWideInfo(C.Structure):
+    _fields_ = [("active", C.c_int), ("traversal", C.c_int), ("numNodes", C.c_uint), ("numTriangles", C.c_uint), ("depth", C.c_int),
+                ("buildThreads", C.c_int), ("buildMs", C.c_float), ("sahCost", C.c_float), ("lastBatchRedo", C.c_ulonglong),
+                ("lastFrameRedo", C.c_ulonglong)]
+
+
 class RendererStats(C.Structure):
     _fields_ = [("raysExtend", C.c_ulonglong), ("raysShadow", C.c_ulonglong), ("samples", C.c_ulonglong),
                 ("kernelLaunches", C.c_ulonglong), ("iterations", C.c_ulonglong), ("resumes", C.c_ulonglong),
@@ -125,8 +131,11 @@ DEVICE_SYMBOLS = [
     "intersectBatchDevice", "generateRayBatchDevice", "rendererDeviceAlloc", "rendererDeviceFree", "rendererCopyToHost",
     "rendererCopyToDevice", "getRendererStats", "setRendererProfiling", "getRendererAccumDevice", "setRendererAccumDevice",
     "finalizeFrame", "setRendererCounting", "getRendererTraversalCounts", "rendererDebugRead", "rendererReleaseCaches", "getRendererChaserCounts", "continueRenderer", "getRendererSamplesDone",
-    "saveRendererCheckpoint", "loadRendererCheckpoint", "scatterBatch",
+    "saveRendererCheckpoint", "loadRendererCheckpoint", "scatterBatch", "intersectBatchDeviceEx", "setRendererTraversal",
+    "getRendererWideInfo",
 ]
+
+TRAVERSAL_WIDE, TRAVERSAL_EXACT, TRAVERSAL_WIDE_UNCERTIFIED = 0, 1, 2
 
 
 def device_lib():
@@ -149,6 +158,10 @@ def device_lib():
         L.intersectBatch.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         L.intersectBatchDevice.restype = C.c_float
         L.intersectBatchDevice.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]
+        L.intersectBatchDeviceEx.restype = C.c_float
+        L.intersectBatchDeviceEx.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int]
+        L.setRendererTraversal.argtypes = [C.c_int]
+        L.getRendererWideInfo.argtypes = [C.POINTER(RendererWideInfo)]
         L.generateRayBatchDevice.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_float, C.c_float]
         L.rendererDeviceAlloc.restype = C.c_void_p
         L.rendererDeviceAlloc.argtypes = [C.c_size_t]
@@ -270,6 +283,17 @@ def set_options(device=-1, sample_stream=0, defer_finalize=0, reset_on_cleanup=0
     o = RendererOptions(device, sample_stream, defer_finalize, reset_on_cleanup, mega_batch,
                         (C.c_int * 3)(slots_per_pixel, trace_budget, trace_min_active))
     device_lib().setRendererOptions(C.byref(o))
+
+
+def set_traversal(mode):
+    """TRAVERSAL_WIDE (default) / TRAVERSAL_EXACT / TRAVERSAL_WIDE_UNCERTIFIED for the next initRenderer; -1 = default."""
+    device_lib().setRendererTraversal(mode)
+
+
+def wide_info():
+    w = RendererWideInfo()
+    device_lib().getRendererWideInfo(C.byref(w))
+    return w
 
 
 def stats():

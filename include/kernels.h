@@ -81,6 +81,9 @@ void intersectBatch(const float* origins, const float* dirs, long long n, float 
 // and (dx,dy,dz,tMax), result float4 (t,u,v, triId as int bits) plus meshID.
 // Used by the 64 Mi-ray microbench (BASELINE config 5).  Returns kernel ms.
 float intersectBatchDevice(const void* dRayO, const void* dRayD, long long n, void* dHit, int* dMeshId);
+// anyHit != 0: the shadow-ray query, hitMesh(.., isShadow = true) (kernels.cu:207,500): t = 0.0f when any triangle lies
+// in (tMin, tMax), FLT_MAX otherwise; ids are -1. anyHit == 0: intersectBatchDevice.
+float intersectBatchDeviceEx(const void* dRayO, const void* dRayD, long long n, void* dHit, int* dMeshId, int anyHit);
 
 // Fills device ray buffers with the config-5 batch: the first
 // half are jittered camera rays over a virtual filmW x filmH film, the second
@@ -153,6 +156,28 @@ void getRendererTraversalCounts(unsigned long long* nodeVisits, unsigned long lo
 // The part of the last frame that chaseKernel did (visits/tests only in counting builds); the rest was traced by traceKernel.
 void getRendererChaserCounts(unsigned long long* raysExtend, unsigned long long* raysShadow, unsigned long long* nodeVisits,
                              unsigned long long* triTests);
+
+// The acceleration structure. The reference walks the caller's bvh_node[] heap (kernels.cu:154-224). By default this
+// library builds its OWN tree from the caller's triangle[] inside initRenderer (8-wide, quantised child boxes, surface-area
+// heuristic: csrc/wide_bvh.h) and certifies per ray that the reference's walk returns the same hit; the few rays it cannot
+// certify (exact ties, last-ulp box culls of the caller's tree) are re-traced in the reference's order over the caller's tree.
+//   0 TRAVERSAL_WIDE (default)   1 TRAVERSAL_EXACT: the caller's tree in the reference's order for every ray (the checker)
+//   2 TRAVERSAL_WIDE_UNCERTIFIED: own tree, no certificate, no re-trace (diagnostic: results may differ on ties)
+// Applies to the next initRenderer. -1 restores the default (or CRT_TRAVERSAL=exact|wide|uncertified from the environment).
+void setRendererTraversal(int mode);
+
+typedef struct renderer_wide_info {
+    int active;                 // the wide tree is in use for this scene
+    int traversal;              // mode in effect
+    unsigned int numNodes, numTriangles;
+    int depth;                  // wide levels (= traversal stack entries per ray)
+    int buildThreads;
+    float buildMs;              // host build inside initRenderer (overlapped with the texture upload)
+    float sahCost;
+    unsigned long long lastBatchRedo;  // rays of the last intersectBatch* call answered by the exact kernel
+    unsigned long long lastFrameRedo;  // rays of the last runRenderer answered by the exact kernel
+} renderer_wide_info;
+void getRendererWideInfo(renderer_wide_info* out);
 
 #ifdef __cplusplus
 }

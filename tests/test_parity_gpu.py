@@ -204,7 +204,9 @@ def test_frame_vs_cpu_oracle(crt, oracle, medium_scene):
 def test_ray_batch_vs_cpu_oracle_and_counters(crt, oracle, medium_scene):
     n = 1 << 16
     L = crt.device_lib()
+    crt.set_traversal(crt.TRAVERSAL_EXACT)  # the counters compared below are those of the reference's walk over the caller's tree
     with crt.Frame(medium_scene, 64, 64, 1):
+        crt.set_traversal(-1)
         dO, dD, dH, dM = L.rendererDeviceAlloc(16 * n), L.rendererDeviceAlloc(16 * n), L.rendererDeviceAlloc(16 * n), L.rendererDeviceAlloc(4 * n)
         L.generateRayBatchDevice(dO, dD, n, 8192, 4096, 0.01, float(FLT_MAX))
         L.setRendererCounting(1)
