@@ -23,6 +23,7 @@
 #include "device_scene.cuh"
 #include "traverse.cuh"
 #include "wavefront_kernels.cuh"
+#include "wide_traverse.cuh"
 
 #define ENTRY_RESUME 0x80000000u
 #define ENTRY_SHADOW 0x40000000u
@@ -36,7 +37,8 @@ struct MeshControl {
     unsigned int shadeCount[2];  // entries in shadeQ[k]
     unsigned int traceCursor;    // dynamic fetch cursor of the running traceKernel
     unsigned int blocksDone;     // shadeKernel's last block resets the consumed queues
-    unsigned int pad0, pad1;
+    unsigned int redoCount;      // entries in redoQ: rays the wide walk could not certify, re-traced in the reference's order
+    unsigned int redoCursor;
     unsigned long long raysExtend;  // finished closest-hit rays
     unsigned long long raysShadow;  // finished any-hit rays
     unsigned long long resumes;     // rays parked and continued in a later launch
@@ -44,6 +46,7 @@ struct MeshControl {
     unsigned long long iterations;
     unsigned long long nodeVisits;
     unsigned long long triTests;
+    unsigned long long redone;      // rays answered by the exact kernel although the wide tree was in use
 };
 
 struct MeshState {
@@ -65,6 +68,7 @@ struct MeshState {
     unsigned int* rngOut;  // the slot's RNG state after its last sample of this run (continueRenderer / checkpoints start from it)
     unsigned int* traceQ[2];
     unsigned int* shadeQ[2];
+    unsigned int* redoQ;   // trace entries of this iteration that go through the exact kernel (wide traversal only)
     float4* accum;
     MeshControl* ctl;
     unsigned int numSlots;
@@ -313,13 +317,15 @@ __device__ __forceinline__ void warpFlagSet(unsigned int sharedBase) {
 
 // CUR (which of the two queue sets is the input) is a template parameter so that the queue pointers are reads of the kernel's
 // parameter bank and not six registers held across the traversal loop.
-template <bool COUNT, int CUR>
+// REDO: the input is redoQ (what wideTraceKernel of the same iteration could not certify) instead of traceQ[CUR]; those rays
+// run to their end here (no step budget: the wide pipeline has no parked rays).
+template <bool COUNT, int CUR, bool REDO = false>
 __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(MeshState st, MeshView mesh) {
     constexpr int cur = CUR;
     __shared__ RayCold coldAll[TRACE_BLOCK];
     RayCold& c = coldAll[threadIdx.x];
     MeshControl* ctl = st.ctl;
-    const unsigned int* __restrict__ queue = st.traceQ[cur];
+    const unsigned int* __restrict__ queue = REDO ? st.redoQ : st.traceQ[cur];
     unsigned int* __restrict__ nextTrace = st.traceQ[cur ^ 1];
     unsigned int* __restrict__ shadeQ = st.shadeQ[cur];
     const unsigned int lane = laneId();
@@ -330,7 +336,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(
     __shared__ unsigned int takeShared, countShared;
     __shared__ unsigned char exhaustedShared[TRACE_BLOCK / 32]; // per warp: the queue has no more entries for this warp
     if (threadIdx.x == 0) {
-        const unsigned int count = ctl->traceCount[cur];
+        const unsigned int count = REDO ? ctl->redoCount : ctl->traceCount[cur];
         const unsigned int totalWarps = gridDim.x * (TRACE_BLOCK / 32);
         countShared = count;
         takeShared = min(32u, max(1u, (count + totalWarps - 1) / totalWarps));
@@ -359,12 +365,12 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(
         // Lanes that still traverse. Finished rays stay in their lanes until the warp runs low on work: retiring them one
         // by one costs the whole warp a pass through the retire code per ray (measured: +25 % kernel time), so rays are
         // retired -- and idle lanes refilled -- in batches.
-        bool working = live && s.idx != 0u && steps < st.traceBudget;
+        bool working = live && s.idx != 0u && (REDO || steps < st.traceBudget);
         unsigned int workMask = __ballot_sync(0xFFFFFFFFu, working);
         if (exhausted ? workMask == 0u : (unsigned int)__popc(workMask) < refillBelow) {
             // ---- retire finished rays, park the ones that ran out of budget
             const bool finished = live && s.idx == 0u;
-            const bool park = live && !finished && steps >= st.traceBudget;
+            const bool park = !REDO && live && !finished && steps >= st.traceBudget;
             const unsigned int entry = __float_as_uint(c.rec.w);
             const unsigned int slot = entry & ENTRY_SLOT_MASK;
             const bool toShade = finished && !isShadow;
@@ -408,6 +414,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(
                 if (mShade) { baseShade = atomicAdd(&ctl->shadeCount[cur], __popc(mShade)); atomicAdd(&ctl->raysExtend, (unsigned long long)__popc(mShade)); }
                 if (mPark) { basePark = atomicAdd(&ctl->traceCount[cur ^ 1], __popc(mPark)); atomicAdd(&ctl->resumes, (unsigned long long)__popc(mPark)); }
                 if (mShadowDone) atomicAdd(&ctl->raysShadow, (unsigned long long)__popc(mShadowDone));
+                if (REDO && (mShade | mShadowDone)) atomicAdd(&ctl->redone, (unsigned long long)__popc(mShade | mShadowDone));
             }
             baseShade = __shfl_sync(0xFFFFFFFFu, baseShade, 0);
             basePark = __shfl_sync(0xFFFFFFFFu, basePark, 0);
@@ -423,7 +430,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(
                 const unsigned int idle = ~workMask; // every lane that does not traverse has just been retired (or was empty)
                 const unsigned int count = tail ? min((unsigned int)__popc(idle), take - (unsigned int)__popc(workMask)) : (unsigned int)__popc(idle);
                 unsigned int base = 0;
-                if (lane == 0) base = atomicAdd(&ctl->traceCursor, count);
+                if (lane == 0) base = atomicAdd(REDO ? &ctl->redoCursor : &ctl->traceCursor, count);
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
                 if (base + count >= n) warpFlagSet(exhaustedBase); // warp-uniform: the tail of the queue has been handed out
                 const unsigned int rank = __popc(idle & below);
@@ -487,6 +494,163 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(
 #undef take
 #undef tail
 #undef refillBelow
+
+// ------------------------------------------------------------- wide trace --
+// The same job as traceKernel over the renderer's own wide tree (wide_traverse.cuh): persistent warps, idle lanes refilled
+// from the queue with one atomic per warp, finished rays retired in batches. Every finished ray that found a triangle is
+// certified against the caller's tree; what cannot be certified (and rays the wide arithmetic does not cover) goes to
+// redoQ and is traced by traceKernel<.., REDO> right after this launch, before the iteration's shade kernel.
+// There is no step budget and no parking: the traversal stack lives in shared memory (wide.stackDepth entries per thread).
+#define WIDE_TRACE_BLOCKS_PER_SM 4 // 64 registers
+template <bool COUNT, int CUR, bool CERTIFY>
+__global__ void __launch_bounds__(TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wideTraceKernel(MeshState st, MeshView mesh, WideView wide) {
+    constexpr int cur = CUR;
+    extern __shared__ uint2 wideStackAll[];
+    __shared__ RayCold coldAll[TRACE_BLOCK];
+    RayCold& c = coldAll[threadIdx.x];
+    uint2* stack = wideStackAll + threadIdx.x;
+    MeshControl* ctl = st.ctl;
+    const unsigned int* __restrict__ queue = st.traceQ[cur];
+    unsigned int* __restrict__ shadeQ = st.shadeQ[cur];
+    const unsigned int lane = laneId();
+    __shared__ unsigned int takeShared, countShared;
+    if (threadIdx.x == 0) {
+        const unsigned int count = ctl->traceCount[cur];
+        const unsigned int totalWarps = gridDim.x * (TRACE_BLOCK / 32);
+        countShared = count;
+        takeShared = min(32u, max(1u, (count + totalWarps - 1) / totalWarps)); // short queue: spread the rays over all warps
+    }
+    __syncthreads();
+    const unsigned int n = countShared, take = takeShared;
+    const bool tail = take < 32u;
+    const unsigned int refillBelow = tail ? take : (unsigned int)st.traceMinActive;
+    const unsigned int k3f = wideConst3F();
+
+    bool live = false, exhausted = false;
+    WideRay r;
+    WideTrav s;
+    unsigned int nodeVisits = 0, triTests = 0;
+    r.ox = r.oy = r.oz = r.ix = r.iy = r.iz = 0.0f; r.oct = 0u;
+    s.ngx = s.ngy = s.tgx = s.tgy = 0u; s.sp = -1; s.closest = 0.0f;
+
+    while (true) {
+        bool working = live && s.sp >= 0;
+        unsigned int workMask = __ballot_sync(0xFFFFFFFFu, working);
+        if (exhausted ? workMask == 0u : (unsigned int)__popc(workMask) < refillBelow) {
+            // ---- retire finished rays
+            const bool finished = live && s.sp < 0;
+            const bool isShadow = (r.oct & WIDE_FLAG_ANYHIT) != 0u;
+            const unsigned int entry = __float_as_uint(c.rec.w);
+            const unsigned int slot = entry & ENTRY_SLOT_MASK;
+            bool redo = false;
+            if (finished) {
+                const unsigned int winner = __float_as_uint(c.rec.z);
+                if (CERTIFY && winner != 0xFFFFFFFFu) redo = !wideCertify(mesh, r, xyz(c.dir), c.dir.w, s.closest, winner);
+                if (!redo) {
+                    if (!isShadow) {
+                        st.hit[slot] = make_float4(s.closest, c.rec.x, c.rec.y, c.rec.z);
+                    } else {
+                        const float4 l = st.shL[slot];
+                        const bool unoccluded = !(s.closest < c.dir.w); // hit(...) false: p.color += p.lightContribution (kernels.cu:500-508)
+                        if (__float_as_uint(l.w) & SHADOW_FLAG_FINAL) {
+                            float4 col = st.shC[slot];
+                            if (unoccluded) { col.x += l.x; col.y += l.y; col.z += l.z; }
+                            accumulatePixel(st, slotPixel(st, slot), col.x, col.y, col.z); // col += p.color (kernels.cu:558)
+                        } else if (unoccluded) {
+                            float4 col = st.pcol[slot];
+                            col.x += l.x; col.y += l.y; col.z += l.z;
+                            st.pcol[slot] = col;
+                        }
+                        st.pending[slot] = 0;
+                    }
+                }
+                live = false;
+            }
+            const bool toShade = finished && !redo && !isShadow;
+            const unsigned int mShade = __ballot_sync(0xFFFFFFFFu, toShade);
+            const unsigned int mShadowDone = __ballot_sync(0xFFFFFFFFu, finished && !redo && isShadow);
+            const unsigned int mRedo = __ballot_sync(0xFFFFFFFFu, redo);
+            unsigned int baseShade = 0, baseRedo = 0;
+            if (lane == 0) {
+                if (mShade) { baseShade = atomicAdd(&ctl->shadeCount[cur], __popc(mShade)); atomicAdd(&ctl->raysExtend, (unsigned long long)__popc(mShade)); }
+                if (mShadowDone) atomicAdd(&ctl->raysShadow, (unsigned long long)__popc(mShadowDone));
+                if (mRedo) baseRedo = atomicAdd(&ctl->redoCount, __popc(mRedo));
+            }
+            baseShade = __shfl_sync(0xFFFFFFFFu, baseShade, 0);
+            baseRedo = __shfl_sync(0xFFFFFFFFu, baseRedo, 0);
+            const unsigned int below = (1u << lane) - 1u;
+            if (toShade) {
+                shadeQ[baseShade + __popc(mShade & below)] = slot;
+                st.ready[slot] = 1;
+            }
+            if (redo) st.redoQ[baseRedo + __popc(mRedo & below)] = entry;
+
+            // ---- refill idle lanes, one atomic per warp
+            if (!exhausted) {
+                const unsigned int idle = ~workMask;
+                const unsigned int count = tail ? min((unsigned int)__popc(idle), take - (unsigned int)__popc(workMask)) : (unsigned int)__popc(idle);
+                unsigned int base = 0;
+                if (lane == 0) base = atomicAdd(&ctl->traceCursor, count);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (base + count >= n) exhausted = true;
+                const unsigned int rank = __popc(idle & below);
+                const unsigned int i = base + rank;
+                bool direct = false; // the ray goes to the exact kernel untraced
+                unsigned int e = 0;
+                if (!live && rank < count && i < n) {
+                    e = queue[i];
+                    const unsigned int sl = e & ENTRY_SLOT_MASK;
+                    const bool shadow = (e & ENTRY_SHADOW) != 0u;
+                    const float4 ro = shadow ? st.shO[sl] : st.rayO[sl];
+                    const float4 rd = shadow ? st.shD[sl] : st.rayD[sl];
+                    const float tMax = shadow ? rd.w : FLT_MAX;
+                    const f3 d = unit(xyz(rd)); // hit(): ray(p.origin, dir) normalises again (kernels.cu:326)
+                    c.dir = mk4(d, tMax);
+                    c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), __uint_as_float(e));
+                    if (!wideSetup(wide, r, xyz(ro), d, shadow) || (e & ENTRY_RESUME)) {
+                        direct = true;
+                    } else {
+                        RayHot rh;
+                        rh.ox = ro.x; rh.oy = ro.y; rh.oz = ro.z;
+                        rh.ix = 1.0f / d.x; rh.iy = 1.0f / d.y; rh.iz = 1.0f / d.z;
+                        wideStart(s, tMax);
+                        if (!rayHitsBounds(mesh, rh, tMax)) { // hitMesh: scene bounds first (kernels.cu:297)
+                            s.sp = -1;
+                            s.closest = FLT_MAX;
+                        }
+                        live = true;
+                    }
+                }
+                const unsigned int mDirect = __ballot_sync(0xFFFFFFFFu, direct);
+                if (mDirect) {
+                    unsigned int b = 0;
+                    if (lane == 0) b = atomicAdd(&ctl->redoCount, __popc(mDirect));
+                    b = __shfl_sync(0xFFFFFFFFu, b, 0);
+                    if (direct) st.redoQ[b + __popc(mDirect & below)] = e;
+                }
+            }
+            if (!__any_sync(0xFFFFFFFFu, live)) {
+                if (exhausted) break;
+                continue;
+            }
+            working = live && s.sp >= 0;
+            workMask = __ballot_sync(0xFFFFFFFFu, working);
+            if (workMask == 0u) continue; // e.g. every new ray missed the scene bounds: retire them
+        }
+        wideRound(wide, r, c, RT_EPSILON, working, s, stack, TRACE_BLOCK, tail ? 1 : max(1, min(TRACE_NODE_QUORUM, __popc(workMask) >> 1)), k3f, nodeVisits, triTests);
+    }
+
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) {
+            nodeVisits += __shfl_xor_sync(0xFFFFFFFFu, nodeVisits, o);
+            triTests += __shfl_xor_sync(0xFFFFFFFFu, triTests, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&ctl->nodeVisits, (unsigned long long)nodeVisits);
+            atomicAdd(&ctl->triTests, (unsigned long long)triTests);
+        }
+    }
+}
 
 // ------------------------------------------------------------------- shade --
 #ifndef SHADE_DENSE_FRACTION
@@ -565,6 +729,8 @@ __global__ void __launch_bounds__(WF_BLOCK, 4) meshShadeKernel(MeshState st, Sha
         ctl->shadeCount[cur] = 0;
         ctl->traceCursor = 0;
         ctl->blocksDone = 0;
+        ctl->redoCount = 0;
+        ctl->redoCursor = 0;
     }
 }
 
@@ -601,7 +767,7 @@ struct ChaseRing {
     // two rings: [0] shared (a warp takes up to 16 slots), [1] exclusive (the most lagging slots: one per warp, lowest latency)
     unsigned int* entries[2];        // numSlots entries each: a slot enters at most once per frame
     unsigned int* ctl;               // per ring r at ctl[8*r + ..]: [0] head (claimed) [1] tail (published) [2] reserved (appended) [4] slots finished
-    unsigned long long* counters;    // [0] extend rays [1] shadow rays [2] node visits [3] triangle tests (counting builds)
+    unsigned long long* counters;    // [0] extend rays [1] shadow rays [2] node visits [3] triangle tests (counting builds) [4] rays re-traced exactly
 };
 
 struct ChasePathSm {   // a main lane's path between two bounces
@@ -626,9 +792,58 @@ struct ChaseSink {
 
 __device__ __forceinline__ unsigned int ldVolatile(const unsigned int* p) { return *(const volatile unsigned int*)p; }
 
-template <bool COUNT>
-__global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(MeshState st, MeshView mesh, ShadeScene sc, CameraDev cam, ChaseRing ring, unsigned int exclusiveEvery,
-                                                                              unsigned int exclusivePairs) {
+// One lane's traversal in the chaser: the wide walk with the certificate, and the order-exact walk (the caller's tree in
+// the reference's order) either as the only traversal (WIDE = false) or, inline, for the rays the certificate rejects.
+template <bool WIDE>
+struct ChaseLane {
+    // exact walk (always available)
+    RayHot r;
+    TravHot s;
+    // wide walk
+    WideRay wr;
+    WideTrav ws;
+    bool exactOnly; // wide: this ray is not covered by the wide arithmetic
+
+    __device__ __forceinline__ void clear() {
+        r.ox = r.oy = r.oz = r.ix = r.iy = r.iz = 0.0f;
+        s.idx = 0u; s.bitStack = 0u; s.closest = 0.0f;
+        wr.ox = wr.oy = wr.oz = wr.ix = wr.iy = wr.iz = 0.0f; wr.oct = 0u;
+        ws.ngx = ws.ngy = ws.tgx = ws.tgy = 0u; ws.sp = -1; ws.closest = 0.0f;
+        exactOnly = false;
+    }
+    // a fresh ray (hit(): the direction is normalised again, kernels.cu:326; hitMesh: scene bounds first, :297)
+    __device__ __forceinline__ void start(const MeshView& mesh, const WideView& wide, RayCold& c, const f3& o, const f3& dRaw, float tMax, bool anyHit) {
+        const f3 d = unit(dRaw);
+        prepRay(r, c, o, d, tMax);
+        c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), 0.0f);
+        const bool inBounds = rayHitsBounds(mesh, r, tMax);
+        if (WIDE) {
+            exactOnly = !wideSetup(wide, wr, o, d, anyHit);
+            wideStart(ws, tMax);
+            if (!inBounds || exactOnly) { ws.sp = -1; ws.closest = inBounds ? tMax : FLT_MAX; }
+            if (!inBounds) exactOnly = false; // a miss of the scene bounds is final
+        }
+        s.idx = 1u; s.bitStack = 1u; s.closest = tMax;
+        if (!inBounds) { s.idx = 0u; s.closest = FLT_MAX; }
+    }
+    // a ray the wavefront parked (exact pipeline only: the wide pipeline has no step budget)
+    __device__ __forceinline__ void resume(RayCold& c, const f3& o, const f3& dRaw, float tMax, const uint2& t, float closest) {
+        prepRay(r, c, o, unit(dRaw), tMax);
+        s.idx = t.x; s.bitStack = t.y; s.closest = closest;
+    }
+    // nothing to trace: the record in c.rec / `closest` is already the answer
+    __device__ __forceinline__ void done(float closest) {
+        s.idx = 0u; s.bitStack = 0u; s.closest = closest;
+        if (WIDE) { ws.sp = -1; ws.closest = closest; exactOnly = false; }
+    }
+    __device__ __forceinline__ bool working() const { return WIDE ? ws.sp >= 0 : s.idx != 0u; }
+    __device__ __forceinline__ float closest() const { return WIDE ? ws.closest : s.closest; }
+};
+
+template <bool COUNT, bool WIDE>
+__global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(MeshState st, MeshView mesh, WideView wide, ShadeScene sc, CameraDev cam, ChaseRing ring,
+                                                                              unsigned int exclusiveEvery, unsigned int exclusivePairs) {
+    extern __shared__ uint2 wideStackAll[];
     __shared__ RayCold coldAll[CHASE_BLOCK];
     __shared__ ChasePathSm pathAll[CHASE_BLOCK / 2];
     __shared__ ChaseShadowSm shadowAll[CHASE_BLOCK / 2];
@@ -643,6 +858,8 @@ __global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(Mes
     RayCold& c = coldAll[threadIdx.x];
     ChasePathSm& path = pathAll[pairIdx];
     ChaseShadowSm& shadow = shadowAll[pairIdx];
+    uint2* stack = wideStackAll + threadIdx.x;
+    const unsigned int k3f = wideConst3F();
 
     // lane state
     enum { IDLE = 0, TRACE = 1, READY = 2, DRAIN = 3 };
@@ -651,12 +868,10 @@ __global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(Mes
     int state = IDLE;
     unsigned int slot = 0;
     bool unoccluded = false;
-    RayHot r;
-    TravHot s;
+    ChaseLane<WIDE> t;
+    t.clear();
     int steps = 0;
-    unsigned int nodeVisits = 0, triTests = 0, doneExtend = 0, doneShadow = 0;
-    r.ox = r.oy = r.oz = r.ix = r.iy = r.iz = 0.0f;
-    s.idx = 0u; s.bitStack = 0u; s.closest = 0.0f;
+    unsigned int nodeVisits = 0, triTests = 0, doneExtend = 0, doneShadow = 0, redone = 0;
 
     while (true) {
         // ---- 1. idle pairs take slots from the ring (one compare-and-swap per warp)
@@ -699,25 +914,23 @@ __global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(Mes
                 path.dFlags = rd;
                 path.attSample = __ldcg(&st.atten[slot]);
                 path.color = __ldcg(&st.pcol[slot]);
-                prepRay(r, c, xyz(ro), unit(xyz(rd)), FLT_MAX); // hit(): ray(p.origin, dir) normalises again (kernels.cu:326)
-                c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), 0.0f);
                 if ((entry & CHASE_ENTRY_DRAIN) == CHASE_ENTRY_DRAIN) {
-                    s.idx = 0u; s.bitStack = 0u; s.closest = FLT_MAX;
+                    c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), 0.0f);
+                    t.done(FLT_MAX);
                     state = DRAIN;
                 } else if (entry & CHASE_ENTRY_SHADE) {
                     const float4 h = __ldcg(&st.hit[slot]);
-                    s.idx = 0u; s.bitStack = 0u; s.closest = h.x;
                     c.rec = make_float4(h.y, h.z, h.w, 0.0f);
+                    t.done(h.x);
                     state = READY;
-                } else if (entry & ENTRY_RESUME) {
-                    const uint2 t = __ldcg(&st.travE[slot]);
+                } else if (!WIDE && (entry & ENTRY_RESUME)) { // (the wide pipeline parks nothing; a parked ray would simply start over)
+                    const uint2 tr = __ldcg(&st.travE[slot]);
                     const float4 h = __ldcg(&st.hit[slot]);
-                    s.idx = t.x; s.bitStack = t.y; s.closest = h.x;
+                    t.resume(c, xyz(ro), xyz(rd), FLT_MAX, tr, h.x);
                     c.rec = make_float4(h.y, h.z, h.w, 0.0f);
                     state = TRACE;
                 } else {
-                    s.idx = 1u; s.bitStack = 1u; s.closest = FLT_MAX;
-                    if (!rayHitsBounds(mesh, r, FLT_MAX)) { s.idx = 0u; s.closest = FLT_MAX; } // hitMesh: scene bounds first (kernels.cu:297)
+                    t.start(mesh, wide, c, xyz(ro), xyz(rd), FLT_MAX, false);
                     state = TRACE;
                 }
             } else {
@@ -729,14 +942,12 @@ __global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(Mes
                     shadow.dDist = sd;
                     shadow.lFlags = __ldcg(&st.shL[slot]);
                     shadow.carried = __ldcg(&st.shC[slot]);
-                    prepRay(r, c, xyz(so), unit(xyz(sd)), sd.w);
-                    c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), 0.0f);
-                    if (pend == 2u) {
-                        const uint2 t = __ldcg(&st.travS[slot]);
-                        s.idx = t.x; s.bitStack = t.y; s.closest = sd.w;
+                    if (!WIDE && pend == 2u) {
+                        const uint2 tr = __ldcg(&st.travS[slot]);
+                        t.resume(c, xyz(so), xyz(sd), sd.w, tr, sd.w);
+                        c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), 0.0f);
                     } else {
-                        s.idx = 1u; s.bitStack = 1u; s.closest = sd.w;
-                        if (!rayHitsBounds(mesh, r, sd.w)) { s.idx = 0u; s.closest = FLT_MAX; }
+                        t.start(mesh, wide, c, xyz(so), xyz(sd), sd.w, true);
                     }
                     state = TRACE;
                 }
@@ -744,14 +955,36 @@ __global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(Mes
         }
 
         // ---- 2. one scheduling round of traversal for every ray in flight
-        const bool working = state == TRACE && s.idx != 0u;
-        if (__any_sync(0xFFFFFFFFu, working)) travRound<true>(mesh, r, c, RT_EPSILON, !isMain, working, s, steps, 1, nodeVisits, triTests);
+        const bool working = state == TRACE && t.working();
+        if (__any_sync(0xFFFFFFFFu, working)) {
+            if (WIDE) wideRound(wide, t.wr, c, RT_EPSILON, working, t.ws, stack, CHASE_BLOCK, 1, k3f, nodeVisits, triTests);
+            else travRound<true>(mesh, t.r, c, RT_EPSILON, !isMain, working, t.s, steps, 1, nodeVisits, triTests);
+        }
+        if (WIDE) {
+            // a finished wide walk must be certified; what is not (and what the wide arithmetic does not cover) is walked in
+            // the reference's order right here, by the lanes concerned, before the ray counts as finished
+            bool needExact = false;
+            if (state == TRACE && t.ws.sp < 0) {
+                const unsigned int winner = __float_as_uint(c.rec.z);
+                needExact = t.exactOnly || (winner != 0xFFFFFFFFu && !wideCertify(mesh, t.wr, xyz(c.dir), c.dir.w, t.ws.closest, winner));
+            }
+            if (__any_sync(0xFFFFFFFFu, needExact)) {
+                if (needExact) { // from the root (start() has already tested the scene bounds)
+                    redone++;
+                    c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), 0.0f);
+                    t.s.idx = 1u; t.s.bitStack = 1u; t.s.closest = c.dir.w;
+                }
+                while (__any_sync(0xFFFFFFFFu, needExact && t.s.idx != 0u))
+                    travRound<true>(mesh, t.r, c, RT_EPSILON, !isMain, needExact && t.s.idx != 0u, t.s, steps, 1, nodeVisits, triTests);
+                if (needExact) { t.ws.closest = t.s.closest; t.exactOnly = false; }
+            }
+        }
 
         // ---- 3. finished rays
-        if (state == TRACE && s.idx == 0u) {
+        if (state == TRACE && !t.working()) {
             state = READY;
             if (isMain) doneExtend++;
-            else { doneShadow++; unoccluded = !(s.closest < c.dir.w); } // hit(...) false: p.color += p.lightContribution (kernels.cu:500-508)
+            else { doneShadow++; unoccluded = !(t.closest() < c.dir.w); } // hit(...) false: p.color += p.lightContribution (kernels.cu:500-508)
         }
 
         // ---- 4. a main lane whose extend ray is done and whose partner is not tracing: apply the shadow result, then shade
@@ -786,7 +1019,7 @@ __global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(Mes
                 p.flags = __float_as_uint(path.dFlags.w);
                 p.sample = __float_as_int(path.attSample.w);
                 p.color = xyz(path.color);
-                const float4 h = make_float4(s.closest, c.rec.x, c.rec.y, c.rec.z);
+                const float4 h = make_float4(t.closest(), c.rec.x, c.rec.y, c.rec.z);
                 ChaseSink sink{st, slot, &shadow};
                 const ShadeResult res = shadePath(st, sc, cam, slot, p, h, sink);
                 cast = res.castsShadow;
@@ -795,10 +1028,7 @@ __global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(Mes
                     path.dFlags = mk4(p.dir, __uint_as_float(p.flags));
                     path.attSample = mk4(p.att, __int_as_float(p.sample));
                     path.color = mk4(p.color, 0.0f);
-                    prepRay(r, c, p.origin, unit(p.dir), FLT_MAX);
-                    c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), 0.0f);
-                    s.idx = 1u; s.bitStack = 1u; s.closest = FLT_MAX;
-                    if (!rayHitsBounds(mesh, r, FLT_MAX)) { s.idx = 0u; s.closest = FLT_MAX; }
+                    t.start(mesh, wide, c, p.origin, p.dir, FLT_MAX, false);
                     steps = 0;
                     state = TRACE;
                 } else if (cast) {
@@ -820,10 +1050,7 @@ __global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(Mes
             if (castMask & mainBit) {
                 const float4 so = shadow.o;
                 const float4 sd = shadow.dDist;
-                prepRay(r, c, xyz(so), unit(xyz(sd)), sd.w);
-                c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), 0.0f);
-                s.idx = 1u; s.bitStack = 1u; s.closest = sd.w;
-                if (!rayHitsBounds(mesh, r, sd.w)) { s.idx = 0u; s.closest = FLT_MAX; }
+                t.start(mesh, wide, c, xyz(so), xyz(sd), sd.w, true);
                 steps = 0;
                 state = TRACE;
             }
@@ -841,6 +1068,7 @@ __global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(Mes
     for (int o = 16; o > 0; o >>= 1) {
         doneExtend += __shfl_xor_sync(0xFFFFFFFFu, doneExtend, o);
         doneShadow += __shfl_xor_sync(0xFFFFFFFFu, doneShadow, o);
+        redone += __shfl_xor_sync(0xFFFFFFFFu, redone, o);
         if (COUNT) {
             nodeVisits += __shfl_xor_sync(0xFFFFFFFFu, nodeVisits, o);
             triTests += __shfl_xor_sync(0xFFFFFFFFu, triTests, o);
@@ -849,6 +1077,7 @@ __global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(Mes
     if (lane == 0) {
         if (doneExtend) atomicAdd(&ring.counters[0], (unsigned long long)doneExtend);
         if (doneShadow) atomicAdd(&ring.counters[1], (unsigned long long)doneShadow);
+        if (redone) atomicAdd(&ring.counters[4], (unsigned long long)redone);
         if (COUNT) {
             atomicAdd(&ring.counters[2], (unsigned long long)nodeVisits);
             atomicAdd(&ring.counters[3], (unsigned long long)triTests);

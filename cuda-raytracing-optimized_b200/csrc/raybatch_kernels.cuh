@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(256, 4) wideIntersectBatchKernel(MeshView mesh
     WideRay r;
     WideTrav s;
     unsigned int nodeVisits = 0, triTests = 0;
+    const unsigned int k3f = wideConst3F();
     r.ox = r.oy = r.oz = r.ix = r.iy = r.iz = 0.0f; r.oct = 0u;
     s.ngx = s.ngy = s.tgx = s.tgy = 0u; s.sp = -1; s.closest = 0.0f;
     while (true) {
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(256, 4) wideIntersectBatchKernel(MeshView mesh
             if (exhausted) break;
             continue;
         }
-        wideRound(wide, r, c, tMinAll[threadIdx.x], live, s, stack, 256u, max(1, min(TRACE_NODE_QUORUM, __popc(liveMask) >> 1)), nodeVisits, triTests);
+        wideRound(wide, r, c, tMinAll[threadIdx.x], live, s, stack, 256u, max(1, min(TRACE_NODE_QUORUM, __popc(liveMask) >> 1)), k3f, nodeVisits, triTests);
         if (live && s.sp < 0) {
             float t = s.closest;
             unsigned int triId = __float_as_uint(c.rec.z);

@@ -204,11 +204,12 @@ static void allocMeshPipeline(RendererContext& c, unsigned int numSlots) {
         s.traceQ[k] = devAlloc<unsigned int>(2 * (size_t)numSlots); // at most one extend and one shadow entry per slot
         s.shadeQ[k] = devAlloc<unsigned int>(numSlots);
     }
+    s.redoQ = devAlloc<unsigned int>(2 * (size_t)numSlots);
     s.ctl = devAlloc<MeshControl>(1);
     c.ring.entries[0] = devAlloc<unsigned int>(numSlots);
     c.ring.entries[1] = devAlloc<unsigned int>(numSlots);
     c.ring.ctl = devAlloc<unsigned int>(16);
-    c.ring.counters = devAlloc<unsigned long long>(4);
+    c.ring.counters = devAlloc<unsigned long long>(8);
 }
 
 extern "C" void setRendererOptions(const renderer_options* opt) {
@@ -438,11 +439,31 @@ static ShadeScene shadeScene(const RendererContext& c) {
     return s;
 }
 
+static bool useWideTree(const RendererContext& c) { return c.wide.stackDepth > 0 && c.traversal != TRAVERSAL_EXACT; }
+
+template <int CUR>
+static void launchWideTrace(RendererContext& c, const MeshState& mp, cudaStream_t stream, int traceBlocks) {
+    const size_t smem = (size_t)c.wide.stackDepth * TRACE_BLOCK * sizeof(uint2);
+    const bool certify = c.traversal != TRAVERSAL_WIDE_UNCERTIFIED;
+    if (c.counting) {
+        if (certify) wideTraceKernel<true, CUR, true><<<traceBlocks, TRACE_BLOCK, smem, stream>>>(mp, c.mesh, c.wide);
+        else wideTraceKernel<true, CUR, false><<<traceBlocks, TRACE_BLOCK, smem, stream>>>(mp, c.mesh, c.wide);
+    } else {
+        if (certify) wideTraceKernel<false, CUR, true><<<traceBlocks, TRACE_BLOCK, smem, stream>>>(mp, c.mesh, c.wide);
+        else wideTraceKernel<false, CUR, false><<<traceBlocks, TRACE_BLOCK, smem, stream>>>(mp, c.mesh, c.wide);
+    }
+    // what the wide walk could not certify, in the reference's order over the caller's tree (usually a handful of rays)
+    traceKernel<false, CUR, true><<<c.numSMs, TRACE_BLOCK, 0, stream>>>(mp, c.mesh);
+}
+
 // One wavefront iteration on `stream`: trace (extend + shadow rays) -> shade (+ retire sample, + next camera ray).
 static void launchMeshIteration(RendererContext& c, const MeshState& mp, cudaStream_t stream, int cur, int traceBlocks, int shadeBlocks,
                                 cudaEvent_t* ev, int shadeThreads = WF_BLOCK) {
     if (ev) cudaEventRecord(ev[0], stream);
-    if (c.counting) {
+    if (useWideTree(c)) {
+        if (cur) launchWideTrace<1>(c, mp, stream, c.wideTraceBlocks);
+        else launchWideTrace<0>(c, mp, stream, c.wideTraceBlocks);
+    } else if (c.counting) {
         if (cur) traceKernel<true, 1><<<traceBlocks, TRACE_BLOCK, 0, stream>>>(mp, c.mesh);
         else traceKernel<true, 0><<<traceBlocks, TRACE_BLOCK, 0, stream>>>(mp, c.mesh);
     } else {
@@ -466,7 +487,6 @@ static cudaGraphExec_t captureMeshBatch(RendererContext& c, const MeshState& mp,
     return exec;
 }
 
-#define MESH_KERNELS_PER_ITERATION 2
 
 void crtRunMesh(RendererContext& c, int ns, bool resume) {
     const unsigned int npix = (unsigned int)c.nx * (unsigned int)c.ny;
@@ -494,6 +514,16 @@ void crtRunMesh(RendererContext& c, int ns, bool resume) {
         CRT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, traceKernel<false, 0>, TRACE_BLOCK, 0));
         c.traceBlocks = c.numSMs * (perSM > 0 ? perSM : 1); // persistent: exactly one resident wave
     }
+    if (useWideTree(c) && !c.wideTraceBlocks) {
+        const size_t smem = (size_t)c.wide.stackDepth * TRACE_BLOCK * sizeof(uint2);
+        auto prep = [&](auto kernel) { CRT_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); };
+        prep(wideTraceKernel<false, 0, true>); prep(wideTraceKernel<false, 1, true>); prep(wideTraceKernel<false, 0, false>); prep(wideTraceKernel<false, 1, false>);
+        prep(wideTraceKernel<true, 0, true>); prep(wideTraceKernel<true, 1, true>); prep(wideTraceKernel<true, 0, false>); prep(wideTraceKernel<true, 1, false>);
+        int perSM = 0;
+        CRT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, wideTraceKernel<false, 0, true>, TRACE_BLOCK, smem));
+        c.wideTraceBlocks = c.numSMs * (perSM > 0 ? perSM : 1);
+    }
+    const int kernelsPerIteration = useWideTree(c) ? 3 : 2;
     cudaStream_t stream = c.stream;
 
     std::memset(&c.stats, 0, sizeof(c.stats));
@@ -527,7 +557,7 @@ void crtRunMesh(RendererContext& c, int ns, bool resume) {
                 for (int cur = 0; cur < 2; cur++) {
                     if (dump) CRT_CHECK(cudaMemcpyAsync(host, mp.ctl, sizeof(MeshControl), cudaMemcpyDeviceToHost, stream));
                     launchMeshIteration(c, mp, stream, cur, c.traceBlocks, c.numSMs * 4, ev);
-                    launches += MESH_KERNELS_PER_ITERATION;
+                    launches += kernelsPerIteration;
                     CRT_CHECK(cudaStreamSynchronize(stream));
                     float msT, msS;
                     cudaEventElapsedTime(&msT, ev[0], ev[1]); c.stats.msTrace += msT;
@@ -563,7 +593,7 @@ void crtRunMesh(RendererContext& c, int ns, bool resume) {
             const long long key = ((long long)mp.samplesPerSlot << 24) ^ ((long long)slotsPerPixel << 8) ^ batch ^
                                   ((long long)c.counting << 60) ^ ((long long)c.maxDepth << 40) ^ ((long long)mp.streamBase << 48) ^
                                   ((long long)mp.traceBudget << 12) ^ ((long long)mp.traceMinActive << 4) ^ ((long long)chase << 59) ^
-                                  ((long long)blocksA << 30) ^ ((long long)shadeBlocksA << 17);
+                                  ((long long)blocksA << 30) ^ ((long long)shadeBlocksA << 17) ^ ((long long)(useWideTree(c) ? 1 + c.traversal : 0) << 56);
             if (!c.graphExec || c.graphKey != key) {
                 if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
                 c.graphExec = captureMeshBatch(c, mp, stream, batch, blocksA, shadeBlocksA);
@@ -577,14 +607,20 @@ void crtRunMesh(RendererContext& c, int ns, bool resume) {
                 cudaStream_t on = g_cache.chaseStreams[wave++ % CHASE_STREAMS];
                 CRT_CHECK(cudaEventRecord(c.evLane, stream));
                 CRT_CHECK(cudaStreamWaitEvent(on, c.evLane, 0));
-                if (c.counting) chaseKernel<true><<<blocks, CHASE_BLOCK, 0, on>>>(mp, c.mesh, scene, c.cam, ring, exclusiveEvery, exclusivePairs);
-                else chaseKernel<false><<<blocks, CHASE_BLOCK, 0, on>>>(mp, c.mesh, scene, c.cam, ring, exclusiveEvery, exclusivePairs);
+                if (useWideTree(c)) {
+                    const size_t smem = (size_t)c.wide.stackDepth * CHASE_BLOCK * sizeof(uint2);
+                    if (c.counting) chaseKernel<true, true><<<blocks, CHASE_BLOCK, smem, on>>>(mp, c.mesh, c.wide, scene, c.cam, ring, exclusiveEvery, exclusivePairs);
+                    else chaseKernel<false, true><<<blocks, CHASE_BLOCK, smem, on>>>(mp, c.mesh, c.wide, scene, c.cam, ring, exclusiveEvery, exclusivePairs);
+                } else {
+                    if (c.counting) chaseKernel<true, false><<<blocks, CHASE_BLOCK, 0, on>>>(mp, c.mesh, c.wide, scene, c.cam, ring, exclusiveEvery, exclusivePairs);
+                    else chaseKernel<false, false><<<blocks, CHASE_BLOCK, 0, on>>>(mp, c.mesh, c.wide, scene, c.cam, ring, exclusiveEvery, exclusivePairs);
+                }
                 CRT_CHECK(cudaGetLastError());
                 launches += 1;
             };
             if (chase) {
                 CRT_CHECK(cudaMemsetAsync(ring.ctl, 0, 16 * sizeof(unsigned int), stream));
-                CRT_CHECK(cudaMemsetAsync(ring.counters, 0, 4 * sizeof(unsigned long long), stream));
+                CRT_CHECK(cudaMemsetAsync(ring.counters, 0, 8 * sizeof(unsigned long long), stream));
                 CRT_CHECK(cudaMemsetAsync(c.laneSums, 0, 8 * sizeof(unsigned long long), stream));
             }
             const bool dumpLanes = std::getenv("CRT_DUMP_LANES") != nullptr;
@@ -614,7 +650,7 @@ void crtRunMesh(RendererContext& c, int ns, bool resume) {
                 } else {
                     CRT_CHECK(cudaGraphLaunch(c.graphExec, stream));
                 }
-                launches += (unsigned long long)batch * MESH_KERNELS_PER_ITERATION;
+                launches += (unsigned long long)batch * kernelsPerIteration;
                 CRT_CHECK(cudaMemcpyAsync(host, mp.ctl, sizeof(MeshControl), cudaMemcpyDeviceToHost, stream));
                 if (chase) CRT_CHECK(cudaMemcpyAsync(hostRing, ring.ctl, 16 * sizeof(unsigned int), cudaMemcpyDeviceToHost, stream));
                 CRT_CHECK(cudaStreamSynchronize(stream));
@@ -644,7 +680,7 @@ void crtRunMesh(RendererContext& c, int ns, bool resume) {
             for (auto& e : profEvents) cudaEventDestroy(e);
             if (chase) { // wait for the chaser's waves, collect their ray counts
                 for (int k = 0; k < (wave < CHASE_STREAMS ? wave : CHASE_STREAMS); k++) CRT_CHECK(cudaStreamSynchronize(g_cache.chaseStreams[k]));
-                CRT_CHECK(cudaMemcpyAsync(hostRing, ring.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+                CRT_CHECK(cudaMemcpyAsync(hostRing, ring.counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
                 CRT_CHECK(cudaStreamSynchronize(stream));
                 const unsigned long long* hc = (const unsigned long long*)hostRing;
                 host->raysExtend += hc[0];
@@ -655,6 +691,7 @@ void crtRunMesh(RendererContext& c, int ns, bool resume) {
                 c.chaserShadowRays = hc[1];
                 c.chaserNodeVisits = hc[2];
                 c.chaserTriTests = hc[3];
+                host->redone += hc[4];
                 if (dumpLanes) {
                     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
                     std::fprintf(stderr, "lanes t=%.2f ms  chaser done: %llu extend + %llu shadow rays in %d waves\n", ms, hc[0], hc[1], wave);
@@ -680,6 +717,7 @@ void crtRunMesh(RendererContext& c, int ns, bool resume) {
     c.stats.iterations = host->iterations;
     c.stats.resumes = host->resumes;
     c.stats.deferred = host->deferred;
+    c.lastFrameRedo = host->redone;
     c.stats.kernelLaunches = launches;
     c.lastNodeVisits = host->nodeVisits;
     c.lastTriTests = host->triTests;

@@ -69,6 +69,7 @@ struct RendererContext {
 
     int samplesDone = 0; // samples per pixel in the sums (runRenderer sets, continueRenderer adds)
     int traceBlocks = 0; // persistent grid of traceKernel: one resident wave
+    int wideTraceBlocks = 0;
     bool counting = false;
     unsigned long long lastNodeVisits = 0, lastTriTests = 0, lastBatchRedo = 0, lastFrameRedo = 0;
     unsigned long long chaserRays = 0, chaserShadowRays = 0, chaserNodeVisits = 0, chaserTriTests = 0; // the chaser's share of the last frame

@@ -16,7 +16,9 @@
 #include <cmath>
 #include <cstring>
 #include <functional>
+#include <condition_variable>
 #include <limits>
+#include <mutex>
 #include <thread>
 
 namespace {
@@ -70,12 +72,15 @@ struct Bins {
     }
 };
 
-// Spin-waiting pool: the build lasts milliseconds, so workers poll a generation counter instead of sleeping.
+// A small pool for the build's parallel passes. Workers spin briefly for the next job (the passes follow each other within
+// microseconds) and then sleep on a condition variable, so an oversubscribed host does not burn its cores on polling.
 struct Pool {
     std::vector<std::thread> workers;
-    std::atomic<uint32_t> generation{0}, next{0}, done{0}, acked{0};
-    std::atomic<bool> quit{false};
-    uint32_t jobCount = 0;
+    std::mutex m;
+    std::condition_variable wake, finished;
+    std::atomic<uint32_t> generation{0}, next{0};
+    uint32_t jobCount = 0, done = 0, leftDrain = 0;
+    bool quit = false;
     std::function<void(uint32_t)> job;
 
     explicit Pool(int threads) {
@@ -83,43 +88,60 @@ struct Pool {
             workers.emplace_back([this] {
                 uint32_t seen = 0;
                 while (true) {
-                    uint32_t g;
-                    while ((g = generation.load(std::memory_order_acquire)) == seen) {
-                        if (quit.load(std::memory_order_relaxed)) return;
-                        std::this_thread::yield();
+                    for (int spin = 0; spin < 2000 && generation.load(std::memory_order_acquire) == seen; spin++) {}
+                    {
+                        std::unique_lock<std::mutex> lk(m);
+                        wake.wait(lk, [&] { return quit || generation.load(std::memory_order_relaxed) != seen; });
+                        if (quit) return;
+                        seen = generation.load(std::memory_order_relaxed);
                     }
-                    seen = g;
-                    drain();
-                    acked.fetch_add(1, std::memory_order_acq_rel); // run() does not return (and set up the next job) before every worker is out of drain()
+                    const uint32_t did = drain();
+                    std::lock_guard<std::mutex> lk(m);
+                    done += did;
+                    leftDrain++;
+                    if (done >= jobCount && leftDrain == workers.size()) finished.notify_one();
                 }
             });
     }
     ~Pool() {
-        quit.store(true);
+        {
+            std::lock_guard<std::mutex> lk(m);
+            quit = true;
+        }
+        wake.notify_all();
         for (auto& w : workers) w.join();
     }
-    void drain() {
+    uint32_t drain() {
+        uint32_t did = 0;
         while (true) {
             const uint32_t i = next.fetch_add(1, std::memory_order_acq_rel);
             if (i >= jobCount) break;
             job(i);
-            done.fetch_add(1, std::memory_order_acq_rel);
+            did++;
         }
+        return did;
     }
+    // Runs fn(0..count-1) on the pool and the calling thread; returns when all are done and every worker is idle again.
     void run(uint32_t count, std::function<void(uint32_t)> fn) {
         if (count == 0) return;
         if (workers.empty() || count == 1) {
             for (uint32_t i = 0; i < count; i++) fn(i);
             return;
         }
-        job = std::move(fn);
-        jobCount = count;
-        done.store(0);
-        next.store(0);
-        acked.store(0);
-        generation.fetch_add(1, std::memory_order_acq_rel);
-        drain();
-        while (done.load(std::memory_order_acquire) < count || acked.load(std::memory_order_acquire) < (uint32_t)workers.size()) std::this_thread::yield();
+        {
+            std::lock_guard<std::mutex> lk(m);
+            job = std::move(fn);
+            jobCount = count;
+            done = 0;
+            leftDrain = 0;
+            next.store(0);
+            generation.fetch_add(1, std::memory_order_release);
+        }
+        wake.notify_all();
+        const uint32_t did = drain();
+        std::unique_lock<std::mutex> lk(m);
+        done += did;
+        finished.wait(lk, [&] { return done >= jobCount && leftDrain == workers.size(); });
     }
     int size() const { return (int)workers.size() + 1; }
 };
@@ -384,6 +406,8 @@ bool buildWideBvh(const triangle* tris, uint32_t numSlots, int threads, WideBvhH
     Builder B;
     uint32_t n = 0;
     Box rootBox, rootCbox;
+    double sah = 0.0;
+    std::chrono::steady_clock::time_point t1;
     {
     Pool pool(threads);
     B.pool = &pool;
@@ -432,116 +456,175 @@ bool buildWideBvh(const triangle* tris, uint32_t numSlots, int threads, WideBvhH
         const Builder::Task& t = B.tasks[k];
         B.build(t.node, t.lo, t.hi, t.cbox, false);
     });
-    B.pool = nullptr;
-    } // the pool's workers spin while they wait: end them before the serial part
     const uint32_t numNodes2 = B.nextNode.load();
-    const auto t1 = std::chrono::steady_clock::now();
+    t1 = std::chrono::steady_clock::now();
     out.stats.numBinaryNodes = numNodes2;
 
-    // ---- collapse + emit, breadth first
-    struct Pending {
-        uint32_t node2;  // binary node that becomes this wide node
-        int depth;
+    // ---- collapse + emit, level by level (breadth-first numbering: the inner children of a node are contiguous, in slot
+    //      order, and so are the leaf triangles of a node). Per level: (1) every node picks its children and their slots in
+    //      parallel, (2) a prefix sum hands out child and triangle indices, (3) every node is quantised and written in parallel.
+    struct Plan {
+        uint32_t node2;
+        uint32_t child[8];      // binary node per SLOT (or ~0u)
+        uint32_t innerCount, triCount;
+        uint32_t childBase, triBase;
     };
-    std::vector<Pending> queue;
-    queue.reserve(n / 2 + 16);
-    queue.push_back(Pending{0, 1});
-    out.nodes.reserve(n / 2 + 16);
-    out.triOrig.reserve(n);
     const std::vector<Node2>& N2 = B.nodes;
-    double sah = 0.0;
-    for (size_t head = 0; head < queue.size(); head++) {
-        const Pending cur = queue[head];
-        out.stats.maxDepth = std::max(out.stats.maxDepth, cur.depth);
-        // children: open the largest inner child until there are 8
-        uint32_t child[8];
-        int nc = 0;
-        if (N2[cur.node2].count) child[nc++] = cur.node2; // the whole tree is one leaf
-        else { child[nc++] = N2[cur.node2].left; child[nc++] = N2[cur.node2].left + 1; }
-        while (nc < 8) {
-            int pick = -1;
-            float bestArea = -1.0f;
-            for (int k = 0; k < nc; k++)
-                if (!N2[child[k]].count) {
-                    const float ar = halfArea(N2[child[k]].b);
-                    if (ar > bestArea) { bestArea = ar; pick = k; }
+    std::vector<Plan> level(1), next;
+    level[0].node2 = 0;
+    out.nodes.clear();
+    out.triOrig.resize(n);
+    uint32_t triCursor = 0;
+    int depth = 0;
+    std::vector<double> sahPart;
+    while (!level.empty()) {
+        depth++;
+        const uint32_t count = (uint32_t)level.size();
+        const uint32_t grain = 64, jobs = (count + grain - 1) / grain;
+        // (1) children and slots
+        pool.run(jobs, [&](uint32_t j) {
+            for (uint32_t i = j * grain; i < std::min(count, (j + 1) * grain); i++) {
+                Plan& pl = level[i];
+                uint32_t child[8];
+                int nc = 0;
+                if (N2[pl.node2].count) child[nc++] = pl.node2; // the whole tree is one leaf
+                else { child[nc++] = N2[pl.node2].left; child[nc++] = N2[pl.node2].left + 1; }
+                while (nc < 8) { // open the inner child with the largest surface area
+                    int pick = -1;
+                    float bestArea = -1.0f;
+                    for (int k = 0; k < nc; k++)
+                        if (!N2[child[k]].count) {
+                            const float ar = halfArea(N2[child[k]].b);
+                            if (ar > bestArea) { bestArea = ar; pick = k; }
+                        }
+                    if (pick < 0) break;
+                    const uint32_t l = N2[child[pick]].left;
+                    child[pick] = l;
+                    child[nc++] = l + 1;
                 }
-            if (pick < 0) break;
-            const uint32_t l = N2[child[pick]].left;
-            child[pick] = l;
-            child[nc++] = l + 1;
-        }
-        // node box and grid
-        Box nb;
-        boxInit(nb);
-        for (int k = 0; k < nc; k++) boxGrow(nb, N2[child[k]].b);
-        WideNode w;
-        std::memset(&w, 0, sizeof(w));
-        double step[3];
-        for (int a = 0; a < 3; a++) {
-            const float p = std::nextafter(nb.lo[a] - out.pad[a], -kInf); // (the subtraction may have rounded up)
-            w.p[a] = p;
-            const double ext = ((double)nb.hi[a] + (double)out.pad[a]) - (double)p;
-            int k = (int)std::ceil(std::log2(std::max(ext, 1e-300) / 127.0));
-            while (std::ldexp(127.0, k) < ext) k++;
-            if (k < -100) k = -100;
-            if (k > 100) k = 100;
-            step[a] = std::ldexp(1.0, k);
-            w.e[a] = (uint8_t)(k + 7 + 127);
-            w.scale[a] = (float)std::ldexp(1.0, k + 7); // A = 128 * step / d
-        }
-        // octant slot assignment: greedy on dot(child centre - node centre, slot direction)
-        float score[8][8];
-        for (int k = 0; k < nc; k++) {
-            float d[3];
-            for (int a = 0; a < 3; a++) d[a] = 0.5f * (N2[child[k]].b.lo[a] + N2[child[k]].b.hi[a]) - 0.5f * (nb.lo[a] + nb.hi[a]);
-            for (int s = 0; s < 8; s++) score[k][s] = ((s & 4) ? d[0] : -d[0]) + ((s & 2) ? d[1] : -d[1]) + ((s & 1) ? d[2] : -d[2]);
-        }
-        int slotOf[8], childOfSlot[8];
-        for (int k = 0; k < 8; k++) { slotOf[k] = -1; childOfSlot[k] = -1; }
-        for (int round = 0; round < nc; round++) {
-            int bk = -1, bs = -1;
-            float bv = -kInf;
-            for (int k = 0; k < nc; k++) {
-                if (slotOf[k] >= 0) continue;
+                Box nb;
+                boxInit(nb);
+                for (int k = 0; k < nc; k++) boxGrow(nb, N2[child[k]].b);
+                // octant slot assignment: greedy on dot(child centre - node centre, slot direction)
+                float score[8][8];
+                for (int k = 0; k < nc; k++) {
+                    float d[3];
+                    for (int a = 0; a < 3; a++) d[a] = 0.5f * (N2[child[k]].b.lo[a] + N2[child[k]].b.hi[a]) - 0.5f * (nb.lo[a] + nb.hi[a]);
+                    for (int s = 0; s < 8; s++) score[k][s] = ((s & 4) ? d[0] : -d[0]) + ((s & 2) ? d[1] : -d[1]) + ((s & 1) ? d[2] : -d[2]);
+                }
+                bool placed[8] = {false, false, false, false, false, false, false, false};
+                for (int s = 0; s < 8; s++) pl.child[s] = ~0u;
+                for (int round = 0; round < nc; round++) {
+                    int bk = -1, bs = -1;
+                    float bv = -kInf;
+                    for (int k = 0; k < nc; k++) {
+                        if (placed[k]) continue;
+                        for (int s = 0; s < 8; s++)
+                            if (pl.child[s] == ~0u && score[k][s] > bv) { bv = score[k][s]; bk = k; bs = s; }
+                    }
+                    placed[bk] = true;
+                    pl.child[bs] = child[bk];
+                }
+                pl.innerCount = pl.triCount = 0;
                 for (int s = 0; s < 8; s++)
-                    if (childOfSlot[s] < 0 && score[k][s] > bv) { bv = score[k][s]; bk = k; bs = s; }
+                    if (pl.child[s] != ~0u) {
+                        if (N2[pl.child[s]].count) pl.triCount += N2[pl.child[s]].count;
+                        else pl.innerCount++;
+                    }
             }
-            slotOf[bk] = bs;
-            childOfSlot[bs] = bk;
+        });
+        // (2) indices
+        const uint32_t levelStart = (uint32_t)out.nodes.size();
+        uint32_t childCursor = levelStart + count;
+        for (uint32_t i = 0; i < count; i++) {
+            level[i].childBase = childCursor;
+            level[i].triBase = triCursor;
+            childCursor += level[i].innerCount;
+            triCursor += level[i].triCount;
         }
-        // emit in slot order
-        w.childBase = (uint32_t)queue.size();
-        w.triBase = (uint32_t)out.triOrig.size();
-        uint32_t triOffset = 0;
-        for (int s = 0; s < 8; s++) {
-            for (int a = 0; a < 3; a++) { w.qlo[a][s] = quantByte(127); w.qhi[a][s] = quantByte(0); } // empty slot: inverted box
-            const int k = childOfSlot[s];
-            if (k < 0) continue;
-            const Node2& c = N2[child[k]];
-            for (int a = 0; a < 3; a++) {
-                const double lo = (double)c.b.lo[a] - (double)out.pad[a], hi = (double)c.b.hi[a] + (double)out.pad[a];
-                int ql = (int)std::floor((lo - (double)w.p[a]) / step[a]);
-                int qh = (int)std::ceil((hi - (double)w.p[a]) / step[a]);
-                while ((double)w.p[a] + ql * step[a] > lo) ql--;
-                while ((double)w.p[a] + qh * step[a] < hi) qh++;
-                w.qlo[a][s] = quantByte(ql);
-                w.qhi[a][s] = quantByte(qh);
+        out.nodes.resize(levelStart + count);
+        next.resize(childCursor - (levelStart + count));
+        sahPart.assign(jobs, 0.0);
+        // (3) quantise and write
+        pool.run(jobs, [&](uint32_t j) {
+            double sahLocal = 0.0;
+            for (uint32_t i = j * grain; i < std::min(count, (j + 1) * grain); i++) {
+                const Plan& pl = level[i];
+                Box nb;
+                boxInit(nb);
+                for (int s = 0; s < 8; s++)
+                    if (pl.child[s] != ~0u) boxGrow(nb, N2[pl.child[s]].b);
+                // grid. The traversal reads the plane byte of an EVEN slot together with the byte of the next slot as excess
+                // mantissa (wide_traverse.cuh planePair): its plane lies (q + g) steps above the origin, 0.248 <= g < 0.25.
+                // Half a step of slack below the lowest plane and above the highest keeps every q inside 0..127.
+                WideNode w;
+                std::memset(&w, 0, sizeof(w));
+                double step[3];
+                for (int a = 0; a < 3; a++) {
+                    const double lo = (double)nb.lo[a] - (double)out.pad[a], hi = (double)nb.hi[a] + (double)out.pad[a];
+                    int k = (int)std::ceil(std::log2(std::max(hi - lo, 1e-300) / 126.0));
+                    if (k < -100) k = -100;
+                    float p;
+                    while (true) {
+                        step[a] = std::ldexp(1.0, k);
+                        p = (float)(lo - 0.5 * step[a]);
+                        if ((double)p > lo - 0.3 * step[a]) p = std::nextafter(p, -kInf);
+                        if ((lo - (double)p) / step[a] >= 0.3 && (hi - (double)p) / step[a] <= 126.7) break;
+                        k++;
+                    }
+                    w.p[a] = p;
+                    w.e[a] = (uint8_t)std::min(std::max(k + 7 + 127, 0), 255);
+                    w.scale[a] = (float)std::ldexp(1.0, k + 7); // A = 128 * step / d
+                }
+                for (int s = 7; s >= 0; s--) { // odd slots before the even slot that reads them as excess mantissa
+                    for (int a = 0; a < 3; a++) { w.qlo[a][s] = quantByte(127); w.qhi[a][s] = quantByte(0); } // empty slot: inverted box
+                    if (pl.child[s] == ~0u) continue;
+                    const Node2& c = N2[pl.child[s]];
+                    for (int a = 0; a < 3; a++) {
+                        const double lo = (double)c.b.lo[a] - (double)out.pad[a], hi = (double)c.b.hi[a] + (double)out.pad[a];
+                        const double inv = 1.0 / step[a];
+                        // excess of this slot's planes in steps (exact: the neighbour's bytes are final)
+                        const double gl = (s & 1) ? 0.0 : (double)(0x3F00 | w.qlo[a][s + 1]) / 65536.0;
+                        const double gh = (s & 1) ? 0.0 : (double)(0x3F00 | w.qhi[a][s + 1]) / 65536.0;
+                        int ql = (int)std::floor((lo - (double)w.p[a]) * inv - gl);
+                        int qh = (int)std::ceil((hi - (double)w.p[a]) * inv - gh);
+                        while ((double)w.p[a] + (ql + gl) * step[a] > lo) ql--;
+                        while ((double)w.p[a] + (qh + gh) * step[a] < hi) qh++;
+                        w.qlo[a][s] = quantByte(ql);
+                        w.qhi[a][s] = quantByte(qh);
+                    }
+                }
+                w.childBase = pl.childBase;
+                w.triBase = pl.triBase;
+                uint32_t triOffset = 0, inner = 0;
+                for (int s = 0; s < 8; s++) { // emit in slot order
+                    if (pl.child[s] == ~0u) continue;
+                    const Node2& c = N2[pl.child[s]];
+                    if (c.count) {
+                        w.meta[s] = (uint8_t)((c.count << 5) | triOffset);
+                        for (uint32_t t = 0; t < c.count; t++) out.triOrig[pl.triBase + triOffset + t] = B.prims[c.first + t].id;
+                        triOffset += c.count;
+                        sahLocal += (double)halfArea(c.b) * c.count * kTriCost;
+                    } else {
+                        w.imask |= (uint8_t)(1u << s);
+                        w.meta[s] = (uint8_t)(0x20 | (24 + s));
+                        next[pl.childBase - (levelStart + count) + inner].node2 = pl.child[s];
+                        inner++;
+                    }
+                }
+                sahLocal += (double)halfArea(nb) * kNodeCost;
+                out.nodes[levelStart + i] = w;
             }
-            if (c.count) {
-                w.meta[s] = (uint8_t)((c.count << 5) | triOffset);
-                for (uint32_t i = 0; i < c.count; i++) out.triOrig.push_back(B.prims[c.first + i].id);
-                triOffset += c.count;
-                sah += (double)halfArea(c.b) * c.count * kTriCost;
-            } else {
-                w.imask |= (uint8_t)(1u << s);
-                w.meta[s] = (uint8_t)(0x20 | (24 + s));
-                queue.push_back(Pending{child[k], cur.depth + 1});
-            }
-        }
-        sah += (double)halfArea(nb) * kNodeCost;
-        out.nodes.push_back(w);
+            sahPart[j] = sahLocal;
+        });
+        for (double v : sahPart) sah += v;
+        level.swap(next);
+        next.clear();
     }
+    out.stats.maxDepth = depth;
+    out.triOrig.resize(triCursor);
+    B.pool = nullptr;
+    } // (the pool's workers spin while they wait: it lives only as long as the build)
     const auto t2 = std::chrono::steady_clock::now();
     out.stats.numNodes = (uint32_t)out.nodes.size();
     out.stats.numTris = (uint32_t)out.triOrig.size();

@@ -54,10 +54,38 @@ __device__ __forceinline__ void ldg256u(const void* p, uint4& a, uint4& b) {
         : "l"(p));
 }
 
-// byte j of `w` (0x80 | q) as the float 1 + q/128: one PRMT
-template <int J>
-__device__ __forceinline__ float planeFloat(unsigned int w) {
-    return __uint_as_float(__byte_perm(w, 0x3F000000u, 0x7044 | (J << 8)));
+// Plane decode, two children per PRMT. The bytes (0x80 | q) of children 2k and 2k+1 and two constant 0x3F bytes form the
+// word [3F][Q 2k][3F][Q 2k+1]: read as a float it is 1 + q/128 for child 2k (plus the low half as 0.248..0.25 of a grid
+// step of excess mantissa, which the builder has already accounted for when it rounded child 2k's planes outward:
+// wide_bvh.cpp), shifted left by 16 it is exactly 1 + q/128 for child 2k+1. The 0x3F bytes come from a register the compiler
+// cannot see through, so that the selector stays an immediate (otherwise ptxas keeps re-materialising selector registers).
+__device__ __forceinline__ unsigned int wideConst3F() {
+    unsigned int k;
+    asm volatile("mov.u32 %0, 0x3F3F3F3F;" : "=r"(k));
+    return k;
+}
+template <int PAIR>
+__device__ __forceinline__ unsigned int planePair(unsigned int w, unsigned int k3f) {
+    unsigned int d;
+    if (PAIR == 0) asm("prmt.b32 %0, %1, %2, 0x4041;" : "=r"(d) : "r"(w), "r"(k3f));
+    else asm("prmt.b32 %0, %1, %2, 0x4243;" : "=r"(d) : "r"(w), "r"(k3f));
+    return d;
+}
+// {t(child 2k), t(child 2k+1)} = {m, m'} * a + b in one packed FMA (sm_100 FFMA2)
+__device__ __forceinline__ float2 slabPairFma(unsigned int pair, float a, float b) {
+    float2 r;
+    const unsigned int second = pair << 16;
+    asm("{\n\t"
+        ".reg .b64 p, q, s;\n\t"
+        "mov.b64 p, {%2, %3};\n\t"
+        "mov.b64 q, {%4, %4};\n\t"
+        "mov.b64 s, {%5, %5};\n\t"
+        "fma.rn.f32x2 p, p, q, s;\n\t"
+        "mov.b64 {%0, %1}, p;\n\t"
+        "}"
+        : "=f"(r.x), "=f"(r.y)
+        : "r"(pair), "r"(second), "f"(a), "f"(b));
+    return r;
 }
 
 // Sets the ray up. Returns false when the fast path does not take it (origin outside the range the padding covers, or a
@@ -68,7 +96,8 @@ __device__ __forceinline__ bool wideSetup(const WideView& w, WideRay& r, const f
     const float dy = fabsf(d.y) < 1e-20f ? copysignf(1e-20f, d.y) : d.y;
     const float dz = fabsf(d.z) < 1e-20f ? copysignf(1e-20f, d.z) : d.z;
     r.ix = 1.0f / dx; r.iy = 1.0f / dy; r.iz = 1.0f / dz;
-    r.oct = (d.x < 0.0f ? 0u : 4u) | (d.y < 0.0f ? 0u : 2u) | (d.z < 0.0f ? 0u : 1u) | (anyHit ? WIDE_FLAG_ANYHIT : 0u);
+    // near / far by the SIGN BIT of the clamped component (-0.0 clamps to -1e-20: its reciprocal is negative)
+    r.oct = (signbit(dx) ? 0u : 4u) | (signbit(dy) ? 0u : 2u) | (signbit(dz) ? 0u : 1u) | (anyHit ? WIDE_FLAG_ANYHIT : 0u);
     const bool finite = (fabsf(d.x) <= 1.0f) && (fabsf(d.y) <= 1.0f) && (fabsf(d.z) <= 1.0f); // false for NaN
     return finite && fabsf(o.x) <= w.rangeX && fabsf(o.y) <= w.rangeY && fabsf(o.z) <= w.rangeZ;
 }
@@ -91,19 +120,10 @@ __device__ __forceinline__ void widePop(WideTrav& s, const uint2* stack, unsigne
     }
 }
 
-// one child: slab distances from the six plane bytes, hit test, one bit of the slot mask
-#define WIDE_CHILD(J, SLOT, NX, FX, NY, FY, NZ, FZ)                                                    \
-    {                                                                                                  \
-        const float tnx = __fmaf_rn(planeFloat<J>(NX), ax, bx), tfx = __fmaf_rn(planeFloat<J>(FX), ax, bx); \
-        const float tny = __fmaf_rn(planeFloat<J>(NY), ay, by), tfy = __fmaf_rn(planeFloat<J>(FY), ay, by); \
-        const float tnz = __fmaf_rn(planeFloat<J>(NZ), az, bz), tfz = __fmaf_rn(planeFloat<J>(FZ), az, bz); \
-        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));                                     \
-        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, limit));                                    \
-        if (tn <= tf) hits |= 1u << (SLOT);                                                            \
-    }
-
 // One wide-node step: take the nearest pending child of the node group, test its 8 children, form the new groups.
-__device__ __forceinline__ void wideNodeStep(const WideView& w, const WideRay& r, WideTrav& s, uint2* stack, unsigned int stride) {
+// Instruction budget (the kernel is bound by instruction issue, mostly the ALU pipe: profiles/r02): per node 24 PRMT,
+// 24 shifts, 24 packed FMAs, 32 min/max, 8 subtractions whose sign bits are funnelled into the miss mask.
+__device__ __forceinline__ void wideNodeStep(const WideView& w, const WideRay& r, WideTrav& s, uint2* stack, unsigned int stride, unsigned int k3f) {
     const unsigned int bit = 31u - (unsigned int)__clz(s.ngy);
     s.ngy &= ~(1u << bit);
     if (s.ngy > 0x00FFFFFFu) {
@@ -123,19 +143,33 @@ __device__ __forceinline__ void wideNodeStep(const WideView& w, const WideRay& r
     const float bz = __fmaf_rn(__uint_as_float(h0.z) - r.oz, r.iz, -az);
     const float limit = (r.oct & WIDE_FLAG_ANYHIT) ? s.closest : s.closest * WIDE_TIE_MARGIN;
     const bool px = (r.oct & 4u) != 0u, py = (r.oct & 2u) != 0u, pz = (r.oct & 1u) != 0u;
-    // near / far plane words per axis and half (slots 0..3, 4..7)
-    const unsigned int nx0 = px ? q0.x : q1.z, nx1 = px ? q0.y : q1.w, fx0 = px ? q1.z : q0.x, fx1 = px ? q1.w : q0.y;
-    const unsigned int ny0 = py ? q0.z : q2.x, ny1 = py ? q0.w : q2.y, fy0 = py ? q2.x : q0.z, fy1 = py ? q2.y : q0.w;
-    const unsigned int nz0 = pz ? q1.x : q2.z, nz1 = pz ? q1.y : q2.w, fz0 = pz ? q2.z : q1.x, fz1 = pz ? q2.w : q1.y;
-    unsigned int hits = 0u;
-    WIDE_CHILD(0, 0, nx0, fx0, ny0, fy0, nz0, fz0)
-    WIDE_CHILD(1, 1, nx0, fx0, ny0, fy0, nz0, fz0)
-    WIDE_CHILD(2, 2, nx0, fx0, ny0, fy0, nz0, fz0)
-    WIDE_CHILD(3, 3, nx0, fx0, ny0, fy0, nz0, fz0)
-    WIDE_CHILD(0, 4, nx1, fx1, ny1, fy1, nz1, fz1)
-    WIDE_CHILD(1, 5, nx1, fx1, ny1, fy1, nz1, fz1)
-    WIDE_CHILD(2, 6, nx1, fx1, ny1, fy1, nz1, fz1)
-    WIDE_CHILD(3, 7, nx1, fx1, ny1, fy1, nz1, fz1)
+    unsigned int miss = 0u;
+#define WIDE_HALF(NX, FX, NY, FY, NZ, FZ)                                                                               \
+    {                                                                                                                    \
+        const float2 nxa = slabPairFma(planePair<0>(NX, k3f), ax, bx), nxb = slabPairFma(planePair<1>(NX, k3f), ax, bx); \
+        const float2 fxa = slabPairFma(planePair<0>(FX, k3f), ax, bx), fxb = slabPairFma(planePair<1>(FX, k3f), ax, bx); \
+        const float2 nya = slabPairFma(planePair<0>(NY, k3f), ay, by), nyb = slabPairFma(planePair<1>(NY, k3f), ay, by); \
+        const float2 fya = slabPairFma(planePair<0>(FY, k3f), ay, by), fyb = slabPairFma(planePair<1>(FY, k3f), ay, by); \
+        const float2 nza = slabPairFma(planePair<0>(NZ, k3f), az, bz), nzb = slabPairFma(planePair<1>(NZ, k3f), az, bz); \
+        const float2 fza = slabPairFma(planePair<0>(FZ, k3f), az, bz), fzb = slabPairFma(planePair<1>(FZ, k3f), az, bz); \
+        WIDE_CHILD(nxb.y, nyb.y, nzb.y, fxb.y, fyb.y, fzb.y)                                                             \
+        WIDE_CHILD(nxb.x, nyb.x, nzb.x, fxb.x, fyb.x, fzb.x)                                                             \
+        WIDE_CHILD(nxa.y, nya.y, nza.y, fxa.y, fya.y, fza.y)                                                             \
+        WIDE_CHILD(nxa.x, nya.x, nza.x, fxa.x, fya.x, fza.x)                                                             \
+    }
+    // hit <=> max(near x, y, z, 0) <= min(far x, y, z, limit); the sign bit of (far - near) is shifted into the miss mask
+#define WIDE_CHILD(TNX, TNY, TNZ, TFX, TFY, TFZ)                                                  \
+    {                                                                                             \
+        const float tn = fmaxf(fmaxf(TNX, TNY), fmaxf(TNZ, 0.0f));                                \
+        const float tf = fminf(fminf(TFX, TFY), fminf(TFZ, limit));                               \
+        miss = __funnelshift_l(__float_as_uint(__fsub_rn(tf, tn)), miss, 1);                      \
+    }
+    // children 7..4 first: the mask is shifted left once per child, so child j ends in bit j
+    WIDE_HALF(px ? q0.y : q1.w, px ? q1.w : q0.y, py ? q0.w : q2.y, py ? q2.y : q0.w, pz ? q1.y : q2.w, pz ? q2.w : q1.y)
+    WIDE_HALF(px ? q0.x : q1.z, px ? q1.z : q0.x, py ? q0.z : q2.x, py ? q2.x : q0.z, pz ? q1.x : q2.z, pz ? q2.z : q1.x)
+#undef WIDE_CHILD
+#undef WIDE_HALF
+    const unsigned int hits = ~miss & 0xFFu;
     const unsigned int imask = h0.w >> 24;
     // inner hits -> priority order: bit (slot ^ octinv), three conditional swaps of an 8-bit mask
     unsigned int prio = hits & imask;
@@ -201,12 +235,12 @@ __device__ __forceinline__ void wideTriPhase(const WideView& w, WideRay& r, RayC
 // issued while at least `quorum` lanes stand on nodes, then every lane that holds triangles tests them.
 // Invariant between calls: a lane that is not finished (sp >= 0) has triangles (tgy != 0) or a pending node (ngy hits).
 __device__ __forceinline__ void wideRound(const WideView& w, WideRay& r, RayCold& c, float tMin, bool on, WideTrav& s, uint2* stack,
-                                          unsigned int stride, int quorum, unsigned int& nodeVisits, unsigned int& triTests) {
+                                          unsigned int stride, int quorum, unsigned int k3f, unsigned int& nodeVisits, unsigned int& triTests) {
     while (true) {
         const bool atNode = on && s.sp >= 0 && s.tgy == 0u;
         if (__popc(__ballot_sync(0xFFFFFFFFu, atNode)) < quorum) break;
         if (atNode) {
-            wideNodeStep(w, r, s, stack, stride);
+            wideNodeStep(w, r, s, stack, stride, k3f);
             nodeVisits++;
         }
     }

@@ -47,13 +47,14 @@ struct Walker {
             if (!(oracleBoxDist(m->bounds.min.e, m->bounds.max.e, o, dRaw, tMax) < FLT_MAX)) return FLT_MAX;
         }
         float idir[3];
-        uint32_t octinv = 0;
+        bool neg[3];
         for (int a = 0; a < 3; a++) {
             float da = d[a];
             if (std::fabs(da) < 1e-20f) da = std::copysign(1e-20f, da);
             idir[a] = 1.0f / da;
+            neg[a] = std::signbit(da); // (-0.0 clamps to -1e-20: near / far follow the sign bit)
         }
-        octinv = (d[0] < 0.0f ? 0u : 4u) | (d[1] < 0.0f ? 0u : 2u) | (d[2] < 0.0f ? 0u : 1u);
+        const uint32_t octinv = (neg[0] ? 0u : 4u) | (neg[1] ? 0u : 2u) | (neg[2] ? 0u : 1u);
         const float delta = 1.00001f;
         float closest = tMax, closestPad = anyHit ? tMax : tMax * delta;
         bool tie = false;
@@ -92,10 +93,13 @@ struct Walker {
                     if (n.meta[s] == 0) continue;
                     float tn = 0.0f, tf = closestPad;
                     for (int a = 0; a < 3; a++) {
-                        const uint8_t bn = d[a] < 0.0f ? n.qhi[a][s] : n.qlo[a][s];
-                        const uint8_t bf = d[a] < 0.0f ? n.qlo[a][s] : n.qhi[a][s];
-                        const float mn = asFloat(0x3F000000u | ((uint32_t)bn << 16));
-                        const float mf = asFloat(0x3F000000u | ((uint32_t)bf << 16));
+                        const uint8_t bn = neg[a] ? n.qhi[a][s] : n.qlo[a][s];
+                        const uint8_t bf = neg[a] ? n.qlo[a][s] : n.qhi[a][s];
+                        // planePair (wide_traverse.cuh): an even slot's byte is read together with the next slot's byte as excess mantissa
+                        const uint32_t gn = (s & 1) ? 0u : (0x3F00u | (neg[a] ? n.qhi[a][s + 1] : n.qlo[a][s + 1]));
+                        const uint32_t gf = (s & 1) ? 0u : (0x3F00u | (neg[a] ? n.qlo[a][s + 1] : n.qhi[a][s + 1]));
+                        const float mn = asFloat(0x3F000000u | ((uint32_t)bn << 16) | gn);
+                        const float mf = asFloat(0x3F000000u | ((uint32_t)bf << 16) | gf);
                         tn = std::fmax(tn, std::fmaf(mn, A[a], Bc[a]));
                         tf = std::fmin(tf, std::fmaf(mf, A[a], Bc[a]));
                     }
@@ -231,7 +235,8 @@ int wideCheckStructure(const kernel_scene* sc, int threads, double* buildMs, uns
             }
             for (int a = 0; a < 3; a++) {
                 const double step = std::ldexp(1.0, (int)n.e[a] - 127 - 7);
-                const double qlo = (double)n.p[a] + (n.qlo[a][s] & 127) * step, qhi = (double)n.p[a] + (n.qhi[a][s] & 127) * step;
+                const double gl = (s & 1) ? 0.0 : (double)(0x3F00 | n.qlo[a][s + 1]) / 65536.0, gh = (s & 1) ? 0.0 : (double)(0x3F00 | n.qhi[a][s + 1]) / 65536.0;
+                const double qlo = (double)n.p[a] + ((n.qlo[a][s] & 127) + gl) * step, qhi = (double)n.p[a] + ((n.qhi[a][s] & 127) + gh) * step;
                 if (qlo > clo[a] - w.pad[a] || qhi < chi[a] + w.pad[a]) return -6;
                 blo[a] = std::fmin(blo[a], clo[a]);
                 bhi[a] = std::fmax(bhi[a], chi[a]);
