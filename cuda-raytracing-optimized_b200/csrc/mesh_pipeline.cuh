@@ -501,32 +501,51 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(
 // certified against the caller's tree; what cannot be certified (and rays the wide arithmetic does not cover) goes to
 // redoQ and is traced by traceKernel<.., REDO> right after this launch, before the iteration's shade kernel.
 // There is no step budget and no parking: the traversal stack lives in shared memory (wide.stackDepth entries per thread).
-#define WIDE_TRACE_BLOCKS_PER_SM 4 // 64 registers
+#ifndef WIDE_TRACE_BLOCK
+#define WIDE_TRACE_BLOCK 128
+#endif
+#ifndef WIDE_TRACE_BLOCKS_PER_SM
+#define WIDE_TRACE_BLOCKS_PER_SM 7 // 72 registers, no spills (256 x 4 = 64 registers spilled 24 bytes inside the node step; same speed)
+#endif
+#ifndef WIDE_TRACE_MIN_ACTIVE
+#define WIDE_TRACE_MIN_ACTIVE 14 // refill when fewer lanes than this hold a ray: a refill pass costs ~300 instructions (measured: 14 < 20 < 24 < 28)
+#endif
 template <bool COUNT, int CUR, bool CERTIFY>
-__global__ void __launch_bounds__(TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wideTraceKernel(MeshState st, MeshView mesh, WideView wide) {
+__global__ void __launch_bounds__(WIDE_TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wideTraceKernel(MeshState st, MeshView mesh, WideView wide) {
     constexpr int cur = CUR;
     extern __shared__ uint2 wideStackAll[];
-    __shared__ RayCold coldAll[TRACE_BLOCK];
+    __shared__ RayCold coldAll[WIDE_TRACE_BLOCK];
+    __shared__ float4 invAll[WIDE_TRACE_BLOCK]; // the reference's 1 / direction (wideSetup)
     RayCold& c = coldAll[threadIdx.x];
+    float4& invT = invAll[threadIdx.x];
     uint2* stack = wideStackAll + threadIdx.x;
     MeshControl* ctl = st.ctl;
     const unsigned int* __restrict__ queue = st.traceQ[cur];
     unsigned int* __restrict__ shadeQ = st.shadeQ[cur];
     const unsigned int lane = laneId();
+    // launch constants and the per-warp "queue exhausted" flag live in shared memory, read where they are used (the same
+    // measure as in traceKernel: held in registers across the traversal loop they cost spills under the 64-register cap)
     __shared__ unsigned int takeShared, countShared;
+    __shared__ unsigned char exhaustedShared[WIDE_TRACE_BLOCK / 32];
     if (threadIdx.x == 0) {
         const unsigned int count = ctl->traceCount[cur];
-        const unsigned int totalWarps = gridDim.x * (TRACE_BLOCK / 32);
+        const unsigned int totalWarps = gridDim.x * (WIDE_TRACE_BLOCK / 32);
         countShared = count;
         takeShared = min(32u, max(1u, (count + totalWarps - 1) / totalWarps)); // short queue: spread the rays over all warps
     }
+    if (threadIdx.x < WIDE_TRACE_BLOCK / 32) exhaustedShared[threadIdx.x] = 0;
     __syncthreads();
-    const unsigned int n = countShared, take = takeShared;
-    const bool tail = take < 32u;
-    const unsigned int refillBelow = tail ? take : (unsigned int)st.traceMinActive;
+    const volatile unsigned int* takePtr = &takeShared;
+    const volatile unsigned int* countPtr = &countShared;
+    const unsigned int exhaustedBase = (unsigned int)__cvta_generic_to_shared(exhaustedShared);
+#define n (*countPtr)
+#define exhausted (warpFlagLoad(exhaustedBase) != 0u)
+#define take (*takePtr)
+#define tail (take < 32u)
+#define refillBelow (tail ? take : (unsigned int)st.traceMinActive)
     const unsigned int k3f = wideConst3F();
 
-    bool live = false, exhausted = false;
+    bool live = false;
     WideRay r;
     WideTrav s;
     unsigned int nodeVisits = 0, triTests = 0;
@@ -545,7 +564,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wideTra
             bool redo = false;
             if (finished) {
                 const unsigned int winner = __float_as_uint(c.rec.z);
-                if (CERTIFY && winner != 0xFFFFFFFFu) redo = !wideCertify(mesh, r, xyz(c.dir), c.dir.w, s.closest, winner);
+                if (CERTIFY && winner != 0xFFFFFFFFu) redo = !wideCertify(mesh, r, xyz(invT), c.dir.w, s.closest, winner);
                 if (!redo) {
                     if (!isShadow) {
                         st.hit[slot] = make_float4(s.closest, c.rec.x, c.rec.y, c.rec.z);
@@ -592,7 +611,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wideTra
                 unsigned int base = 0;
                 if (lane == 0) base = atomicAdd(&ctl->traceCursor, count);
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                if (base + count >= n) exhausted = true;
+                if (base + count >= n) warpFlagSet(exhaustedBase); // warp-uniform: the tail of the queue has been handed out
                 const unsigned int rank = __popc(idle & below);
                 const unsigned int i = base + rank;
                 bool direct = false; // the ray goes to the exact kernel untraced
@@ -607,14 +626,14 @@ __global__ void __launch_bounds__(TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wideTra
                     const f3 d = unit(xyz(rd)); // hit(): ray(p.origin, dir) normalises again (kernels.cu:326)
                     c.dir = mk4(d, tMax);
                     c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), __uint_as_float(e));
-                    if (!wideSetup(wide, r, xyz(ro), d, shadow) || (e & ENTRY_RESUME)) {
+                    f3 inv;
+                    const bool covered = wideSetup(wide, r, xyz(ro), d, shadow, inv);
+                    invT = mk4(inv, 0.0f);
+                    if (!covered || (e & ENTRY_RESUME)) {
                         direct = true;
                     } else {
-                        RayHot rh;
-                        rh.ox = ro.x; rh.oy = ro.y; rh.oz = ro.z;
-                        rh.ix = 1.0f / d.x; rh.iy = 1.0f / d.y; rh.iz = 1.0f / d.z;
                         wideStart(s, tMax);
-                        if (!rayHitsBounds(mesh, rh, tMax)) { // hitMesh: scene bounds first (kernels.cu:297)
+                        if (!wideHitsBounds(mesh, r, inv, tMax)) { // hitMesh: scene bounds first (kernels.cu:297)
                             s.sp = -1;
                             s.closest = FLT_MAX;
                         }
@@ -637,7 +656,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wideTra
             workMask = __ballot_sync(0xFFFFFFFFu, working);
             if (workMask == 0u) continue; // e.g. every new ray missed the scene bounds: retire them
         }
-        wideRound(wide, r, c, RT_EPSILON, working, s, stack, TRACE_BLOCK, tail ? 1 : max(1, min(TRACE_NODE_QUORUM, __popc(workMask) >> 1)), k3f, nodeVisits, triTests);
+        wideRound(wide, r, c, RT_EPSILON, working, s, stack, WIDE_TRACE_BLOCK, tail ? 1 : max(1, min(TRACE_NODE_QUORUM, __popc(workMask) >> 1)), k3f, nodeVisits, triTests);
     }
 
     if (COUNT) {
@@ -651,6 +670,12 @@ __global__ void __launch_bounds__(TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wideTra
         }
     }
 }
+
+#undef n
+#undef exhausted
+#undef take
+#undef tail
+#undef refillBelow
 
 // ------------------------------------------------------------------- shade --
 #ifndef SHADE_DENSE_FRACTION
@@ -757,7 +782,7 @@ __global__ void __launch_bounds__(WF_BLOCK, 4) meshShadeKernel(MeshState st, Sha
 #define CHASE_BLOCK 64     // small blocks: a block gives its registers back when both its warps are done
 #endif
 #ifndef CHASE_MIN_BLOCKS
-#define CHASE_MIN_BLOCKS 12 // register cap 80
+#define CHASE_MIN_BLOCKS 10 // register cap 96: no spills (at 12 blocks / 80 registers the wide chaser spilled 88 bytes)
 #endif
 #define CHASE_SLOTS_PER_WARP 16
 #define CHASE_ENTRY_SHADE 0x40000000u // ring entry: the slot waits to be shaded (ENTRY_RESUME keeps its meaning: parked extend ray)
@@ -818,7 +843,8 @@ struct ChaseLane {
         c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), 0.0f);
         const bool inBounds = rayHitsBounds(mesh, r, tMax);
         if (WIDE) {
-            exactOnly = !wideSetup(wide, wr, o, d, anyHit);
+            f3 inv;
+            exactOnly = !wideSetup(wide, wr, o, d, anyHit, inv); // (inv == {r.ix, r.iy, r.iz}: prepRay made the same divisions)
             wideStart(ws, tMax);
             if (!inBounds || exactOnly) { ws.sp = -1; ws.closest = inBounds ? tMax : FLT_MAX; }
             if (!inBounds) exactOnly = false; // a miss of the scene bounds is final
@@ -851,7 +877,7 @@ __global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(Mes
     const unsigned int warpInBlock = threadIdx.x >> 5;
     const bool exclusive = ((blockIdx.x * (CHASE_BLOCK / 32) + warpInBlock) % exclusiveEvery) == 0u;
     unsigned int* const rctl = ring.ctl + (exclusive ? 8 : 0);
-    const unsigned int* const rentries = ring.entries[exclusive ? 1 : 0];
+    const unsigned int* const rentries = exclusive ? ring.entries[1] : ring.entries[0]; // (a select, not an index: an indexed read would copy the parameter struct to local memory)
     const unsigned int pairLimit = exclusive ? exclusivePairs : 0xFFFFu; // mask of the pairs this warp may fill
     const bool isMain = lane < CHASE_SLOTS_PER_WARP;
     const unsigned int pairIdx = warpInBlock * CHASE_SLOTS_PER_WARP + (lane & (CHASE_SLOTS_PER_WARP - 1u)); // shared by a main lane and its partner
@@ -966,7 +992,7 @@ __global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(Mes
             bool needExact = false;
             if (state == TRACE && t.ws.sp < 0) {
                 const unsigned int winner = __float_as_uint(c.rec.z);
-                needExact = t.exactOnly || (winner != 0xFFFFFFFFu && !wideCertify(mesh, t.wr, xyz(c.dir), c.dir.w, t.ws.closest, winner));
+                needExact = t.exactOnly || (winner != 0xFFFFFFFFu && !wideCertify(mesh, t.wr, mk3(t.r.ix, t.r.iy, t.r.iz), c.dir.w, t.ws.closest, winner));
             }
             if (__any_sync(0xFFFFFFFFu, needExact)) {
                 if (needExact) { // from the root (start() has already tested the scene bounds)

@@ -88,17 +88,19 @@ __global__ void __launch_bounds__(256, 5) intersectBatchKernel(MeshView mesh, co
 
 // The same query through the renderer's own wide tree (wide_traverse.cuh). Rays whose result the certificate does not
 // cover are not answered here: their indices go to `redo` and the order-exact kernel above answers them.
-// Dynamic shared memory: wide.stackDepth * 256 uint2.
+// Dynamic shared memory: wide.stackDepth * WIDE_BATCH_BLOCK uint2.
+#define WIDE_BATCH_BLOCK 128 // 7 blocks per SM at 72 registers: no spills
 template <bool COUNT, bool CERTIFY>
-__global__ void __launch_bounds__(256, 4) wideIntersectBatchKernel(MeshView mesh, WideView wide, const float4* __restrict__ triShade,
+__global__ void __launch_bounds__(WIDE_BATCH_BLOCK, 7) wideIntersectBatchKernel(MeshView mesh, WideView wide, const float4* __restrict__ triShade,
                                                                    const float4* __restrict__ rayO, const float4* __restrict__ rayD,
                                                                    unsigned long long n, float4* __restrict__ outHit, int* __restrict__ outMesh,
                                                                    unsigned long long* cursor, unsigned long long* counts, unsigned int* __restrict__ redo,
                                                                    unsigned long long* redoCount, int anyHit) {
     extern __shared__ uint2 wideStackAll[];
-    __shared__ RayCold coldAll[256];
-    __shared__ float tMinAll[256];
+    __shared__ RayCold coldAll[WIDE_BATCH_BLOCK];
+    __shared__ float4 invAll[WIDE_BATCH_BLOCK]; // {the reference's 1 / direction, tMin}
     RayCold& c = coldAll[threadIdx.x];
+    float4& invT = invAll[threadIdx.x];
     uint2* stack = wideStackAll + threadIdx.x;
     const unsigned int lane = threadIdx.x & 31u;
     bool live = false, exhausted = false;
@@ -124,15 +126,14 @@ __global__ void __launch_bounds__(256, 4) wideIntersectBatchKernel(MeshView mesh
                 const float4 rd = __ldg(rayD + i);
                 const f3 d = unit(xyz(rd)); // the ray constructor normalises (ray.h:9)
                 c.dir = mk4(d, rd.w);
-                tMinAll[threadIdx.x] = ro.w;
                 c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), 0.0f);
-                if (!wideSetup(wide, r, xyz(ro), d, anyHit != 0)) {
+                f3 inv;
+                const bool covered = wideSetup(wide, r, xyz(ro), d, anyHit != 0, inv);
+                invT = mk4(inv, ro.w);
+                if (!covered) {
                     redo[atomicAdd(redoCount, 1ull)] = (unsigned int)i;
                 } else {
-                    RayHot rh;
-                    rh.ox = ro.x; rh.oy = ro.y; rh.oz = ro.z;
-                    rh.ix = 1.0f / d.x; rh.iy = 1.0f / d.y; rh.iz = 1.0f / d.z;
-                    if (!rayHitsBounds(mesh, rh, rd.w)) { // hitMesh: scene bounds first (kernels.cu:297)
+                    if (!wideHitsBounds(mesh, r, inv, rd.w)) { // hitMesh: scene bounds first (kernels.cu:297)
                         outHit[i] = make_float4(FLT_MAX, 0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu));
                         outMesh[i] = -1;
                     } else {
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(256, 4) wideIntersectBatchKernel(MeshView mesh
             if (exhausted) break;
             continue;
         }
-        wideRound(wide, r, c, tMinAll[threadIdx.x], live, s, stack, 256u, max(1, min(TRACE_NODE_QUORUM, __popc(liveMask) >> 1)), k3f, nodeVisits, triTests);
+        wideRound(wide, r, c, invT.w, live, s, stack, WIDE_BATCH_BLOCK, max(1, min(TRACE_NODE_QUORUM, __popc(liveMask) >> 1)), k3f, nodeVisits, triTests);
         if (live && s.sp < 0) {
             float t = s.closest;
             unsigned int triId = __float_as_uint(c.rec.z);
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(256, 4) wideIntersectBatchKernel(MeshView mesh
             int meshID = -1;
             bool certified = true;
             if (triId != 0xFFFFFFFFu && t < c.dir.w) {
-                if (CERTIFY) certified = wideCertify(mesh, r, xyz(c.dir), c.dir.w, t, triId);
+                if (CERTIFY) certified = wideCertify(mesh, r, xyz(invT), c.dir.w, t, triId);
                 if (anyHit) { t = 0.0f; triId = 0xFFFFFFFFu; u = v = 0.0f; }
                 else meshID = __float_as_int(__ldg(triShade + 3 * triId).w);
             } else {

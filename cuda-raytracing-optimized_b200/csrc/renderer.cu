@@ -427,6 +427,8 @@ extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb,
     c.light.color = mk3(20.0f, 20.0f, 20.0f);
 }
 
+static bool useWideTree(const RendererContext& c) { return c.wide.stackDepth > 0 && c.traversal != TRAVERSAL_EXACT; }
+
 static ShadeScene shadeScene(const RendererContext& c) {
     ShadeScene s;
     s.triShade = c.triShade;
@@ -439,18 +441,17 @@ static ShadeScene shadeScene(const RendererContext& c) {
     return s;
 }
 
-static bool useWideTree(const RendererContext& c) { return c.wide.stackDepth > 0 && c.traversal != TRAVERSAL_EXACT; }
 
 template <int CUR>
 static void launchWideTrace(RendererContext& c, const MeshState& mp, cudaStream_t stream, int traceBlocks) {
-    const size_t smem = (size_t)c.wide.stackDepth * TRACE_BLOCK * sizeof(uint2);
+    const size_t smem = (size_t)c.wide.stackDepth * WIDE_TRACE_BLOCK * sizeof(uint2);
     const bool certify = c.traversal != TRAVERSAL_WIDE_UNCERTIFIED;
     if (c.counting) {
-        if (certify) wideTraceKernel<true, CUR, true><<<traceBlocks, TRACE_BLOCK, smem, stream>>>(mp, c.mesh, c.wide);
-        else wideTraceKernel<true, CUR, false><<<traceBlocks, TRACE_BLOCK, smem, stream>>>(mp, c.mesh, c.wide);
+        if (certify) wideTraceKernel<true, CUR, true><<<traceBlocks, WIDE_TRACE_BLOCK, smem, stream>>>(mp, c.mesh, c.wide);
+        else wideTraceKernel<true, CUR, false><<<traceBlocks, WIDE_TRACE_BLOCK, smem, stream>>>(mp, c.mesh, c.wide);
     } else {
-        if (certify) wideTraceKernel<false, CUR, true><<<traceBlocks, TRACE_BLOCK, smem, stream>>>(mp, c.mesh, c.wide);
-        else wideTraceKernel<false, CUR, false><<<traceBlocks, TRACE_BLOCK, smem, stream>>>(mp, c.mesh, c.wide);
+        if (certify) wideTraceKernel<false, CUR, true><<<traceBlocks, WIDE_TRACE_BLOCK, smem, stream>>>(mp, c.mesh, c.wide);
+        else wideTraceKernel<false, CUR, false><<<traceBlocks, WIDE_TRACE_BLOCK, smem, stream>>>(mp, c.mesh, c.wide);
     }
     // what the wide walk could not certify, in the reference's order over the caller's tree (usually a handful of rays)
     traceKernel<false, CUR, true><<<c.numSMs, TRACE_BLOCK, 0, stream>>>(mp, c.mesh);
@@ -508,19 +509,19 @@ void crtRunMesh(RendererContext& c, int ns, bool resume) {
         mp.tilesX = (c.nx % 8 == 0 && c.ny % 4 == 0 && !(v && v[0] == '0')) ? (unsigned int)c.nx / 8u : 0u;
     }
     mp.traceBudget = c.opts.reserved[1] > 0 ? c.opts.reserved[1] : TRACE_BUDGET;
-    mp.traceMinActive = c.opts.reserved[2] > 0 ? c.opts.reserved[2] : TRACE_MIN_ACTIVE;
+    mp.traceMinActive = c.opts.reserved[2] > 0 ? c.opts.reserved[2] : (useWideTree(c) ? WIDE_TRACE_MIN_ACTIVE : TRACE_MIN_ACTIVE);
     if (!c.traceBlocks) {
         int perSM = 0;
         CRT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, traceKernel<false, 0>, TRACE_BLOCK, 0));
         c.traceBlocks = c.numSMs * (perSM > 0 ? perSM : 1); // persistent: exactly one resident wave
     }
     if (useWideTree(c) && !c.wideTraceBlocks) {
-        const size_t smem = (size_t)c.wide.stackDepth * TRACE_BLOCK * sizeof(uint2);
+        const size_t smem = (size_t)c.wide.stackDepth * WIDE_TRACE_BLOCK * sizeof(uint2);
         auto prep = [&](auto kernel) { CRT_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); };
         prep(wideTraceKernel<false, 0, true>); prep(wideTraceKernel<false, 1, true>); prep(wideTraceKernel<false, 0, false>); prep(wideTraceKernel<false, 1, false>);
         prep(wideTraceKernel<true, 0, true>); prep(wideTraceKernel<true, 1, true>); prep(wideTraceKernel<true, 0, false>); prep(wideTraceKernel<true, 1, false>);
         int perSM = 0;
-        CRT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, wideTraceKernel<false, 0, true>, TRACE_BLOCK, smem));
+        CRT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, wideTraceKernel<false, 0, true>, WIDE_TRACE_BLOCK, smem));
         c.wideTraceBlocks = c.numSMs * (perSM > 0 ? perSM : 1);
     }
     const int kernelsPerIteration = useWideTree(c) ? 3 : 2;
@@ -939,13 +940,13 @@ extern "C" float intersectBatchDeviceEx(const void* dRayO, const void* dRayD, lo
     const float4* rayO = (const float4*)dRayO;
     const float4* rayD = (const float4*)dRayD;
     if (useWide) {
-        const size_t smem = (size_t)c.wide.stackDepth * 256 * sizeof(uint2);
+        const size_t smem = (size_t)c.wide.stackDepth * WIDE_BATCH_BLOCK * sizeof(uint2);
         const bool certify = c.traversal != TRAVERSAL_WIDE_UNCERTIFIED;
         auto launch = [&](auto kernel) {
             CRT_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int perSM = 1;
-            CRT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, 256, smem));
-            kernel<<<c.numSMs * (perSM > 0 ? perSM : 1), 256, smem, c.stream>>>(c.mesh, c.wide, c.triShade, rayO, rayD, (unsigned long long)n, (float4*)dHit,
+            CRT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, WIDE_BATCH_BLOCK, smem));
+            kernel<<<c.numSMs * (perSM > 0 ? perSM : 1), WIDE_BATCH_BLOCK, smem, c.stream>>>(c.mesh, c.wide, c.triShade, rayO, rayD, (unsigned long long)n, (float4*)dHit,
                                                                                 dMeshId, cursor, counts, c.batchRedo, c.batchScratch + 4, anyHit);
         };
         if (c.counting) { if (certify) launch(wideIntersectBatchKernel<true, true>); else launch(wideIntersectBatchKernel<true, false>); }
@@ -1028,6 +1029,23 @@ extern "C" int scatterBatch(int preset, long long n, const float* in, float* out
     cudaFree(dIn);
     cudaFree(dOut);
     return 0;
+}
+
+// sinCosSmall (wavefront_kernels.cuh) against the math library's sinf / cosf for every float in [0, 2*pi]: returns the number of
+// arguments for which a bit differs (expected 0), or -1 without a device.
+extern "C" long long rendererTrigSelfTest() {
+    unsigned long long* d = nullptr;
+    if (cudaMalloc((void**)&d, sizeof(*d)) != cudaSuccess) return -1;
+    CRT_CHECK(cudaMemset(d, 0, sizeof(*d)));
+    const float twoPi = 6.2831855f;
+    unsigned int last;
+    std::memcpy(&last, &twoPi, 4);
+    trigSelfTestKernel<<<1184, 256>>>(0u, last + 1u, d);
+    CRT_CHECK(cudaGetLastError());
+    unsigned long long h = 0;
+    CRT_CHECK(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return (long long)h;
 }
 
 extern "C" void* rendererDeviceAlloc(size_t bytes) {

@@ -88,18 +88,29 @@ __device__ __forceinline__ float2 slabPairFma(unsigned int pair, float a, float 
     return r;
 }
 
-// Sets the ray up. Returns false when the fast path does not take it (origin outside the range the padding covers, or a
-// non-finite direction): the caller hands it to the exact kernel.
-__device__ __forceinline__ bool wideSetup(const WideView& w, WideRay& r, const f3& o, const f3& d, bool anyHit) {
+// Sets the ray up. `inv` receives the reference's own reciprocal direction (IEEE, may be infinite): the scene-bounds test at
+// the start and the certificate at the end use it, so the three divisions are done once per ray. Returns false when the
+// fast path does not take the ray (origin outside the range the padding covers, or a non-finite direction): the caller
+// hands it to the exact kernel.
+__device__ __forceinline__ bool wideSetup(const WideView& w, WideRay& r, const f3& o, const f3& d, bool anyHit, f3& inv) {
     r.ox = o.x; r.oy = o.y; r.oz = o.z;
-    const float dx = fabsf(d.x) < 1e-20f ? copysignf(1e-20f, d.x) : d.x;
-    const float dy = fabsf(d.y) < 1e-20f ? copysignf(1e-20f, d.y) : d.y;
-    const float dz = fabsf(d.z) < 1e-20f ? copysignf(1e-20f, d.z) : d.z;
-    r.ix = 1.0f / dx; r.iy = 1.0f / dy; r.iz = 1.0f / dz;
-    // near / far by the SIGN BIT of the clamped component (-0.0 clamps to -1e-20: its reciprocal is negative)
-    r.oct = (signbit(dx) ? 0u : 4u) | (signbit(dy) ? 0u : 2u) | (signbit(dz) ? 0u : 1u) | (anyHit ? WIDE_FLAG_ANYHIT : 0u);
+    inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const float big = 1.0f / 1e-20f; // |direction| is clamped to >= 1e-20
+    r.ix = fabsf(d.x) < 1e-20f ? copysignf(big, d.x) : inv.x;
+    r.iy = fabsf(d.y) < 1e-20f ? copysignf(big, d.y) : inv.y;
+    r.iz = fabsf(d.z) < 1e-20f ? copysignf(big, d.z) : inv.z;
+    // near / far by the SIGN BIT of the component (-0.0 clamps to -1e-20: its reciprocal is negative)
+    r.oct = (signbit(d.x) ? 0u : 4u) | (signbit(d.y) ? 0u : 2u) | (signbit(d.z) ? 0u : 1u) | (anyHit ? WIDE_FLAG_ANYHIT : 0u);
     const bool finite = (fabsf(d.x) <= 1.0f) && (fabsf(d.y) <= 1.0f) && (fabsf(d.z) <= 1.0f); // false for NaN
     return finite && fabsf(o.x) <= w.rangeX && fabsf(o.y) <= w.rangeY && fabsf(o.z) <= w.rangeZ;
+}
+
+// hit_bbox (intersections.h:7-23) against the scene bounds, hitMesh's early out (kernels.cu:297)
+__device__ __forceinline__ bool wideHitsBounds(const MeshView& m, const WideRay& r, const f3& inv, float tMax) {
+    RayPrep p;
+    p.o = mk3(r.ox, r.oy, r.oz);
+    p.inv = inv;
+    return boxHit(m.boundsMin, m.boundsMax, p, tMax);
 }
 
 __device__ __forceinline__ void wideStart(WideTrav& s, float tMax) {
@@ -247,9 +258,10 @@ __device__ __forceinline__ void wideRound(const WideView& w, WideRay& r, RayCold
     if (on && s.sp >= 0 && s.tgy != 0u) wideTriPhase(w, r, c, tMin, s, stack, stride, triTests);
 }
 
-// The certificate (header comment). `winner` = caller's slot index of the triangle the walk found, `d` the unit direction,
-// tMax the ray's own limit, `closest` the winner's t (closest-hit rays). True: the reference returns the same hit.
-__device__ __forceinline__ bool wideCertify(const MeshView& m, const WideRay& r, const f3& d, float tMax, float closest, unsigned int winner) {
+// The certificate (header comment). `winner` = caller's slot index of the triangle the walk found, `inv` the reference's
+// reciprocal direction (wideSetup), tMax the ray's own limit, `closest` the winner's t (closest-hit rays). True: the
+// reference returns the same hit.
+__device__ __forceinline__ bool wideCertify(const MeshView& m, const WideRay& r, const f3& inv, float tMax, float closest, unsigned int winner) {
     if (r.oct & WIDE_FLAG_TIE) return false;
     const unsigned int leaf = m.firstLeaf + winner / m.primsPerLeaf;
     const float4* rec = m.nodes + 4ull * (leaf >> 1); // {Lmin, Lmax, Rmin, Rmax} per axis for the children of leaf >> 1
@@ -257,7 +269,7 @@ __device__ __forceinline__ bool wideCertify(const MeshView& m, const WideRay& r,
     const bool right = (leaf & 1u) != 0u;
     RayPrep p;
     p.o = mk3(r.ox, r.oy, r.oz);
-    p.inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z); // the reference's own reciprocal (may be inf)
+    p.inv = inv;
     const float bound = (r.oct & WIDE_FLAG_ANYHIT) ? tMax : fminf(tMax, closest * WIDE_TIE_MARGIN);
     const float entry = boxDist(mk3(right ? qx.z : qx.x, right ? qy.z : qy.x, right ? qz.z : qz.x),
                                 mk3(right ? qx.w : qx.y, right ? qy.w : qy.y, right ? qz.w : qz.y), p, bound);

@@ -132,7 +132,7 @@ DEVICE_SYMBOLS = [
     "rendererCopyToDevice", "getRendererStats", "setRendererProfiling", "getRendererAccumDevice", "setRendererAccumDevice",
     "finalizeFrame", "setRendererCounting", "getRendererTraversalCounts", "rendererDebugRead", "rendererReleaseCaches", "getRendererChaserCounts", "continueRenderer", "getRendererSamplesDone",
     "saveRendererCheckpoint", "loadRendererCheckpoint", "scatterBatch", "intersectBatchDeviceEx", "setRendererTraversal",
-    "getRendererWideInfo",
+    "getRendererWideInfo", "rendererTrigSelfTest",
 ]
 
 TRAVERSAL_WIDE, TRAVERSAL_EXACT, TRAVERSAL_WIDE_UNCERTIFIED = 0, 1, 2
@@ -161,6 +161,7 @@ def device_lib():
         L.intersectBatchDeviceEx.restype = C.c_float
         L.intersectBatchDeviceEx.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int]
         L.setRendererTraversal.argtypes = [C.c_int]
+        L.rendererTrigSelfTest.restype = C.c_longlong
         L.getRendererWideInfo.argtypes = [C.POINTER(RendererWideInfo)]
         L.generateRayBatchDevice.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_float, C.c_float]
         L.rendererDeviceAlloc.restype = C.c_void_p

@@ -104,6 +104,10 @@ void rendererReleaseCaches();
 // after, 0, 0, 0}.  HOST pointers; returns 0, or -1 for an unknown preset.
 int scatterBatch(int preset, long long n, const float* in, float* out);
 
+// Self test: the light sampler's sine / cosine (the math library's fast path restated, csrc/wavefront_kernels.cuh) against
+// sinf / cosf for every float in [0, 2*pi]. Returns the number of differing arguments (0 expected).
+long long rendererTrigSelfTest(void);
+
 void* rendererDeviceAlloc(size_t bytes);
 void rendererDeviceFree(void* p);
 void rendererCopyToHost(void* dst, const void* dSrc, size_t bytes);

@@ -375,3 +375,128 @@ def test_large_ray_batch_side_by_side(crt, oracle, medium_scene):
     assert np.array_equal(hit[:, 3].view(np.uint32), rhit[:, 3].view(np.uint32)) and np.array_equal(mesh, rmesh)
     h = rmesh >= 0
     assert (np.abs(hit[h, 0] - rhit[h, 0]) / np.abs(rhit[h, 0])).max() <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------------------ round 2 --
+HAVE_REF = os.path.exists(os.path.join(os.path.dirname(G), "..", "oracle", "_ref", "ref_driver"))
+HAVE_SHIM = os.path.exists(os.path.join(os.path.dirname(G), "..", "oracle", "_ref", "ref_shim_driver"))
+
+
+def test_light_sampler_trig_equals_libm_on_every_argument(crt):
+    """sinCosSmall (the math library's fast path restated so that no large-argument reduction with its local-memory table is
+    compiled into the kernels) returns the bits of sinf / cosf for EVERY float in [0, 2*pi]."""
+    assert crt.device_lib().rendererTrigSelfTest() == 0
+
+
+def test_any_hit_ray_batch_vs_golden_occluded(crt, small_scene):
+    """The shadow-ray query on the GPU (hitMesh(.., isShadow = true), kernels.cu:207,500) against the reference's own answers
+    for the golden batch, through both traversals."""
+    z = np.load(os.path.join(G, "rays_8192.npz"))
+    rd = z["ray_d"].copy()
+    rd[:, 3] = z["shadow_tmax"]
+    n = rd.shape[0]
+    L = crt.device_lib()
+    for mode in (crt.TRAVERSAL_WIDE, crt.TRAVERSAL_EXACT):
+        crt.set_traversal(mode)
+        with crt.Frame(small_scene, 8, 8, 1):
+            crt.set_traversal(-1)
+            ptrs = [L.rendererDeviceAlloc(16 * n) for _ in range(3)] + [L.rendererDeviceAlloc(4 * n)]
+            L.rendererCopyToDevice(ptrs[0], np.ascontiguousarray(z["ray_o"]).ctypes.data, 16 * n)
+            L.rendererCopyToDevice(ptrs[1], np.ascontiguousarray(rd).ctypes.data, 16 * n)
+            L.intersectBatchDeviceEx(ptrs[0], ptrs[1], n, ptrs[2], ptrs[3], 1)
+            hit = np.zeros((n, 4), np.float32)
+            L.rendererCopyToHost(hit.ctypes.data, ptrs[2], 16 * n)
+            for p in ptrs:
+                L.rendererDeviceFree(p)
+            assert crt.wide_info().active == (1 if mode == crt.TRAVERSAL_WIDE else 0)
+        occluded = hit[:, 0] == 0.0
+        assert np.array_equal(occluded, z["occluded"]), mode
+        assert np.all((hit[:, 0] == 0.0) | (hit[:, 0] == FLT_MAX))
+        assert 0.05 < occluded.mean() < 0.95
+
+
+def test_wide_tree_equals_exact_walk(crt, medium_scene):
+    """The renderer's own wide tree (+ certificate + exact re-trace) against the order-exact walk of the caller's tree: ray
+    batches (closest hit and any-hit) and a frame, bit for bit; the certificate hands only a handful of rays to the exact kernel."""
+    n = 1 << 20
+    L = crt.device_lib()
+    res = {}
+    for mode in (crt.TRAVERSAL_EXACT, crt.TRAVERSAL_WIDE):
+        crt.set_traversal(mode)
+        with crt.Frame(medium_scene, 240, 160, 64) as fr:
+            crt.set_traversal(-1)
+            dO, dD, dH, dM = (L.rendererDeviceAlloc(16 * n) for _ in range(4))
+            out = []
+            for any_hit, tmax in ((0, float(FLT_MAX)), (1, 250.0)):
+                L.generateRayBatchDevice(dO, dD, n, 8192, 4096, 0.01, tmax)
+                L.intersectBatchDeviceEx(dO, dD, n, dH, dM, any_hit)
+                hit, mesh = np.zeros((n, 4), np.float32), np.zeros(n, np.int32)
+                L.rendererCopyToHost(hit.ctypes.data, dH, 16 * n)
+                L.rendererCopyToHost(mesh.ctypes.data, dM, 4 * n)
+                out += [hit, mesh]
+                if mode == crt.TRAVERSAL_WIDE:
+                    assert crt.wide_info().active == 1 and crt.wide_info().lastBatchRedo < 1e-3 * n
+            for p in (dO, dD, dH, dM):
+                L.rendererDeviceFree(p)
+            img = fr.run(8)
+            st = crt.stats()
+            out += [img, st.raysExtend + st.raysShadow, crt.wide_info().lastFrameRedo]
+        res[mode] = out
+    e, w = res[crt.TRAVERSAL_EXACT], res[crt.TRAVERSAL_WIDE]
+    for k in range(4):
+        assert np.array_equal(e[k].view(np.uint32), w[k].view(np.uint32)), k
+    assert np.array_equal(e[4], w[4]) and e[5] == w[5]
+    assert e[6] == 0 and w[6] < 1e-3 * w[5]
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+def test_benchmark_scene_side_by_side_with_reference_kernel(crt, oracle):
+    """BASELINE config 3's own scene and frame size (detail 1.0, 1024^2 textures, 1200x800, depth 64) at 4 spp against the
+    reference's kernel on the same box. Stated bar: >= 99.9 % of pixels within 1e-3 and PSNR >= 50 dB; observed: identical
+    bits. Ray counts: the reference cannot count its rays (its STATS build does not compile on Linux), bench.py's reference arm
+    takes them from profiles/raycounts.json, which rests on the frames being identical -- checked here at 4 spp, and the
+    100-spp count in the file must be what 25 of these frames extrapolate to within the run-to-run spread of path lengths."""
+    nx, ny, ns, depth = 1200, 800, 4, 64
+    tmp = tempfile.mkdtemp()
+    ref, _ = oracle.ref_render(1.0, 1024, 5, nx, ny, ns, depth, os.path.join(tmp, "r.ref"))
+    scene = crt.Scene.staircase(1.0, 1024, 5)
+    with crt.Frame(scene, nx, ny, depth) as fr:
+        img = fr.run(ns)
+        st = crt.stats()
+        info = crt.wide_info()
+    scene.close()
+    within, psnr, exact = frame_stats(img, ref)
+    assert info.active == 1
+    assert within >= 0.999 and psnr >= 50.0, (within, psnr, exact)
+    assert exact == 1.0, f"expected a bit-exact frame, {exact:.6f} of pixels are"
+    rays4 = st.raysExtend + st.raysShadow
+    counts = json.load(open(os.path.join(os.path.dirname(G), "..", "profiles", "raycounts.json")))
+    rays100 = counts["staircase:1.000:1024:1200x800x100:d64"]
+    assert abs(rays100 / 25.0 - rays4) <= 0.01 * rays4, (rays100, rays4)
+
+
+@pytest.mark.skipif(not HAVE_SHIM, reason="oracle/_ref not built")
+def test_config5_rays_on_the_benchmark_bvh_side_by_side(crt, oracle):
+    """4 Mi rays of BASELINE config 5 (half camera rays, half incoherent) against the config-3 BVH (detail 1.0): triangle and
+    mesh ids bit-exact against the reference's hitMesh (oracle/ref_shim.cu), t within 1e-5 relative (observed: t, u, v exact)."""
+    n = 1 << 22
+    L = crt.device_lib()
+    scene = crt.Scene.staircase(1.0, 32, 5)
+    with crt.Frame(scene, 64, 64, 1):
+        dO, dD, dH, dM = (L.rendererDeviceAlloc(16 * n) for _ in range(4))
+        L.generateRayBatchDevice(dO, dD, n, 8192, 4096, 0.01, float(FLT_MAX))
+        L.intersectBatchDevice(dO, dD, n, dH, dM)
+        ro, rd, hit, mesh = np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32), np.zeros(n, np.int32)
+        for a, p in ((ro, dO), (rd, dD), (hit, dH)):
+            L.rendererCopyToHost(a.ctypes.data, p, 16 * n)
+        L.rendererCopyToHost(mesh.ctypes.data, dM, 4 * n)
+        for p in (dO, dD, dH, dM):
+            L.rendererDeviceFree(p)
+        assert crt.wide_info().active == 1
+    scene.close()
+    rhit, rmesh, _ = oracle.ref_intersect_batch(1.0, 32, 5, ro, rd, False, tempfile.mkdtemp())
+    assert np.array_equal(hit[:, 3].view(np.uint32), rhit[:, 3].view(np.uint32)) and np.array_equal(mesh, rmesh)
+    h = rmesh >= 0
+    assert h.mean() > 0.9
+    assert (np.abs(hit[h, 0] - rhit[h, 0]) / np.abs(rhit[h, 0])).max() <= 1e-5
+    assert np.array_equal(hit.view(np.uint32), rhit.view(np.uint32)), "t/u/v are expected to be bit-exact as well"
