@@ -20,6 +20,7 @@
 #include "raybatch_kernels.cuh"
 #include "renderer_internal.h"
 #include "wavefront_kernels.cuh"
+#include "wide_build.cuh"
 #include "wide_bvh.h"
 #include "wide_traverse.cuh"
 
@@ -294,6 +295,112 @@ static void initCommon(RendererContext& c, const camera& cam, vec3** fb, int nx,
     c.initialised = true;
 }
 
+// ------------------------------------------------------------ wide tree on the device --
+struct DeviceWideTree {
+    WideNode* nodes = nullptr;
+    unsigned int* triOrig = nullptr;
+    unsigned int numNodes = 0, numTris = 0, numBinary = 0;
+    int depth = 0, levels = 0;
+    float range[3] = {0, 0, 0};
+    float ms = 0.0f;
+};
+
+// Builds the wide tree from the caller's triangle records already on the device (wide_build.cuh). All work is queued on the
+// default stream; the host reads one counter per level. Returns false when there is no real triangle.
+static bool buildWideOnDevice(const float* dTris, unsigned int numSlots, DeviceWideTree& out) {
+    const auto t0 = std::chrono::steady_clock::now();
+    PhaseTimer pt;
+    GpuBuild b;
+    std::memset(&b, 0, sizeof(b));
+    const size_t n = numSlots;
+    b.n = numSlots;
+    b.primSlot = devAlloc<unsigned int>(n);
+    b.primLo = devAlloc<float4>(n);
+    b.primHi = devAlloc<float4>(n);
+    for (int k = 0; k < 2; k++) { b.order[k] = devAlloc<unsigned int>(n); b.nodeOf[k] = devAlloc<unsigned int>(n); b.active[k] = devAlloc<unsigned int>(n); }
+    b.nLo = devAlloc<float4>(2 * n + 2);
+    b.nHi = devAlloc<float4>(2 * n + 2);
+    b.cLo = devAlloc<int>(3 * (2 * n + 2));
+    b.cHi = devAlloc<int>(3 * (2 * n + 2));
+    b.nFirst = devAlloc<unsigned int>(2 * n + 2);
+    b.nCursor = devAlloc<unsigned int>(2 * n + 2);
+    b.nSlot = devAlloc<int>(2 * n + 2);
+    b.nSplit = devAlloc<uint2>(2 * n + 2);
+    b.binCapacity = n / 2 + 1;
+    b.binCnt = devAlloc<unsigned int>(b.binCapacity * 3 * GB_BINS);
+    b.binLo = devAlloc<int>(b.binCapacity * 3 * GB_BINS * 3);
+    b.binHi = devAlloc<int>(b.binCapacity * 3 * GB_BINS * 3);
+    b.pending = devAlloc<unsigned int>(n + 1);
+    b.depthOf = devAlloc<unsigned int>(n + 1);
+    b.counters = devAlloc<unsigned int>(32);
+    out.nodes = (WideNode*)arenaAlloc((n + 1) * sizeof(WideNode));
+    out.triOrig = devAlloc<unsigned int>(n);
+
+    unsigned int init[32];
+    std::memset(init, 0, sizeof(init));
+    for (int a = 0; a < 3; a++) {
+        init[8 + a] = 0x7F800000u;  init[11 + a] = 0xFF800000u ^ 0x7FFFFFFFu;  // box min / max (order-preserving images of +inf / -inf)
+        init[14 + a] = 0x7F800000u; init[17 + a] = 0xFF800000u ^ 0x7FFFFFFFu;  // centroid min / max
+    }
+    pt.mark("  wide build: allocation");
+    CRT_CHECK(cudaMemcpy(b.counters, init, sizeof(init), cudaMemcpyHostToDevice));
+    gbPrimsKernel<<<(numSlots + 255) / 256, 256>>>(dTris, numSlots, b);
+    gbRootKernel<<<1, 1>>>(b);
+    CRT_CHECK(cudaGetLastError());
+    unsigned int h[8];
+    CRT_CHECK(cudaMemcpy(h, b.counters, sizeof(h), cudaMemcpyDeviceToHost));
+    const unsigned int prims = h[0];
+    if (prims == 0) return false;
+    float4 rootLo, rootHi;
+    CRT_CHECK(cudaMemcpy(&rootLo, b.nLo, sizeof(float4), cudaMemcpyDeviceToHost));
+    CRT_CHECK(cudaMemcpy(&rootHi, b.nHi, sizeof(float4), cudaMemcpyDeviceToHost));
+    const float lo[3] = {rootLo.x, rootLo.y, rootLo.z}, hi[3] = {rootHi.x, rootHi.y, rootHi.z};
+    float pad[3];
+    for (int a = 0; a < 3; a++) {
+        out.range[a] = std::max(std::max(std::fabs(lo[a]), std::fabs(hi[a])), 1e-30f);
+        pad[a] = out.range[a] * WIDE_PAD_SCALE;
+    }
+    pt.mark("  wide build: primitives");
+    // binary tree, level by level
+    int cur = 0;
+    unsigned int activeCount = h[2];
+    const unsigned int primBlocks = (prims + 255) / 256;
+    while (activeCount > 0 && out.levels < 256) {
+        gbClearBinsKernel<<<std::min<unsigned int>((activeCount * 3u * GB_BINS + 255u) / 256u, 4096u), 256>>>(b, activeCount);
+        gbBinKernel<<<primBlocks, 256>>>(b, cur);
+        CRT_CHECK(cudaMemsetAsync(&b.counters[2 + (cur ^ 1)], 0, sizeof(unsigned int)));
+        gbSplitKernel<<<(activeCount * 32u + 255u) / 256u, 256>>>(b, cur, activeCount);
+        gbPartitionKernel<<<primBlocks, 256>>>(b, cur);
+        cur ^= 1;
+        CRT_CHECK(cudaMemcpy(&activeCount, &b.counters[2 + cur], sizeof(unsigned int), cudaMemcpyDeviceToHost));
+        out.levels++;
+    }
+    CRT_CHECK(cudaGetLastError());
+    pt.mark("  wide build: binary levels");
+    // collapse, level by level
+    const unsigned int one = 1u, zero = 0u;
+    CRT_CHECK(cudaMemcpy(&b.counters[4], &one, 4, cudaMemcpyHostToDevice));
+    CRT_CHECK(cudaMemcpy(&b.counters[5], &zero, 4, cudaMemcpyHostToDevice));
+    CRT_CHECK(cudaMemcpy(&b.counters[6], &zero, 4, cudaMemcpyHostToDevice));
+    CRT_CHECK(cudaMemcpy(b.pending, &zero, 4, cudaMemcpyHostToDevice));
+    CRT_CHECK(cudaMemcpy(b.depthOf, &one, 4, cudaMemcpyHostToDevice));
+    unsigned int start = 0, end = 1;
+    while (end > start) {
+        gbCollapseKernel<<<(end - start + 63) / 64, 64>>>(b, cur, start, end, make_float3(pad[0], pad[1], pad[2]), out.nodes, out.triOrig);
+        start = end;
+        CRT_CHECK(cudaMemcpy(&end, &b.counters[4], sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    }
+    CRT_CHECK(cudaGetLastError());
+    pt.mark("  wide build: collapse");
+    CRT_CHECK(cudaMemcpy(h, b.counters, sizeof(h), cudaMemcpyDeviceToHost));
+    out.numBinary = h[1];
+    out.numNodes = h[4];
+    out.numTris = h[5];
+    out.depth = (int)h[6];
+    out.ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return out.numTris == prims;
+}
+
 extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb, int nx, int ny, int maxDepth) {
     RendererContext& c = g_ctx;
     if (c.initialised) cleanupRenderer();
@@ -306,10 +413,13 @@ extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb,
     const unsigned int numSlots = m->numTris;
     // our own tree is built on host threads from the caller's triangles while this thread uploads the scene
     c.traversal = traversalMode();
+    // CRT_WIDE_BUILD=host: the host builder (wide_bvh.cpp; the device build's cross-check), overlapped with the uploads
+    const char* buildEnv = std::getenv("CRT_WIDE_BUILD");
+    const bool hostBuild = buildEnv && buildEnv[0] == 'h';
     WideBvhHost wideHost;
     bool wideBuilt = false;
     std::thread wideBuilder;
-    if (c.traversal != TRAVERSAL_EXACT && numSlots > 0)
+    if (hostBuild && c.traversal != TRAVERSAL_EXACT && numSlots > 0)
         wideBuilder = std::thread([&] { wideBuilt = buildWideBvh(m->tris, numSlots, 0, wideHost); });
     // triangles: upload the caller's 64-byte records once, re-tile on the device, drop the staging copy
     float* staging = (float*)arenaAlloc((size_t)(numSlots ? numSlots : 1) * sizeof(triangle));
@@ -386,39 +496,68 @@ extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb,
 
     pt.mark("init: materials+textures");
 
-    // the wide tree: nodes and triangle order from the host build, leaf triangles re-tiled on the device
+    // the wide tree: built on the device from the staged triangles (or by the host builder), leaf triangles re-tiled on the device
     c.wide = WideView{};
+    c.wideStats = WideBvhStats();
     if (wideBuilder.joinable()) wideBuilder.join();
-    pt.mark("init: wide tree (host build, overlapped)");
-    c.wideStats = wideHost.stats;
-    if (wideBuilt && wideHost.stats.maxDepth <= 24 && sc.numPrimitivesPerLeaf > 0 && firstLeaf > 0) {
-        const size_t nn = wideHost.nodes.size(), nt = wideHost.triOrig.size();
-        uint4* dNodes = (uint4*)arenaAlloc(nn * sizeof(WideNode));
-        unsigned int* dOrig = devAlloc<unsigned int>(nt);
-        float4* dTriA = devAlloc<float4>(2 * nt);
-        float2* dTriB = devAlloc<float2>(nt);
-        unsigned int* dBad = devAlloc<unsigned int>(1);
-        CRT_CHECK(cudaMemcpy(dNodes, wideHost.nodes.data(), nn * sizeof(WideNode), cudaMemcpyHostToDevice));
-        CRT_CHECK(cudaMemcpy(dOrig, wideHost.triOrig.data(), nt * sizeof(unsigned int), cudaMemcpyHostToDevice));
-        CRT_CHECK(cudaMemset(dBad, 0, sizeof(unsigned int)));
-        wideTrianglesKernel<<<(unsigned int)((nt + 255) / 256), 256>>>(staging, dOrig, (unsigned int)nt, dTriA, dTriB);
-        checkRefTreeKernel<<<(unsigned int)((m->numBvhNodes + 255) / 256), 256>>>(nodeStaging, (unsigned int)m->numBvhNodes, dBad);
-        CRT_CHECK(cudaGetLastError());
-        unsigned int bad = 0;
-        CRT_CHECK(cudaMemcpy(&bad, dBad, sizeof(bad), cudaMemcpyDeviceToHost));
-        if (bad == 0) { // (else: the caller's boxes do not nest, the certificate's premise fails: exact traversal only)
-            c.wide.nodes = dNodes;
-            c.wide.triA = dTriA;
-            c.wide.triB = dTriB;
-            c.wide.rangeX = WIDE_ORIGIN_RANGE * wideHost.range[0];
-            c.wide.rangeY = WIDE_ORIGIN_RANGE * wideHost.range[1];
-            c.wide.rangeZ = WIDE_ORIGIN_RANGE * wideHost.range[2];
-            c.wide.stackDepth = (unsigned int)wideHost.stats.maxDepth;
+    if (c.traversal != TRAVERSAL_EXACT && numSlots > 0 && sc.numPrimitivesPerLeaf > 0 && firstLeaf > 0) {
+        uint4* dNodes = nullptr;
+        unsigned int* dOrig = nullptr;
+        size_t nt = 0;
+        float range[3] = {0, 0, 0};
+        bool ok = false;
+        if (hostBuild) {
+            if (wideBuilt) {
+                const size_t nn = wideHost.nodes.size();
+                nt = wideHost.triOrig.size();
+                dNodes = (uint4*)arenaAlloc(nn * sizeof(WideNode));
+                dOrig = devAlloc<unsigned int>(nt);
+                CRT_CHECK(cudaMemcpy(dNodes, wideHost.nodes.data(), nn * sizeof(WideNode), cudaMemcpyHostToDevice));
+                CRT_CHECK(cudaMemcpy(dOrig, wideHost.triOrig.data(), nt * sizeof(unsigned int), cudaMemcpyHostToDevice));
+                c.wideStats = wideHost.stats;
+                for (int a = 0; a < 3; a++) range[a] = wideHost.range[a];
+                ok = true;
+            }
+        } else {
+            DeviceWideTree t;
+            ok = buildWideOnDevice(staging, numSlots, t);
+            dNodes = (uint4*)t.nodes;
+            dOrig = t.triOrig;
+            nt = t.numTris;
+            c.wideStats.numNodes = t.numNodes;
+            c.wideStats.numTris = t.numTris;
+            c.wideStats.numBinaryNodes = t.numBinary;
+            c.wideStats.maxDepth = t.depth;
+            c.wideStats.msTotal = t.ms;
+            c.wideStats.threads = 0; // built on the device
+            for (int a = 0; a < 3; a++) range[a] = t.range[a];
         }
-        if (pt.on)
-            std::fprintf(stderr, "[crt timing] wide tree: %u nodes, %u triangles, depth %d, build %.2f ms (binary %.2f, collapse %.2f) on %d threads, ref tree nests: %s\n",
-                         wideHost.stats.numNodes, wideHost.stats.numTris, wideHost.stats.maxDepth, wideHost.stats.msTotal, wideHost.stats.msBinary,
-                         wideHost.stats.msCollapse, wideHost.stats.threads, bad ? "NO" : "yes");
+        pt.mark("init: wide tree build");
+        if (ok && c.wideStats.maxDepth <= 24) {
+            float4* dTriA = devAlloc<float4>(2 * nt);
+            float2* dTriB = devAlloc<float2>(nt);
+            unsigned int* dBad = devAlloc<unsigned int>(1);
+            CRT_CHECK(cudaMemset(dBad, 0, sizeof(unsigned int)));
+            wideTrianglesKernel<<<(unsigned int)((nt + 255) / 256), 256>>>(staging, dOrig, (unsigned int)nt, dTriA, dTriB);
+            checkRefTreeKernel<<<(unsigned int)((m->numBvhNodes + 255) / 256), 256>>>(nodeStaging, (unsigned int)m->numBvhNodes, dBad);
+            CRT_CHECK(cudaGetLastError());
+            unsigned int bad = 0;
+            CRT_CHECK(cudaMemcpy(&bad, dBad, sizeof(bad), cudaMemcpyDeviceToHost));
+            if (bad == 0) { // (else: the caller's boxes do not nest, the certificate's premise fails: exact traversal only)
+                c.wide.nodes = dNodes;
+                c.wide.triA = dTriA;
+                c.wide.triB = dTriB;
+                c.wide.rangeX = WIDE_ORIGIN_RANGE * range[0];
+                c.wide.rangeY = WIDE_ORIGIN_RANGE * range[1];
+                c.wide.rangeZ = WIDE_ORIGIN_RANGE * range[2];
+                c.wide.stackDepth = (unsigned int)c.wideStats.maxDepth;
+                c.wideNodesDev = dNodes;
+                c.wideTriOrigDev = dOrig;
+            }
+            if (pt.on)
+                std::fprintf(stderr, "[crt timing] wide tree: %u nodes, %u triangles, depth %d, %s build %.2f ms, ref tree nests: %s\n", c.wideStats.numNodes,
+                             c.wideStats.numTris, c.wideStats.maxDepth, hostBuild ? "host" : "device", c.wideStats.msTotal, bad ? "NO" : "yes");
+        }
     }
     pt.mark("init: wide tree upload");
     // light: RenderContext default members, kernels.cu:93-94
@@ -883,6 +1022,17 @@ extern "C" void getRendererWideInfo(renderer_wide_info* out) {
     out->sahCost = (float)c.wideStats.sahCost;
     out->lastBatchRedo = c.lastBatchRedo;
     out->lastFrameRedo = c.lastFrameRedo;
+}
+
+// Test hook: copies the wide tree in use to the host (96-byte node records, csrc/wide_bvh.h; caller's slot index per leaf
+// triangle). Returns the number of nodes (0 = no wide tree); copies at most the given capacities.
+extern "C" unsigned int getRendererWideTree(void* nodes, unsigned int nodeCapacity, unsigned int* triOrig, unsigned int triCapacity) {
+    const RendererContext& c = g_ctx;
+    if (!c.initialised || !c.wideNodesDev) return 0;
+    const unsigned int nn = std::min(nodeCapacity, c.wideStats.numNodes), nt = std::min(triCapacity, c.wideStats.numTris);
+    if (nodes && nn) CRT_CHECK(cudaMemcpy(nodes, c.wideNodesDev, (size_t)nn * sizeof(WideNode), cudaMemcpyDeviceToHost));
+    if (triOrig && nt) CRT_CHECK(cudaMemcpy(triOrig, c.wideTriOrigDev, (size_t)nt * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+    return c.wideStats.numNodes;
 }
 
 extern "C" void getRendererChaserCounts(unsigned long long* raysExtend, unsigned long long* raysShadow, unsigned long long* nodeVisits,

@@ -45,6 +45,8 @@ struct RendererContext {
     unsigned int* batchRedo = nullptr; // ray indices the wide walk could not certify (intersectBatchDevice)
     size_t batchRedoCap = 0;
     WideBvhStats wideStats;
+    const void* wideNodesDev = nullptr;        // (kept for getRendererWideTree: tests download and check the tree)
+    const unsigned int* wideTriOrigDev = nullptr;
     int traversal = 0;                 // TRAVERSAL_* in effect for this scene
 
     // sphere scene

@@ -182,6 +182,9 @@ typedef struct renderer_wide_info {
     unsigned long long lastFrameRedo;  // rays of the last runRenderer answered by the exact kernel
 } renderer_wide_info;
 void getRendererWideInfo(renderer_wide_info* out);
+// Test hook: copies the wide tree in use to the host (96-byte node records of csrc/wide_bvh.h; the caller's slot index of
+// every leaf triangle). Returns the number of nodes (0 = no wide tree in use).
+unsigned int getRendererWideTree(void* nodes, unsigned int nodeCapacity, unsigned int* triOrig, unsigned int triCapacity);
 
 #ifdef __cplusplus
 }

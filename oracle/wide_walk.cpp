@@ -195,6 +195,8 @@ int wideWalkBatch(const kernel_scene* sc, const float* rayO, const float* rayD, 
     return 0;
 }
 
+static int checkTree(const kernel_scene* sc, const WideBvhHost& w);
+
 // Structural check of a build: every real triangle appears exactly once; every child box (decoded in double) contains the
 // padded boxes of everything below it. Returns 0 when sound, else a negative code.
 int wideCheckStructure(const kernel_scene* sc, int threads, double* buildMs, unsigned long long* numNodes) {
@@ -202,6 +204,43 @@ int wideCheckStructure(const kernel_scene* sc, int threads, double* buildMs, uns
     if (!buildWideBvh(sc->m->tris, sc->m->numTris, threads, w)) return -1;
     if (buildMs) *buildMs = w.stats.msTotal;
     if (numNodes) *numNodes = w.stats.numNodes;
+    return checkTree(sc, w);
+}
+
+// The same check for a tree built elsewhere (the device build, downloaded through getRendererWideTree). The padding is the
+// builder's rule: 2^-18 of the largest |coordinate| of the triangles per axis. `depthOut` receives the tree's depth.
+int wideCheckGiven(const kernel_scene* sc, const void* nodes, unsigned int numNodes, const unsigned int* triOrig, unsigned int numTris, int* depthOut) {
+    WideBvhHost w;
+    w.nodes.assign((const WideNode*)nodes, (const WideNode*)nodes + numNodes);
+    w.triOrig.assign(triOrig, triOrig + numTris);
+    float range[3] = {1e-30f, 1e-30f, 1e-30f};
+    const mesh* m = sc->m;
+    for (uint32_t i = 0; i < m->numTris; i++) {
+        if (std::isinf(m->tris[i].v[0].e[0])) continue;
+        for (int v = 0; v < 3; v++)
+            for (int a = 0; a < 3; a++) range[a] = std::fmax(range[a], std::fabs(m->tris[i].v[v].e[a]));
+    }
+    for (int a = 0; a < 3; a++) { w.range[a] = range[a]; w.pad[a] = range[a] * WIDE_PAD_SCALE; }
+    if (depthOut) { // depth by a walk from the root
+        std::vector<int> depth(numNodes, 0);
+        int deepest = 0;
+        if (numNodes) depth[0] = 1;
+        for (unsigned int k = 0; k < numNodes; k++) {
+            const WideNode& n = w.nodes[k];
+            if (depth[k] > deepest) deepest = depth[k];
+            for (int s = 0; s < 8; s++)
+                if (n.imask & (1u << s)) {
+                    const uint32_t c = n.childBase + (uint32_t)__builtin_popcount(n.imask & ((1u << s) - 1u));
+                    if (c < numNodes) depth[c] = depth[k] + 1;
+                }
+        }
+        *depthOut = deepest;
+    }
+    return checkTree(sc, w);
+}
+}
+
+static int checkTree(const kernel_scene* sc, const WideBvhHost& w) {
     const mesh* m = sc->m;
     std::vector<unsigned char> seen(m->numTris, 0);
     for (uint32_t id : w.triOrig) {
@@ -245,5 +284,4 @@ int wideCheckStructure(const kernel_scene* sc, int threads, double* buildMs, uns
         for (int a = 0; a < 3; a++) { lo[3 * k + a] = blo[a]; hi[3 * k + a] = bhi[a]; }
     }
     return 0;
-}
 }

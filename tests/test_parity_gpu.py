@@ -500,3 +500,35 @@ def test_config5_rays_on_the_benchmark_bvh_side_by_side(crt, oracle):
     assert h.mean() > 0.9
     assert (np.abs(hit[h, 0] - rhit[h, 0]) / np.abs(rhit[h, 0])).max() <= 1e-5
     assert np.array_equal(hit.view(np.uint32), rhit.view(np.uint32)), "t/u/v are expected to be bit-exact as well"
+
+
+def test_device_built_wide_tree_is_sound(crt, oracle, medium_scene, small_scene):
+    """The tree the device build (csrc/wide_build.cuh) produces, downloaded and checked on the host: every real triangle exactly
+    once, every quantised child box contains (padded) everything below it, reported depth = real depth. Also for a few tiny
+    scenes (1, 2, 7 triangles; coincident centroids)."""
+    import ctypes as C
+    oracle.lib()
+    W = C.CDLL(os.path.join(os.path.dirname(G), "..", "oracle", "build", "libwide_walk.so"))
+    W.wideCheckGiven.argtypes = [C.POINTER(crt.KernelScene), C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.POINTER(C.c_int)]
+    rng = np.random.default_rng(11)
+    tiny = []
+    for ntri in (1, 2, 7):
+        t = np.zeros((ntri, 16), np.float32)
+        t[:, :9] = rng.random((ntri, 9), dtype=np.float32) * 10
+        tiny.append(crt.Scene.from_triangles(t, 5, 16))
+    same = np.zeros((9, 16), np.float32)
+    same[:, :9] = np.array([0, 0, 0, 10, 0, 0, 0, 10, 0], np.float32)  # nine coincident triangles: no plane separates their centroids
+    tiny.append(crt.Scene.from_triangles(same, 5, 16))
+    for scene in [small_scene, medium_scene] + tiny:
+        with crt.Frame(scene, 8, 8, 1):
+            info = crt.wide_info()
+            assert info.active == 1 and info.buildThreads == 0, "the device build is the default"
+            nodes = np.zeros((info.numNodes, 96), np.uint8)
+            orig = np.zeros(info.numTriangles, np.uint32)
+            assert crt.device_lib().getRendererWideTree(nodes.ctypes.data, info.numNodes, orig.ctypes.data, info.numTriangles) == info.numNodes
+        assert info.numTriangles == scene.num_real_triangles
+        depth = C.c_int()
+        assert W.wideCheckGiven(C.byref(scene.ks), nodes.ctypes.data, info.numNodes, orig.ctypes.data, info.numTriangles, C.byref(depth)) == 0
+        assert depth.value == info.depth
+    for s in tiny:
+        s.close()
