@@ -330,6 +330,8 @@ static bool buildWideOnDevice(const float* dTris, unsigned int numSlots, DeviceW
     b.binCnt = devAlloc<unsigned int>(b.binCapacity * 3 * GB_BINS);
     b.binLo = devAlloc<int>(b.binCapacity * 3 * GB_BINS * 3);
     b.binHi = devAlloc<int>(b.binCapacity * 3 * GB_BINS * 3);
+    b.dpCost = devAlloc<float>(7 * (2 * n + 2));
+    b.dpDec = devAlloc<unsigned char>(8 * (2 * n + 2));
     b.pending = devAlloc<unsigned int>(n + 1);
     b.depthOf = devAlloc<unsigned int>(n + 1);
     b.counters = devAlloc<unsigned int>(32);
@@ -365,6 +367,7 @@ static bool buildWideOnDevice(const float* dTris, unsigned int numSlots, DeviceW
     int cur = 0;
     unsigned int activeCount = h[2];
     const unsigned int primBlocks = (prims + 255) / 256;
+    std::vector<unsigned int> levelEnd(1, 1u); // binary nodes [levelEnd[L-1], levelEnd[L]) were created by the split of level L-1
     while (activeCount > 0 && out.levels < 256) {
         gbClearBinsKernel<<<std::min<unsigned int>((activeCount * 3u * GB_BINS + 255u) / 256u, 4096u), 256>>>(b, activeCount);
         gbBinKernel<<<primBlocks, 256>>>(b, cur);
@@ -372,12 +375,21 @@ static bool buildWideOnDevice(const float* dTris, unsigned int numSlots, DeviceW
         gbSplitKernel<<<(activeCount * 32u + 255u) / 256u, 256>>>(b, cur, activeCount);
         gbPartitionKernel<<<primBlocks, 256>>>(b, cur);
         cur ^= 1;
-        CRT_CHECK(cudaMemcpy(&activeCount, &b.counters[2 + cur], sizeof(unsigned int), cudaMemcpyDeviceToHost));
+        unsigned int hc[4];
+        CRT_CHECK(cudaMemcpy(hc, b.counters, sizeof(hc), cudaMemcpyDeviceToHost));
+        activeCount = hc[2 + cur];
+        levelEnd.push_back(hc[1]);
         out.levels++;
     }
     CRT_CHECK(cudaGetLastError());
     pt.mark("  wide build: binary levels");
-    // collapse, level by level
+    // collapse: cost tables bottom-up (deepest binary level first), then the wide nodes level by level
+    const int greedy = std::getenv("CRT_WIDE_GREEDY") ? 1 : 0; // (diagnostic: the greedy collapse the cost tables replaced)
+    const float triCost = std::getenv("CRT_WIDE_TRICOST") ? (float)std::atof(std::getenv("CRT_WIDE_TRICOST")) : GB_WIDE_TRI_COST; // (tuning knob)
+    for (size_t l = levelEnd.size(); l-- > 0;) {
+        const unsigned int s0 = l ? levelEnd[l - 1] : 0u, s1 = levelEnd[l];
+        if (s1 > s0) gbCollapseCostKernel<<<(s1 - s0 + 127) / 128, 128>>>(b, s0, s1, triCost, 0);
+    }
     const unsigned int one = 1u, zero = 0u;
     CRT_CHECK(cudaMemcpy(&b.counters[4], &one, 4, cudaMemcpyHostToDevice));
     CRT_CHECK(cudaMemcpy(&b.counters[5], &zero, 4, cudaMemcpyHostToDevice));
@@ -386,7 +398,7 @@ static bool buildWideOnDevice(const float* dTris, unsigned int numSlots, DeviceW
     CRT_CHECK(cudaMemcpy(b.depthOf, &one, 4, cudaMemcpyHostToDevice));
     unsigned int start = 0, end = 1;
     while (end > start) {
-        gbCollapseKernel<<<(end - start + 63) / 64, 64>>>(b, cur, start, end, make_float3(pad[0], pad[1], pad[2]), out.nodes, out.triOrig);
+        gbCollapseKernel<<<(end - start + 63) / 64, 64>>>(b, cur, start, end, make_float3(pad[0], pad[1], pad[2]), out.nodes, out.triOrig, greedy);
         start = end;
         CRT_CHECK(cudaMemcpy(&end, &b.counters[4], sizeof(unsigned int), cudaMemcpyDeviceToHost));
     }
@@ -550,7 +562,9 @@ extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb,
                 c.wide.rangeX = WIDE_ORIGIN_RANGE * range[0];
                 c.wide.rangeY = WIDE_ORIGIN_RANGE * range[1];
                 c.wide.rangeZ = WIDE_ORIGIN_RANGE * range[2];
-                c.wide.stackDepth = (unsigned int)c.wideStats.maxDepth;
+                // entries per thread: the tree's depth, rounded up to a multiple of 4 and at least 16 (see the carve-out note in crtRunMesh)
+                c.wide.stackDepth = std::max(16u, ((unsigned int)c.wideStats.maxDepth + 3u) & ~3u);
+                if (std::getenv("CRT_WIDE_STACK")) c.wide.stackDepth = std::max((unsigned int)c.wideStats.maxDepth, (unsigned int)std::atoi(std::getenv("CRT_WIDE_STACK"))); // (diagnostic)
                 c.wideNodesDev = dNodes;
                 c.wideTriOrigDev = dOrig;
             }
@@ -662,6 +676,22 @@ void crtRunMesh(RendererContext& c, int ns, bool resume) {
         int perSM = 0;
         CRT_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, wideTraceKernel<false, 0, true>, WIDE_TRACE_BLOCK, smem));
         c.wideTraceBlocks = c.numSMs * (perSM > 0 ? perSM : 1);
+        // Shared-memory carve-out: left to the driver. Measured on the benchmark frame (profiles/r02/carveout_sweep.txt): with the
+        // driver's own choice per kernel the frame takes 357 ms at 13, 14, 16 or 20 stack entries per thread but 380-390 ms at
+        // exactly 12 (6 KB per chaser block, 12 KB per trace block); stating one split for every kernel of the frame gives 363 ms at
+        // best (the shade kernel then loses L1), too small a split 390-410 ms (one trace block per SM does not fit), too large 380 ms.
+        // The stack is therefore sized to a multiple of 4 entries, at least 16 (initRenderer); CRT_WIDE_CARVEOUT=<percent> states a
+        // split for the trace kernels (tuning knob).
+        cudaFuncAttributes fa;
+        CRT_CHECK(cudaFuncGetAttributes(&fa, wideTraceKernel<false, 0, true>));
+        int pct = -1;
+        if (std::getenv("CRT_WIDE_CARVEOUT")) pct = std::min(std::max(std::atoi(std::getenv("CRT_WIDE_CARVEOUT")), -1), 100);
+        if (pct >= 0) {
+            auto carve = [&](auto kernel) { CRT_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct)); };
+            carve(wideTraceKernel<false, 0, true>); carve(wideTraceKernel<false, 1, true>); carve(wideTraceKernel<false, 0, false>); carve(wideTraceKernel<false, 1, false>);
+            carve(wideTraceKernel<true, 0, true>); carve(wideTraceKernel<true, 1, true>); carve(wideTraceKernel<true, 0, false>); carve(wideTraceKernel<true, 1, false>);
+        }
+        if (std::getenv("CRT_TIMING")) std::fprintf(stderr, "[crt timing] wide trace: %d blocks/SM, %zu B shared per block, carve-out %d %%\n", perSM, (size_t)fa.sharedSizeBytes + smem, pct);
     }
     const int kernelsPerIteration = useWideTree(c) ? 3 : 2;
     cudaStream_t stream = c.stream;

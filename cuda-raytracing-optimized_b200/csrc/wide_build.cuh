@@ -21,6 +21,9 @@
 #define GB_BINS 32
 #define GB_NODE_COST 1.0f
 #define GB_TRI_COST 1.0f
+#define GB_WIDE_NODE_COST 1.0f // collapse cost model (wide_bvh.cpp): one wide-node visit against one triangle test
+#define GB_WIDE_TRI_COST 0.3f
+#define GB_LEAF_BIT 0x80000000u
 
 struct GpuBuild {
     unsigned int n;                 // capacity: triangle slots
@@ -32,7 +35,7 @@ struct GpuBuild {
     unsigned int* nodeOf[2];        // binary node of a position
     // binary nodes (2n)
     float4* nLo;                    // box min, w = left child (0 = leaf)
-    float4* nHi;                    // box max, w = primitive count
+    float4* nHi;                    // box max, w = primitives below the node
     int* cLo;                       // centroid bounds, order-preserving ints, 3 per node
     int* cHi;
     unsigned int* nFirst;
@@ -46,6 +49,8 @@ struct GpuBuild {
     int* binHi;
     size_t binCapacity;             // active nodes the bin arrays hold
     // collapse
+    float* dpCost;                  // 7 per binary node: C(n, 1..7) (wide_bvh.cpp)
+    unsigned char* dpDec;           // 8 per binary node: the arg-mins
     unsigned int* pending;          // binary node of wide node w
     unsigned int* depthOf;
     // counters: [0] primitives [1] binary nodes [2],[3] active counts [4] wide nodes [5] leaf triangles [6] depth [8..13] root box ints [14..19] root centroid ints
@@ -251,8 +256,7 @@ __global__ void gbSplitKernel(GpuBuild b, int cur, unsigned int activeCount) {
         for (int k = 0; k < 3; k++) { L.lo[k] = R.lo[k] = nl[k]; L.hi[k] = R.hi[k] = nh[k]; }
     }
     const unsigned int left = atomicAdd(&b.counters[1], 2u);
-    b.nLo[node].w = __uint_as_float(left);
-    b.nHi[node].w = __uint_as_float(0u);
+    b.nLo[node].w = __uint_as_float(left); // (nHi.w keeps the number of primitives below the node)
     b.nSplit[node] = make_uint2(axis, plane);
     for (int s = 0; s < 2; s++) {
         const GbBox& cb = s ? R : L;
@@ -318,45 +322,119 @@ __global__ void gbPartitionKernel(GpuBuild b, int cur) {
 // after the last level the nodes that were active but not split are leaves: nothing to do (nLo.w == 0 marks a leaf)
 
 // ---- collapse to 8-wide nodes -----------------------------------------------------------------------------------------------
+// The dynamic programme of wide_bvh.cpp (Ylitie, Karras, Laine 2017, section 4.1) for the binary nodes [start, end) of one
+// level, deepest level first: C(n, i) = least cost of the subtree of n represented by at most i wide-tree roots.
+__global__ void gbCollapseCostKernel(GpuBuild b, unsigned int start, unsigned int end, float triCost, int greedy) {
+    const unsigned int node = start + blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= end) return;
+    const float4 lo = b.nLo[node], hi = b.nHi[node];
+    const float l3[3] = {lo.x, lo.y, lo.z}, h3[3] = {hi.x, hi.y, hi.z};
+    const float area = gbHalfArea(l3, h3);
+    const unsigned int span = __float_as_uint(hi.w), left = __float_as_uint(lo.w);
+    const float inf = __int_as_float(0x7F800000);
+    const float leaf = (span <= WIDE_MAX_LEAF_TRIS && !(greedy && left != 0u)) ? area * (float)span * triCost : inf;
+    float* C = b.dpCost + 7ull * node;
+    unsigned char* D = b.dpDec + 8ull * node;
+    if (left == 0u) {
+        for (int i = 0; i < 7; i++) { C[i] = leaf; D[i] = 0; }
+        D[7] = 0;
+        return;
+    }
+    float L[7], R[7];
+    for (int i = 0; i < 7; i++) { L[i] = b.dpCost[7ull * left + i]; R[i] = b.dpCost[7ull * (left + 1u) + i]; }
+    float dist[9];
+    unsigned char kbest[9];
+#pragma unroll
+    for (int j = 2; j <= 8; j++) {
+        dist[j] = inf;
+        kbest[j] = 1;
+#pragma unroll
+        for (int k = 1; k <= 7; k++) {
+            if (k < j - 7 || k > j - 1) continue;
+            const float v = L[k - 1] + R[j - k - 1];
+            if (v < dist[j]) { dist[j] = v; kbest[j] = (unsigned char)k; }
+        }
+    }
+    const float inner = dist[8] + area * GB_WIDE_NODE_COST;
+    D[7] = kbest[8];
+    float prev;
+    if (leaf <= inner) { prev = leaf; D[0] = 0; }
+    else { prev = inner; D[0] = 1; }
+    C[0] = prev;
+#pragma unroll
+    for (int i = 2; i <= 7; i++) {
+        if (dist[i] < prev) { prev = dist[i]; D[i - 1] = kbest[i]; }
+        else D[i - 1] = 0;
+        C[i - 1] = prev;
+    }
+}
+
 __device__ __forceinline__ unsigned char gbQuantByte(int q) { return (unsigned char)(0x80 | (q < 0 ? 0 : (q > 127 ? 127 : q))); }
 
 // One thread per wide node of the level [start, end): the statements of wide_bvh.cpp's collapse (children, octant slots, grid,
 // outward quantisation with the even-slot excess), children and leaf triangles allocated with one atomic each.
 __global__ void gbCollapseKernel(GpuBuild b, int finalOrder, unsigned int start, unsigned int end, float3 pad, WideNode* __restrict__ out,
-                                 unsigned int* __restrict__ triOrig) {
+                                 unsigned int* __restrict__ triOrig, int greedy) {
     const unsigned int w = start + blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= end) return;
     const unsigned int node2 = b.pending[w];
     const unsigned int depth = b.depthOf[w];
     atomicMax(&b.counters[6], depth);
     const float padv[3] = {pad.x, pad.y, pad.z};
-    unsigned int child[8];
+    unsigned int child[8]; // binary nodes, | GB_LEAF_BIT = emitted as one leaf (possibly an inner binary node with <= 3 triangles)
     int nc = 0;
     {
         const unsigned int left = __float_as_uint(b.nLo[node2].w);
-        if (left == 0u) child[nc++] = node2; // the whole tree is one leaf
-        else { child[nc++] = left; child[nc++] = left + 1u; }
-    }
-    while (nc < 8) { // open the inner child with the largest surface area
-        int pick = -1;
-        float bestArea = -1.0f;
-        for (int k = 0; k < nc; k++) {
-            const float4 lo = b.nLo[child[k]], hi = b.nHi[child[k]];
-            if (__float_as_uint(lo.w) != 0u) {
-                const float l3[3] = {lo.x, lo.y, lo.z}, h3[3] = {hi.x, hi.y, hi.z};
-                const float ar = gbHalfArea(l3, h3);
-                if (ar > bestArea) { bestArea = ar; pick = k; }
+        if (left == 0u) {
+            child[nc++] = node2 | GB_LEAF_BIT; // the whole tree is one leaf
+        } else if (greedy) { // (diagnostic: open the inner child with the largest surface area until there are 8)
+            child[nc++] = left; child[nc++] = left + 1u;
+            while (nc < 8) {
+                int pick = -1;
+                float bestArea = -1.0f;
+                for (int k = 0; k < nc; k++) {
+                    const float4 lo = b.nLo[child[k]], hi = b.nHi[child[k]];
+                    if (__float_as_uint(lo.w) != 0u) {
+                        const float l3[3] = {lo.x, lo.y, lo.z}, h3[3] = {hi.x, hi.y, hi.z};
+                        const float ar = gbHalfArea(l3, h3);
+                        if (ar > bestArea) { bestArea = ar; pick = k; }
+                    }
+                }
+                if (pick < 0) break;
+                const unsigned int l = __float_as_uint(b.nLo[child[pick]].w);
+                child[pick] = l;
+                child[nc++] = l + 1u;
+            }
+            for (int k = 0; k < nc; k++)
+                if (__float_as_uint(b.nLo[child[k]].w) == 0u) child[k] |= GB_LEAF_BIT;
+        } else { // follow the arg-mins of D(node, 8)
+            unsigned int stackNode[16];
+            int stackBudget[16];
+            int sp = 0;
+            const int k8 = b.dpDec[8ull * node2 + 7];
+            stackNode[sp] = left + 1u; stackBudget[sp++] = 8 - k8;
+            stackNode[sp] = left; stackBudget[sp++] = k8;
+            while (sp > 0) {
+                sp--;
+                const unsigned int nd = stackNode[sp];
+                int budget = stackBudget[sp];
+                const unsigned char* D = b.dpDec + 8ull * nd;
+                while (budget > 1 && D[budget - 1] == 0) budget--;
+                if (budget == 1) {
+                    child[nc++] = D[0] ? nd : (nd | GB_LEAF_BIT);
+                } else {
+                    const int k = D[budget - 1];
+                    const unsigned int cl = __float_as_uint(b.nLo[nd].w);
+                    stackNode[sp] = cl + 1u; stackBudget[sp++] = budget - k;
+                    stackNode[sp] = cl; stackBudget[sp++] = k;
+                }
             }
         }
-        if (pick < 0) break;
-        const unsigned int l = __float_as_uint(b.nLo[child[pick]].w);
-        child[pick] = l;
-        child[nc++] = l + 1u;
     }
     float nbLo[3] = {__int_as_float(0x7F800000), __int_as_float(0x7F800000), __int_as_float(0x7F800000)};
     float nbHi[3] = {-nbLo[0], -nbLo[1], -nbLo[2]};
     for (int k = 0; k < nc; k++) {
-        const float4 lo = b.nLo[child[k]], hi = b.nHi[child[k]];
+        const float4 lo = b.nLo[child[k] & ~GB_LEAF_BIT], hi = b.nHi[child[k] & ~GB_LEAF_BIT];
         nbLo[0] = fminf(nbLo[0], lo.x); nbLo[1] = fminf(nbLo[1], lo.y); nbLo[2] = fminf(nbLo[2], lo.z);
         nbHi[0] = fmaxf(nbHi[0], hi.x); nbHi[1] = fmaxf(nbHi[1], hi.y); nbHi[2] = fmaxf(nbHi[2], hi.z);
     }
@@ -369,7 +447,7 @@ __global__ void gbCollapseKernel(GpuBuild b, int finalOrder, unsigned int start,
         float bv = -__int_as_float(0x7F800000);
         for (int k = 0; k < nc; k++) {
             if (placed & (1u << k)) continue;
-            const float4 lo = b.nLo[child[k]], hi = b.nHi[child[k]];
+            const float4 lo = b.nLo[child[k] & ~GB_LEAF_BIT], hi = b.nHi[child[k] & ~GB_LEAF_BIT];
             const float d0 = 0.5f * (lo.x + hi.x) - 0.5f * (nbLo[0] + nbHi[0]);
             const float d1 = 0.5f * (lo.y + hi.y) - 0.5f * (nbLo[1] + nbHi[1]);
             const float d2 = 0.5f * (lo.z + hi.z) - 0.5f * (nbLo[2] + nbHi[2]);
@@ -408,9 +486,9 @@ __global__ void gbCollapseKernel(GpuBuild b, int finalOrder, unsigned int start,
     for (int s = 7; s >= 0; s--) { // odd slots before the even slot that reads them as excess mantissa
         for (int a = 0; a < 3; a++) { wn.qlo[a][s] = gbQuantByte(127); wn.qhi[a][s] = gbQuantByte(0); }
         if (slotChild[s] == 0xFFFFFFFFu) continue;
-        const float4 clo = b.nLo[slotChild[s]], chi = b.nHi[slotChild[s]];
+        const float4 clo = b.nLo[slotChild[s] & ~GB_LEAF_BIT], chi = b.nHi[slotChild[s] & ~GB_LEAF_BIT];
         const float cl[3] = {clo.x, clo.y, clo.z}, ch[3] = {chi.x, chi.y, chi.z};
-        if (__float_as_uint(clo.w) != 0u) innerCount++;
+        if (!(slotChild[s] & GB_LEAF_BIT)) innerCount++;
         else triCount += __float_as_uint(chi.w);
         for (int a = 0; a < 3; a++) {
             const double lo = (double)cl[a] - (double)padv[a], hi = (double)ch[a] + (double)padv[a];
@@ -432,8 +510,8 @@ __global__ void gbCollapseKernel(GpuBuild b, int finalOrder, unsigned int start,
     unsigned int triOffset = 0u, inner = 0u;
     for (int s = 0; s < 8; s++) {
         if (slotChild[s] == 0xFFFFFFFFu) continue;
-        const unsigned int c2 = slotChild[s];
-        if (__float_as_uint(b.nLo[c2].w) == 0u) {
+        const unsigned int c2 = slotChild[s] & ~GB_LEAF_BIT;
+        if (slotChild[s] & GB_LEAF_BIT) {
             const unsigned int cnt = __float_as_uint(b.nHi[c2].w), first = b.nFirst[c2];
             wn.meta[s] = (unsigned char)((cnt << 5) | triOffset);
             for (unsigned int t = 0; t < cnt; t++) triOrig[triBase + triOffset + t] = b.primSlot[b.order[finalOrder][first + t]];

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--budget", type=int, default=0)
     ap.add_argument("--min-active", type=int, default=0)
     ap.add_argument("--sah", action="store_true", help="BVH split by the surface-area heuristic (same layout, same hits)")
+    ap.add_argument("--count", action="store_true", help="one extra frame with the traversal counters on: node visits / triangle tests per ray")
     ap.add_argument("--profile", action="store_true", help="per-kernel-family CUDA events (serialised iterations)")
     args = ap.parse_args()
     crt.set_options(slots_per_pixel=args.slots, trace_budget=args.budget, trace_min_active=args.min_active)
@@ -36,7 +37,17 @@ def main():
             fr.run(args.ns, copy=False)
             st = crt.stats()
             rays = st.raysExtend + st.raysShadow
-            print(json.dumps(dict(ms=st.msTotal, mrays=rays / (st.msTotal * 1e3), rays=rays, iterations=st.iterations, launches=st.kernelLaunches,
+            extra = {}
+            if args.count and _ == args.steps - 1:
+                L = crt.device_lib()
+                L.setRendererCounting(1)
+                fr.run(args.ns, copy=False)
+                L.setRendererCounting(0)
+                nv, tt = crt.C.c_ulonglong(), crt.C.c_ulonglong()
+                L.getRendererTraversalCounts(crt.C.byref(nv), crt.C.byref(tt))
+                w = crt.wide_info()
+                extra = dict(visits_per_ray=nv.value / rays, tests_per_ray=tt.value / rays, wide_nodes=w.numNodes, depth=w.depth, redo=int(w.lastFrameRedo), build_ms=w.buildMs)
+            print(json.dumps(dict(extra, ms=st.msTotal, mrays=rays / (st.msTotal * 1e3), rays=rays, iterations=st.iterations, launches=st.kernelLaunches,
                                   resumes=st.resumes, deferred=st.deferred, ms_trace=st.msTrace, ms_shade=st.msShade)))
 
 
