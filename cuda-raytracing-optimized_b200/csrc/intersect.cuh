@@ -81,7 +81,7 @@ __device__ __forceinline__ float triHit(const f3& v0, const f3& edge1, const f3&
     const f3 h = cross(r.d, edge2);
     const float a = dot(edge1, h);
     if (a > -EPS && a < EPS) return FLT_MAX;
-    const float f = __fdiv_rn(1.0f, a);
+    const float f = __frcp_rn(a); // 1.0 / a, correctly rounded: the same float as the reference's division, fewer instructions
     const f3 s = subPinned(r.o, v0);
     const float u = __fmul_rn(f, dot(s, h));
     if (u < 0.0f || u > 1.0f) return FLT_MAX;

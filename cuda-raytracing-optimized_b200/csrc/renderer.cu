@@ -545,7 +545,7 @@ extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb,
             for (int a = 0; a < 3; a++) range[a] = t.range[a];
         }
         pt.mark("init: wide tree build");
-        if (ok && c.wideStats.maxDepth <= 24) {
+        if (ok && c.wideStats.maxDepth <= 27) {
             float4* dTriA = devAlloc<float4>(2 * nt);
             float2* dTriB = devAlloc<float2>(nt);
             unsigned int* dBad = devAlloc<unsigned int>(1);
@@ -563,8 +563,9 @@ extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb,
                 c.wide.rangeY = WIDE_ORIGIN_RANGE * range[1];
                 c.wide.rangeZ = WIDE_ORIGIN_RANGE * range[2];
                 // entries per thread: the tree's depth, rounded up to a multiple of 4 and at least 16 (see the carve-out note in crtRunMesh)
-                c.wide.stackDepth = std::max(16u, ((unsigned int)c.wideStats.maxDepth + 3u) & ~3u);
-                if (std::getenv("CRT_WIDE_STACK")) c.wide.stackDepth = std::max((unsigned int)c.wideStats.maxDepth, (unsigned int)std::atoi(std::getenv("CRT_WIDE_STACK"))); // (diagnostic)
+                // (+1: the last entry parks the current node's leaf meta bytes, wide_traverse.cuh)
+                c.wide.stackDepth = std::max(16u, ((unsigned int)c.wideStats.maxDepth + 1u + 3u) & ~3u);
+                if (std::getenv("CRT_WIDE_STACK")) c.wide.stackDepth = std::max((unsigned int)c.wideStats.maxDepth + 1u, (unsigned int)std::atoi(std::getenv("CRT_WIDE_STACK"))); // (diagnostic)
                 c.wideNodesDev = dNodes;
                 c.wideTriOrigDev = dOrig;
             }

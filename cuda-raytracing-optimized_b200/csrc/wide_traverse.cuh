@@ -43,7 +43,7 @@ struct WideRay {
 
 struct WideTrav {
     unsigned int ngx, ngy;  // node group: child base | hits in priority order (bits 24..31) + imask (bits 0..7)
-    unsigned int tgx, tgy;  // triangle group: triangle base | mask of triangles still to test (24 bits)
+    unsigned int tgx, tgy;  // triangle group: the node's triangle base | mask of the hit leaf slots still to test (8 bits)
     int sp;                 // entries on the stack; -1 = traversal finished
     float closest;
 };
@@ -94,7 +94,7 @@ __device__ __forceinline__ float2 slabPairFma(unsigned int pair, float a, float 
 // hands it to the exact kernel.
 __device__ __forceinline__ bool wideSetup(const WideView& w, WideRay& r, const f3& o, const f3& d, bool anyHit, f3& inv) {
     r.ox = o.x; r.oy = o.y; r.oz = o.z;
-    inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    inv = mk3(__frcp_rn(d.x), __frcp_rn(d.y), __frcp_rn(d.z)); // = 1.0f / d, correctly rounded (the reference's invD, intersections.h:27)
     const float big = 1.0f / 1e-20f; // |direction| is clamped to >= 1e-20
     r.ix = fabsf(d.x) < 1e-20f ? copysignf(big, d.x) : inv.x;
     r.iy = fabsf(d.y) < 1e-20f ? copysignf(big, d.y) : inv.y;
@@ -189,55 +189,60 @@ __device__ __forceinline__ void wideNodeStep(const WideView& w, const WideRay& r
     if (r.oct & 4u) prio = ((prio & 0x0Fu) << 4) | ((prio >> 4) & 0x0Fu);
     s.ngx = h1.x;
     s.ngy = (prio << 24) | imask;
-    // leaf hits -> mask of the triangles to test (meta = count << 5 | offset)
-    unsigned int leafHits = hits & ~imask, tris = 0u;
-    while (leafHits) {
-        const unsigned int sl = (unsigned int)__ffs((int)leafHits) - 1u;
-        leafHits &= leafHits - 1u;
-        const unsigned int meta = ((sl < 4u ? h1.z : h1.w) >> (8u * (sl & 3u))) & 0xFFu;
-        tris |= ((1u << (meta >> 5)) - 1u) << (meta & 31u);
-    }
+    // leaf hits: the slots go to the triangle group; their triangle ranges (meta = count << 5 | offset) are decoded in the
+    // triangle phase, from the node's meta bytes parked in the thread's LAST stack entry (which the tree never reaches:
+    // stackDepth > tree depth). Decoding here would make the lanes that continue with nodes wait for it.
+    const unsigned int leafHits = hits & ~imask;
     s.tgx = h1.y;
-    s.tgy = tris;
-    if (tris == 0u && s.ngy <= 0x00FFFFFFu) widePop(s, stack, stride);
+    s.tgy = leafHits;
+    if (leafHits != 0u) stack[(w.stackDepth - 1u) * stride] = make_uint2(h1.z, h1.w);
+    else if (s.ngy <= 0x00FFFFFFu) widePop(s, stack, stride);
 }
 
-// The triangles of the lane's triangle group (kernels.cu:200-216 with the near-tie margin). c.rec = {u, v, winner slot, user}.
+// The triangles of the lane's triangle group: every hit leaf slot of the last node, 1..3 triangles each (kernels.cu:200-216 with
+// the near-tie margin). c.rec = {u, v, winner slot, user}.
 __device__ __forceinline__ void wideTriPhase(const WideView& w, WideRay& r, RayCold& c, float tMin, WideTrav& s, const uint2* stack,
                                              unsigned int stride, unsigned int& triTests) {
     RayPrep rp;
     rp.o = mk3(r.ox, r.oy, r.oz);
     rp.d = xyz(c.dir);
     const bool anyHit = (r.oct & WIDE_FLAG_ANYHIT) != 0u;
-    while (s.tgy) {
-        const unsigned int k = s.tgx + (unsigned int)__ffs((int)s.tgy) - 1u;
-        s.tgy &= s.tgy - 1u;
-        float4 t0, t1;
-        ldg256(w.triA + 2ull * k, t0, t1);
-        const float2 t2 = __ldg(w.triB + k);
-        triTests++;
-        const float limit = anyHit ? s.closest : s.closest * WIDE_TIE_MARGIN;
-        float u, v;
-        const float hitT = triHit(mk3(t0.x, t0.y, t0.z), mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), rp, tMin, limit, u, v);
-        if (hitT < limit) {
-            if (anyHit) { // kernels.cu:207: the first hit ends an any-hit walk
-                s.closest = hitT;
-                c.rec.z = t2.y;
-                s.tgy = 0u;
-                s.sp = -1;
-                return;
+    const uint2 meta = stack[(w.stackDepth - 1u) * stride];
+    unsigned int slots = s.tgy;
+    s.tgy = 0u;
+    while (slots) {
+        const unsigned int sl = (unsigned int)__ffs((int)slots) - 1u;
+        slots &= slots - 1u;
+        const unsigned int m = ((sl < 4u ? meta.x : meta.y) >> (8u * (sl & 3u))) & 0xFFu;
+        unsigned int k = s.tgx + (m & 31u), left = m >> 5;
+        do {
+            float4 t0, t1;
+            ldg256(w.triA + 2ull * k, t0, t1);
+            const float2 t2 = __ldg(w.triB + k);
+            triTests++;
+            const float limit = anyHit ? s.closest : s.closest * WIDE_TIE_MARGIN;
+            float u, v;
+            const float hitT = triHit(mk3(t0.x, t0.y, t0.z), mk3(t0.w, t1.x, t1.y), mk3(t1.z, t1.w, t2.x), rp, tMin, limit, u, v);
+            if (hitT < limit) {
+                if (anyHit) { // kernels.cu:207: the first hit ends an any-hit walk
+                    s.closest = hitT;
+                    c.rec.z = t2.y;
+                    s.sp = -1;
+                    return;
+                }
+                if (hitT < s.closest) {
+                    // new best; the previous one (and whatever was accepted before it) may lie within the margin of the new one
+                    r.oct = (s.closest <= hitT * WIDE_TIE_MARGIN) ? (r.oct | WIDE_FLAG_TIE) : (r.oct & ~WIDE_FLAG_TIE);
+                    s.closest = hitT;
+                    c.rec.x = u;
+                    c.rec.y = v;
+                    c.rec.z = t2.y;
+                } else if (__float_as_uint(t2.y) != __float_as_uint(c.rec.z)) {
+                    r.oct |= WIDE_FLAG_TIE;
+                }
             }
-            if (hitT < s.closest) {
-                // new best; the previous one (and whatever was accepted before it) may lie within the margin of the new one
-                r.oct = (s.closest <= hitT * WIDE_TIE_MARGIN) ? (r.oct | WIDE_FLAG_TIE) : (r.oct & ~WIDE_FLAG_TIE);
-                s.closest = hitT;
-                c.rec.x = u;
-                c.rec.y = v;
-                c.rec.z = t2.y;
-            } else if (__float_as_uint(t2.y) != __float_as_uint(c.rec.z)) {
-                r.oct |= WIDE_FLAG_TIE;
-            }
-        }
+            k++;
+        } while (--left != 0u);
     }
     if (s.ngy <= 0x00FFFFFFu) widePop(s, stack, stride);
 }
