@@ -36,7 +36,21 @@ EXTEND_BYTES_PER_RAY = 56   # queue entry 4 + {origin,rng} 16 + {dir,flags} 16 r
 SHADOW_BYTES_PER_RAY = 85   # entry 4 + {origin} 16 + {dir,dist} 16 + {contribution,flags} 16 read; colour 16 read + 16 written; pending 1
 RESUME_BYTES = 64           # a parked ray: state 8 + hit 16 + entry 4 written, then ray 32 + the same 28 read again
 BATCH_BYTES_PER_RAY = 52    # 32 in, 16 + 4 out
-TRACE_DRAM_BYTES_PER_LAUNCH = 179.7e6  # dram__bytes_read.sum + dram__bytes_write.sum of one bulk traceKernel launch (profiles/r01/d_trace_ncu_summary.txt)
+# Flop model: the order-exact walk costs 36 flops per dual-node visit (two slab tests); a visit of an 8-wide node of
+# the renderer's own tree costs 8 x (6 fused multiply-adds + 4 min/max + 1 subtraction) + 12 of per-node setup = 148; a triangle
+# test 48; 3 per ray for the reciprocal direction.
+FLOPS_PER_DUAL_VISIT, FLOPS_PER_WIDE_VISIT, FLOPS_PER_TRI_TEST, FLOPS_PER_RAY = 36.0, 148.0, 48.0, 3.0
+NCU_FILE = os.path.join(ROOT, "profiles", "r02", "trace_ncu.json")  # DRAM bytes of the dominant kernel's bulk launch (ncu --set full)
+
+
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE bulk launch of `kernel`, from the ncu capture kept under profiles/ (the
+    capture is a separate run of the same frame: bench.py itself never runs under a profiler)."""
+    if os.path.exists(NCU_FILE):
+        d = json.load(open(NCU_FILE)).get(kernel)
+        if d:
+            return d
+    return None
 
 
 def shard_samples(ns_total, world):
@@ -117,7 +131,9 @@ RAYCOUNT_FILE = os.path.join(ROOT, "profiles", "raycounts.json")
 def raycount_key(args, ns):
     if args.workload == "rtiow":
         return "rtiow:seed1:%dx%dx%d:d50" % (args.nx, args.ny, ns)
-    return "staircase:%.3f:%d:%dx%dx%d:d%d" % (args.detail, args.tex, args.nx, args.ny, ns, args.depth)
+    # (the caller's tree does not change which rays are traced -- frames are identical for both build modes -- but the key says
+    # which file the count was taken on)
+    return "staircase:%.3f:%d:%dx%dx%d:d%d%s" % (args.detail, args.tex, args.nx, args.ny, ns, args.depth, ":sah" if args.bvh == "sah" else "")
 
 
 def known_raycount(args, ns):
@@ -142,8 +158,8 @@ def run_reference(args, rank, world):
     # that job -- 200 spp -- and the rate (Mrays/s) is what is reported; the run stays within a minute or two at every N.
     job_ns = args.spp * world
     ns = min(job_ns, max(2 * args.spp, args.spp))
-    cfg = dict(workload_params(args), gpus_used=1, total_spp=job_ns, sampled_spp=ns,
-               l2="state + textures (>230 MB) exceed L2; rewritten every step")
+    cfg = workload_params(args)  # the same keys and values as the other arm's `config`; what is specific to this arm is in `arm`
+    arm = dict(gpus_used=1, total_spp=job_ns, sampled_spp=ns, l2="state + textures (>230 MB) exceed L2; rewritten every step")
     if args.workload == "staircase":
         spec = args.detail
         if args.bvh == "sah":  # the reference reads the SAH-built tree from a BVH_00.04 file, like any scene of its own
@@ -177,7 +193,7 @@ def run_reference(args, rank, world):
         est = True
     value = rays / (ms * 1e3)
     e2e_ms = sum(e2e["ms"]) / len(e2e["ms"])
-    line = dict(base, metric="Mrays/s", value=value, unit="Mrays/s", ms_per_step=ms, config=cfg, rays_per_step=rays,
+    line = dict(base, metric="Mrays/s", value=value, unit="Mrays/s", ms_per_step=ms, config=cfg, arm=arm, rays_per_step=rays,
                 rays_estimated=est, msamples_per_s=args.nx * args.ny * ns / (ms * 1e3),
                 cpu_baseline=dict(value=value, unit="Mrays/s", cores=0, kind=kind,
                                   sample="%d of the job's %d spp, full frame, on the GPU: the reference's render path is a CUDA kernel, it has "
@@ -283,19 +299,22 @@ def run_ours(args, rank, world, local_rank):
     value = total_rays / (ms_per_step * 1e3)
     clocks = clk.summary()
 
-    # ---- roofline of the dominant kernel (traceKernel): one extra step in the timed configuration with CUDA events around every
+    # ---- roofline of the dominant kernel (the trace kernel): one extra step in the timed configuration with CUDA events around every
     # trace / shade launch (setRendererProfiling(2): same kernels, same chaser beside them, launched one by one instead of as a
     # graph), and one counting step for the flop side; both untimed
     roof, extra = None, {}
+    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    fp32_peak = sms * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
     if rank == 0 and not spheres:
         import ctypes as C
+        wide = crt.wide_info()
         L.setRendererProfiling(2)
         L.runRenderer(ns, 8, 8)
         L.setRendererProfiling(0)
         ps = crt.stats()
         ce, cs, cn, ct = C.c_ulonglong(), C.c_ulonglong(), C.c_ulonglong(), C.c_ulonglong()
         L.getRendererChaserCounts(C.byref(ce), C.byref(cs), C.byref(cn), C.byref(ct))
-        wave_extend, wave_shadow = ps.raysExtend - ce.value, ps.raysShadow - cs.value  # the rays traceKernel traced
+        wave_extend, wave_shadow = ps.raysExtend - ce.value, ps.raysShadow - cs.value  # the rays the trace kernel traced
         L.setRendererCounting(1)
         L.runRenderer(ns, 8, 8)
         L.setRendererCounting(0)
@@ -305,27 +324,48 @@ def run_ours(args, rank, world, local_rank):
         iters = max(int(ps.iterations), 1)
         avg_ms = ps.msTrace / iters
         rays_all = ps.raysExtend + ps.raysShadow
+        kernel = "wideTraceKernel<false,*,true>" if wide.active else "traceKernel<false,*>"
+        per_visit = FLOPS_PER_WIDE_VISIT if wide.active else FLOPS_PER_DUAL_VISIT
         bytes_per_launch = (EXTEND_BYTES_PER_RAY * wave_extend + SHADOW_BYTES_PER_RAY * wave_shadow + RESUME_BYTES * ps.resumes) / iters
-        achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
-        flops_wave = 3.0 * (wave_extend + wave_shadow) + 36.0 * (nv.value - cn.value) + 48.0 * (tt.value - ct.value)
-        flops_all = 3.0 * rays_all + 36.0 * nv.value + 48.0 * tt.value
-        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
-        fp32_peak = sms * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
-        roof = dict(bound="hbm", kernel="traceKernel<false>", achieved=achieved, peak=pk["hbm_gbs"], unit="GB/s", frac=achieved / pk["hbm_gbs"],
-                    traffic=TRACE_DRAM_BYTES_PER_LAUNCH, peak_source=pk["src"], avg_launch_ms=avg_ms, launches=iters,
-                    bytes_per_ray=dict(extend=EXTEND_BYTES_PER_RAY, shadow=SHADOW_BYTES_PER_RAY, resumed=RESUME_BYTES),
-                    note="scene (19 MB) is L2-resident by design: the kernel is bound by L1/L2 latency and instruction issue, not HBM; "
-                         "`traffic` = dram bytes of one bulk launch (1.66 M rays) from profiles/r01 (ncu --set full); see fp32",
-                    fp32=dict(achieved=flops_wave / (ps.msTrace * 1e-3) / 1e12, peak=fp32_peak, unit="TFLOP/s",
-                              frac=flops_wave / (ps.msTrace * 1e-3) / 1e12 / fp32_peak, kernels="traceKernel (its own rays over its own launch time)",
+        hbm_achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+        flops_wave = FLOPS_PER_RAY * (wave_extend + wave_shadow) + per_visit * (nv.value - cn.value) + FLOPS_PER_TRI_TEST * (tt.value - ct.value)
+        flops_all = FLOPS_PER_RAY * rays_all + per_visit * nv.value + FLOPS_PER_TRI_TEST * tt.value
+        fp32_achieved = flops_wave / (ps.msTrace * 1e-3) / 1e12
+        hbm_frac, fp32_frac = hbm_achieved / pk["hbm_gbs"], fp32_achieved / fp32_peak
+        ncu = measured_traffic("wideTraceKernel" if wide.active else "traceKernel")
+        roof = dict(bound="fp32" if fp32_frac >= hbm_frac else "hbm", kernel=kernel,
+                    achieved=fp32_achieved if fp32_frac >= hbm_frac else hbm_achieved, peak=fp32_peak if fp32_frac >= hbm_frac else pk["hbm_gbs"],
+                    unit="TFLOP/s" if fp32_frac >= hbm_frac else "GB/s", frac=max(fp32_frac, hbm_frac),
+                    traffic=ncu["dram_bytes_per_launch"] if ncu else None,
+                    traffic_source=(ncu["source"] if ncu else None),
+                    traffic_over_algorithmic=(ncu["dram_bytes_per_launch"] / (ncu["algorithmic_bytes_per_launch"]) if ncu else None),
+                    peak_source="SMs x 128 lanes x 2 x sm_max_mhz (cudaGetDeviceProperties, MEASURED_PEAKS.json)", avg_launch_ms=avg_ms, launches=iters,
+                    binding_resource="instruction issue, ALU pipe first (profiles/r02: issue active 70 %, ALU pipe 60 %, 18 of 32 lanes per "
+                                     "instruction); the scene is L2-resident by design, so the HBM term is small",
+                    hbm=dict(achieved=hbm_achieved, peak=pk["hbm_gbs"], unit="GB/s", frac=hbm_frac, peak_source=pk["src"],
+                             bytes_per_ray=dict(extend=EXTEND_BYTES_PER_RAY, shadow=SHADOW_BYTES_PER_RAY, resumed=RESUME_BYTES),
+                             algorithmic_bytes_per_launch=bytes_per_launch),
+                    fp32=dict(achieved=fp32_achieved, peak=fp32_peak, unit="TFLOP/s", frac=fp32_frac,
+                              kernels="the trace kernel's own rays over its own launch time",
                               whole_frame_frac=flops_all / (ms_per_step * 1e-3) / 1e12 / fp32_peak,
                               node_visits_per_ray=nv.value / max(rays_all, 1), tri_tests_per_ray=tt.value / max(rays_all, 1),
-                              formula="3*rays + 36*dual-node visits + 48*triangle tests (SURVEY.md 8d)"))
+                              formula="%g*rays + %g*node visits + %g*triangle tests (%s)" %
+                                      (FLOPS_PER_RAY, per_visit, FLOPS_PER_TRI_TEST, "8-wide nodes of the renderer's own tree" if wide.active else "dual-node visits, SURVEY.md 8d")))
         extra = dict(kernel_ms_profiled=dict(trace=ps.msTrace, shade=ps.msShade,
-                                             note="CUDA events around every traceKernel / meshShadeKernel launch of one frame in the timed "
-                                                  "configuration (chaser waves run beside them)"),
+                                             note="CUDA events around every trace / shade launch of one frame in the timed configuration (chaser waves run beside them)"),
                      wavefront_iterations=iters, resumed_rays=int(ps.resumes), deferred_shades=int(ps.deferred),
-                     chaser=dict(rays=int(ce.value + cs.value), share_of_rays=(ce.value + cs.value) / max(rays_all, 1)))
+                     chaser=dict(rays=int(ce.value + cs.value), share_of_rays=(ce.value + cs.value) / max(rays_all, 1)),
+                     acceleration_structure=dict(own_tree=bool(wide.active), wide_nodes=int(wide.numNodes), depth=int(wide.depth),
+                                                 build_ms_inside_initRenderer=float(wide.buildMs), built_on="device" if wide.buildThreads == 0 else "host",
+                                                 rays_retraced_in_reference_order=int(wide.lastFrameRedo)))
+    elif rank == 0:
+        # sphere scenes: the extend kernel walks a sphere BVH (20 flops per sphere test, ~25 per node); report the byte side and the
+        # flop side of the frame as a whole (no per-kernel event timing in this pipeline)
+        bytes_frame = 150.0 * total_rays  # ~150 B of queue traffic per ray in a wavefront
+        hbm_achieved = bytes_frame / (ms_per_step * 1e-3) / 1e9
+        roof = dict(bound="hbm", kernel="extendSpheresBvhKernel + shadeSpheresKernel (whole frame)", achieved=hbm_achieved, peak=pk["hbm_gbs"], unit="GB/s",
+                    frac=hbm_achieved / pk["hbm_gbs"], traffic=None, peak_source=pk["src"],
+                    note="whole-frame figure from the SURVEY 8d byte model (150 B per ray); latency-bound gathers, no ncu capture committed for this path")
     fr.close()
 
     # ---- e2e: host buffers -> frame on the host, through the reference-facing entry points, every step
@@ -337,10 +377,46 @@ def run_ours(args, rank, world, local_rank):
         step(fr)
         if rank == 0:
             host = fr.frame(copy=True)    # D2H: the managed frame buffer read on the host
+            if extra.get("acceleration_structure"):  # the tree build of a WARM frame (the first frame of a process also allocates)
+                extra["acceleration_structure"]["build_ms_inside_initRenderer"] = float(crt.wide_info().buildMs)
         fr.close()
     barrier()
     e2e_ms = allmax((time.perf_counter() - t0) * 1e3 / e2e_steps)
     e2e_value = total_rays / (e2e_ms * 1e3)
+
+    # ---- BASELINE config 4 (strong scaling): ONE frame of 3840x2160 at 1024 spp IN TOTAL, the samples split over the ranks
+    # (1024 / N each, rank g on RNG stream g), the un-normalised sums reduced once to rank 0. Not part of `value`; no warm-up.
+    c4 = None
+    if args.c4 and not spheres:
+        nx4, ny4, total4 = 3840, 2160, 1024
+        mine = shard_samples(total4, world)[rank]
+        acc4 = torch.zeros(ny4 * nx4, 4, device="cuda") if world > 1 else None
+        crt.set_options(device=local_rank, sample_stream=rank, defer_finalize=1 if world > 1 else 0, slots_per_pixel=args.slots)
+        fr4 = crt.Frame(scene, nx4, ny4, depth)
+        if world > 1:
+            L.setRendererAccumDevice(acc4.data_ptr())
+        barrier()
+        t0 = time.perf_counter()
+        L.runRenderer(mine, 8, 8)
+        st4 = crt.stats()
+        ms4 = st4.msTotal
+        if world > 1:
+            ev0.record()
+            dist.reduce(acc4, dst=0, op=dist.ReduceOp.SUM)
+            ev1.record()
+            torch.cuda.synchronize()
+            ms4 += ev0.elapsed_time(ev1)
+            if rank == 0:
+                L.finalizeFrame(total4)
+        barrier()
+        wall4 = (time.perf_counter() - t0) * 1e3
+        ms4 = allmax(ms4)
+        rays4 = allsum(st4.raysExtend + st4.raysShadow)
+        fr4.close()
+        del acc4
+        c4 = dict(ms=ms4, wall_ms=wall4, mrays_per_s=rays4 / (ms4 * 1e3), msamples_per_s=nx4 * ny4 * total4 / (ms4 * 1e3), rays=int(rays4),
+                  spp_per_gpu=shard_samples(total4, world), frame="3840x2160", total_spp=total4, scaling="strong",
+                  note="device time of runRenderer (max over ranks) + the NCCL reduce of %d MB per rank + finalize on rank 0" % (nx4 * ny4 * 16 >> 20))
 
     if rank != 0:
         if dist:
@@ -352,7 +428,7 @@ def run_ours(args, rank, world, local_rank):
     import oracle
     cpu = None
     if world == 1:
-        stride, cpu_ns = 40, min(ns, 25)
+        stride, cpu_ns = 4, min(ns, 25)  # ~10-20 s of work on 16 host threads
         t0 = time.perf_counter()
         if spheres:
             _, cnt = oracle.render_spheres(scene, nx, ny, cpu_ns, depth, count=True, row_stride=stride)
@@ -365,16 +441,17 @@ def run_ours(args, rank, world, local_rank):
                    sample="every %dth row of the %dx%d frame at %d spp (%d rays, %.1f s), OpenMP over rows, -O3 -ffp-contract=off" %
                           (stride, nx, ny, cpu_ns, cr, sec))
 
-    cfg = dict(workload_params(args), parallelism="sample-sharded x%d, 1 NCCL reduce/frame" % world if world > 1 else "single GPU",
+    cfg = workload_params(args)  # the same keys and values as the reference arm's `config`; what is specific to this arm is in `arm`
+    arm = dict(parallelism="sample-sharded x%d, 1 NCCL reduce/frame" % world if world > 1 else "single GPU",
                total_spp=ns_total, rng="reference seeding (stream = rank), %d slot(s)/pixel" % max(args.slots, 1),
                l2="256 MB written between timed steps; path state + textures (>230 MB) exceed the 126 MB L2")
     line = dict(metric="Mrays/s", value=value, unit="Mrays/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
-                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=cfg,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=cfg, arm=arm,
                 rays_per_step=int(total_rays), msamples_per_s=nx * ny * ns_total / (ms_per_step * 1e3), wall_ms_per_step=wall_ms / args.steps,
                 clocks=clocks, e2e=dict(value=e2e_value, unit="Mrays/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                                         ms_per_step=e2e_ms, steps=e2e_steps,
                                         note="initRenderer (scene upload from caller-owned host memory) + runRenderer + frame read + cleanupRenderer, per step"),
-                gpu_launches=launches, roofline=roof, cpu_baseline=cpu, **extra)
+                gpu_launches=launches, roofline=roof, cpu_baseline=cpu, c4_strong=c4, **extra)
     print(json.dumps(line))
     if dist:
         dist.destroy_process_group()
@@ -403,6 +480,7 @@ def run_raybatch(args, rank, world, local_rank):
         import ctypes as C
         nv, tt = C.c_ulonglong(), C.c_ulonglong()
         L.getRendererTraversalCounts(C.byref(nv), C.byref(tt))
+        wide_active, redo = bool(crt.wide_info().active), int(crt.wide_info().lastBatchRedo)
         # e2e: host rays in, host hits out
         ro, rd = np.zeros((n, 4), np.float32), np.zeros((n, 4), np.float32)
         L.rendererCopyToHost(ro.ctypes.data, dO, 16 * n)
@@ -421,7 +499,7 @@ def run_raybatch(args, rank, world, local_rank):
         return
     avg = sum(ms) / len(ms)
     achieved = BATCH_BYTES_PER_RAY * n / (avg * 1e-3) / 1e9
-    flops = 3.0 * n + 36.0 * nv.value + 48.0 * tt.value
+    flops = FLOPS_PER_RAY * n + (FLOPS_PER_WIDE_VISIT if wide_active else FLOPS_PER_DUAL_VISIT) * nv.value + FLOPS_PER_TRI_TEST * tt.value
     sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
     fp32_peak = sms * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
     line = dict(metric="Mrays/s", value=n * world / (avg * 1e3), unit="Mrays/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=avg,
@@ -429,8 +507,14 @@ def run_raybatch(args, rank, world, local_rank):
                 config=dict(workload_params(args), l2="ray batch (%d MB) exceeds L2" % (52 * n >> 20)), clocks=clk.summary(),
                 e2e=dict(value=n / (e2e_ms * 1e3), unit="Mrays/s", h2d_bytes_per_step=32 * n, d2h_bytes_per_step=20 * n, ms_per_step=e2e_ms),
                 gpu_launches=args.steps,
-                roofline=dict(bound="hbm", kernel="intersectBatchKernel<false>", achieved=achieved, peak=pk["hbm_gbs"], unit="GB/s",
-                              frac=achieved / pk["hbm_gbs"], traffic=None, peak_source=pk["src"],
+                roofline=dict(bound="fp32" if flops / (avg * 1e-3) / 1e12 / fp32_peak >= achieved / pk["hbm_gbs"] else "hbm",
+                              kernel="wideIntersectBatchKernel<false,true> (+ intersectBatchKernel for %d uncertified rays)" % redo if wide_active else "intersectBatchKernel<false>",
+                              achieved=max(flops / (avg * 1e-3) / 1e12, 0.0) if flops / (avg * 1e-3) / 1e12 / fp32_peak >= achieved / pk["hbm_gbs"] else achieved,
+                              peak=fp32_peak if flops / (avg * 1e-3) / 1e12 / fp32_peak >= achieved / pk["hbm_gbs"] else pk["hbm_gbs"],
+                              unit="TFLOP/s" if flops / (avg * 1e-3) / 1e12 / fp32_peak >= achieved / pk["hbm_gbs"] else "GB/s",
+                              frac=max(flops / (avg * 1e-3) / 1e12 / fp32_peak, achieved / pk["hbm_gbs"]),
+                              traffic=(measured_traffic("wideIntersectBatchKernel") or {}).get("dram_bytes_per_launch"),
+                              hbm=dict(achieved=achieved, peak=pk["hbm_gbs"], unit="GB/s", frac=achieved / pk["hbm_gbs"], peak_source=pk["src"], bytes_per_ray=BATCH_BYTES_PER_RAY),
                               fp32=dict(achieved=flops / (avg * 1e-3) / 1e12, peak=fp32_peak, unit="TFLOP/s", frac=flops / (avg * 1e-3) / 1e12 / fp32_peak,
                                         node_visits_per_ray=nv.value / n, tri_tests_per_ray=tt.value / n)),
                 cpu_baseline=None)
@@ -452,6 +536,7 @@ def main():
     ap.add_argument("--tex", type=int, default=1024)
     ap.add_argument("--rays", type=int, default=1 << 26)
     ap.add_argument("--slots", type=int, default=0, help="path slots per pixel (0/1 = reference RNG streams)")
+    ap.add_argument("--no-c4", dest="c4", action="store_false", help="skip the BASELINE config 4 frame (3840x2160, 1024 spp in total: ~30 s on one GPU)")
     ap.add_argument("--bvh", default="median", choices=["median", "sah"],
                     help="how the host builds the scene's BVH_00.04 tree: the reference author's median split (default) or the "
                          "surface-area heuristic inside the same layout (both arms get the same file)")
