@@ -5,7 +5,7 @@ CXX   ?= g++
 PKG   := cuda-raytracing-optimized_b200
 ARCH  := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -Iinclude -I$(PKG)/csrc
-CSRC  := $(wildcard $(PKG)/csrc/*.cu $(PKG)/csrc/*.cuh $(PKG)/csrc/*.h $(PKG)/csrc/*.cpp) include/kernels.h include/rt_types.h
+CSRC  := $(wildcard $(PKG)/csrc/*.inc $(PKG)/csrc/*.cu $(PKG)/csrc/*.cuh $(PKG)/csrc/*.h $(PKG)/csrc/*.cpp) include/kernels.h include/rt_types.h
 HOSTSRC := $(PKG)/host/host_api.cpp $(PKG)/host/bvh_builder.cpp
 
 .PHONY: all oracle clean
@@ -17,7 +17,7 @@ build/libcrt_host.so: $(HOSTSRC) $(PKG)/host/host_api.h $(PKG)/host/bvh_builder.
 
 build/libcrt_b200.so: $(CSRC)
 	@mkdir -p build
-	$(NVCC) $(NVFLAGS) -Xcompiler -pthread -shared $(PKG)/csrc/renderer.cu $(PKG)/csrc/wide_bvh.cpp -o $@
+	$(NVCC) $(NVFLAGS) -Xcompiler -pthread -shared $(PKG)/csrc/renderer.cu $(PKG)/csrc/wide_bvh.cpp -o $@ -ldl
 
 build/crt_render: $(PKG)/host/main.cpp build/libcrt_host.so build/libcrt_b200.so
 	$(CXX) -O2 -std=c++17 -Iinclude -I$(PKG)/host $< -o $@ -Lbuild -lcrt_b200 -lcrt_host -Wl,-rpath,'$$ORIGIN'

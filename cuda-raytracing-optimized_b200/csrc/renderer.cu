@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "kernels.h"
+#include "multi_gpu.h"
 #include "raybatch_kernels.cuh"
 #include "renderer_internal.h"
 #include "wavefront_kernels.cuh"
@@ -32,10 +33,11 @@ void crtCheckCuda(cudaError_t result, const char* func, const char* file, int li
     }
 }
 
-RendererContext g_ctx;
-renderer_options g_opts = {-1, 0u, 0, 0, 0, {0, 0, 0}};
-static int g_profiling = 0;
-static int g_traversal = -1; // setRendererTraversal(); -1 = CRT_TRAVERSAL from the environment, else TRAVERSAL_WIDE
+thread_local RendererContext g_ctx;
+thread_local renderer_options g_opts = {-1, 0u, 0, 0, 0, {0, 0, 0}};
+static thread_local int g_profiling = 0;
+static int g_traversal = -1;
+static thread_local bool g_isGpuWorker = false; // setRendererTraversal(); -1 = CRT_TRAVERSAL from the environment, else TRAVERSAL_WIDE
 
 static f3 toF3(const vec3& v) { return mk3(v.e[0], v.e[1], v.e[2]); }
 
@@ -67,7 +69,7 @@ struct DeviceArena {
     size_t wanted = 0;   // bytes requested since the last reset
     int device = -1;
 };
-static DeviceArena g_arena;
+static thread_local DeviceArena g_arena;
 
 static void arenaFreeAll() {
     for (auto& b : g_arena.blocks) cudaFree(b.first);
@@ -126,7 +128,7 @@ struct HostCache {
     void* fb = nullptr;           // pinned + mapped frame buffer
     size_t fbBytes = 0;
 };
-static HostCache g_cache;
+static thread_local HostCache g_cache;
 
 static void releaseCaches() {
     if (g_cache.device >= 0) {
@@ -579,6 +581,19 @@ extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb,
     c.light.center = mk3(52.514355f, 715.686951f, -272.620972f);
     c.light.radius = 50.0f;
     c.light.color = mk3(20.0f, 20.0f, 20.0f);
+
+    // setRendererGpus(N > 1): N - 1 further devices, one host thread each (multi_gpu.h). Worker threads themselves are single.
+    extern int crtRequestedGpus();
+    if (crtRequestedGpus() > 1 && !g_isGpuWorker) {
+        int dev = 0;
+        CRT_CHECK(cudaGetDevice(&dev));
+        c.opts.deferFinalize = 1;
+        g_isGpuWorker = true; // (the lambda-spawned threads have their own flag; this one guards re-entry from this thread)
+        crtMultiGpuStart(sc, cam, nx, ny, maxDepth, crtRequestedGpus(), dev, c.opts.sampleStream);
+        g_isGpuWorker = false;
+        c.opts.sampleStream = c.opts.sampleStream * (unsigned int)crtRequestedGpus();
+        pt.mark("init: worker devices");
+    }
 }
 
 static bool useWideTree(const RendererContext& c) { return c.wide.stackDepth > 0 && c.traversal != TRAVERSAL_EXACT; }
@@ -901,7 +916,8 @@ extern "C" void runRenderer(int ns, int tx, int ty) {
         std::fprintf(stderr, "runRenderer called before initRenderer\n");
         std::exit(99);
     }
-    if (c.kind == SCENE_MESH) crtRunMesh(c, ns, false);
+    if (c.kind == SCENE_MESH && crtMultiGpuCount() > 1) crtMultiGpuRun(ns, [](int own) { crtRunMesh(g_ctx, own, false); });
+    else if (c.kind == SCENE_MESH) crtRunMesh(c, ns, false);
     else crtRunSpheres(c, ns);
 }
 
@@ -912,7 +928,7 @@ extern "C" void runRenderer(int ns, int tx, int ty) {
 extern "C" int continueRenderer(int nsMore, int tx, int ty) {
     (void)tx; (void)ty;
     RendererContext& c = g_ctx;
-    if (!c.initialised || c.kind != SCENE_MESH || c.samplesDone <= 0 || !c.mp.rngOut || c.mp.slotsPerPixel != 1) return -1;
+    if (!c.initialised || c.kind != SCENE_MESH || c.samplesDone <= 0 || !c.mp.rngOut || c.mp.slotsPerPixel != 1 || crtMultiGpuCount() > 1) return -1;
     crtRunMesh(c, nsMore, true);
     return 0;
 }
@@ -1078,6 +1094,7 @@ extern "C" void cleanupRenderer() {
     RendererContext& c = g_ctx;
     if (!c.initialised) return;
     PhaseTimer pt;
+    if (crtMultiGpuCount() > 1) crtMultiGpuStop();
     CRT_CHECK(cudaStreamSynchronize(c.stream));
     CRT_CHECK(cudaStreamSynchronize(c.streamFast));
     freeWavefront(c);
@@ -1243,3 +1260,4 @@ extern "C" void rendererCopyToDevice(void* dDst, const void* src, size_t bytes) 
 }
 
 #include "spheres_path.cuh"
+#include "multi_gpu.cu.inc"

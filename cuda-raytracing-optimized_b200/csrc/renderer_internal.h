@@ -78,8 +78,10 @@ struct RendererContext {
     renderer_stats stats = {};
 };
 
-extern RendererContext g_ctx;
-extern renderer_options g_opts;
+// One renderer per HOST THREAD (the reference has one per process, kernels.cu:145; a single-threaded caller sees no difference):
+// the multi-GPU mode runs one host thread per device, each with its own context, arena and stream cache.
+extern thread_local RendererContext g_ctx;
+extern thread_local renderer_options g_opts;
 
 void crtRunMesh(RendererContext& c, int ns, bool resume);
 void crtRunSpheres(RendererContext& c, int ns);

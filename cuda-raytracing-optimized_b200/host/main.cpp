@@ -4,7 +4,7 @@
 // PPM on stdout / file -> optional RMSE against a REF_00.01 frame -> cleanupRenderer.
 //
 //   crt_render [--scene staircase|rtiow|file.bvh] [--nx N] [--ny N] [--ns N] [--depth N] [--detail F]
-//              [--tex N] [--ppm out.ppm|-] [--ref frame.ref] [--save-ref frame.ref] [--bvh-out file.bvh]
+//              [--tex N] [--ppm out.ppm|-] [--ref frame.ref] [--save-ref frame.ref] [--bvh-out file.bvh] [--gpus N] [--frames K]
 //   (the reference's single positional argument, maxDepth, is still accepted: main.cpp:73-74)
 #include <chrono>
 #include <cstdio>
@@ -19,6 +19,7 @@
 int main(int argc, char** argv) {
     int nx = 640, ny = 800, ns = 256, maxDepth = 64, tx = 8, ty = 8, texSize = 1024; // main.cpp:65-70
     float detail = 1.0f;
+    int gpus = 1, frames = 1;
     std::string scene = "staircase", ppm, refIn, refOut, bvhOut;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -34,6 +35,8 @@ int main(int argc, char** argv) {
         else if (a == "--ref") refIn = next();
         else if (a == "--save-ref") refOut = next();
         else if (a == "--bvh-out") bvhOut = next();
+        else if (a == "--frames") frames = std::atoi(next()); // render the frame this many times (the last one is kept)
+        else if (a == "--gpus") gpus = std::atoi(next()); // sample-sharded over N devices of this box, one NCCL reduce per frame
         else if (a[0] != '-') maxDepth = (int)std::strtol(a.c_str(), NULL, 10);
         else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
     }
@@ -57,16 +60,18 @@ int main(int argc, char** argv) {
                      ksc->numPrimitivesPerLeaf); // staircase_scene.h:177-179
         if (!bvhOut.empty() && crtSceneSaveBVH(sc, bvhOut.c_str()) != 0) std::fprintf(stderr, "cannot write %s\n", bvhOut.c_str());
         crtStaircaseCamera(nx, ny, &cam);
+        if (gpus > 1) setRendererGpus(gpus);
         initRenderer(*ksc, cam, &fb, nx, ny, maxDepth);
     }
 
+    for (int f = 1; f < frames; f++) runRenderer(ns, tx, ty);
     const auto start = std::chrono::steady_clock::now();
     runRenderer(ns, tx, ty);
     const double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
     renderer_stats st;
     getRendererStats(&st);
-    std::fprintf(stderr, "took %.3f seconds (device %.1f ms; %.1f Mrays/s, %.2f Msamples/s, %llu wavefront iterations).\n", seconds,
-                 st.msTotal, (st.raysExtend + st.raysShadow) / (st.msTotal * 1e3), st.samples / (st.msTotal * 1e3), st.iterations);
+    std::fprintf(stderr, "took %.3f seconds on %d GPU(s) (device %.1f ms; %.1f Mrays/s, %.2f Msamples/s, %llu wavefront iterations).\n", seconds,
+                 getRendererGpus(), st.msTotal, (st.raysExtend + st.raysShadow) / (st.msTotal * 1e3), st.samples / (st.msTotal * 1e3), st.iterations);
 
     if (!ppm.empty()) crtWritePPM(ppm.c_str(), nx, ny, fb);
     if (!refIn.empty()) { // main.cpp:108-128

@@ -132,7 +132,7 @@ DEVICE_SYMBOLS = [
     "rendererCopyToDevice", "getRendererStats", "setRendererProfiling", "getRendererAccumDevice", "setRendererAccumDevice",
     "finalizeFrame", "setRendererCounting", "getRendererTraversalCounts", "rendererDebugRead", "rendererReleaseCaches", "getRendererChaserCounts", "continueRenderer", "getRendererSamplesDone",
     "saveRendererCheckpoint", "loadRendererCheckpoint", "scatterBatch", "intersectBatchDeviceEx", "setRendererTraversal",
-    "getRendererWideInfo", "rendererTrigSelfTest", "getRendererWideTree",
+    "getRendererWideInfo", "rendererTrigSelfTest", "getRendererWideTree", "setRendererGpus", "getRendererGpus",
 ]
 
 TRAVERSAL_WIDE, TRAVERSAL_EXACT, TRAVERSAL_WIDE_UNCERTIFIED = 0, 1, 2
@@ -162,6 +162,7 @@ def device_lib():
         L.intersectBatchDeviceEx.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int]
         L.setRendererTraversal.argtypes = [C.c_int]
         L.rendererTrigSelfTest.restype = C.c_longlong
+        L.setRendererGpus.argtypes = [C.c_int]
         L.getRendererWideTree.restype = C.c_uint
         L.getRendererWideTree.argtypes = [C.c_void_p, C.c_uint, C.c_void_p, C.c_uint]
         L.getRendererWideInfo.argtypes = [C.POINTER(RendererWideInfo)]

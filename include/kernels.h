@@ -139,6 +139,15 @@ void* getRendererAccumDevice();   // device pointer, nx*ny float4
 void setRendererAccumDevice(void* dAccum); // render into a caller-owned device buffer (e.g. a torch tensor) instead
 void finalizeFrame(int nsTotal);  // fb = accum / nsTotal (blocking)
 
+// Several GPUs of one box inside the library (the reference is single-GPU). setRendererGpus(N) applies to the next
+// initRenderer of the calling thread: it brings up N - 1 worker host threads, one per further device (devices d, d+1, ... from
+// the caller's current device), each uploading and indexing the whole scene. runRenderer(ns) then renders ns/N samples of every
+// pixel per device (device g on RNG stream g; g = 0 is the reference's stream), combines the un-normalised sums with ONE
+// ncclReduce to the caller's device and writes fb = sum / ns there; cleanupRenderer ends the workers. NCCL (libnccl.so.2) is
+// loaded at run time, only in this mode. Mesh scenes only. N <= 1 restores single-GPU rendering.
+void setRendererGpus(int n);
+int getRendererGpus(void); // devices the calling thread's renderer uses (1 = single)
+
 // Progressive rendering (mesh scenes, one slot per pixel). A pixel's samples are ONE RNG stream (reference
 // kernels.cu:542-548), so a frame can be continued exactly: runRenderer(a) followed by continueRenderer(b) leaves in fb the
 // bits runRenderer(a + b) would. saveRendererCheckpoint writes the running sums and the stream positions

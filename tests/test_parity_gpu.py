@@ -532,3 +532,42 @@ def test_device_built_wide_tree_is_sound(crt, oracle, medium_scene, small_scene)
         assert depth.value == info.depth
     for s in tiny:
         s.close()
+
+
+def _gpu_count():
+    try:
+        import subprocess
+        return len(subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=20).stdout.strip().splitlines())
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs in the box")
+def test_multi_gpu_inside_the_library(crt, medium_scene):
+    """setRendererGpus(2): one host thread per device inside libcrt_b200.so, sample streams 0 and 1, one ncclReduce, fb on device 0.
+    The frame is the average of the two single-GPU frames of streams 0 and 1 (same sums, one float addition apart), the ray
+    count their sum, and it agrees statistically with a one-GPU frame of the same total sample count."""
+    nx, ny, ns, depth = 240, 160, 16, 64
+    L = crt.device_lib()
+    L.setRendererGpus(2)
+    with crt.Frame(medium_scene, nx, ny, depth) as fr:
+        assert L.getRendererGpus() == 2
+        both = fr.run(ns)
+        st = crt.stats()
+        again = fr.run(ns)
+    L.setRendererGpus(1)
+    halves, rays = [], 0
+    for g in (0, 1):
+        crt.set_options(sample_stream=g)
+        with crt.Frame(medium_scene, nx, ny, depth) as fr:
+            halves.append(fr.run(ns // 2).astype(np.float64))
+            s = crt.stats()
+            rays += s.raysExtend + s.raysShadow
+    crt.set_options()
+    assert L.getRendererGpus() == 1
+    assert np.array_equal(both, again)
+    assert st.samples == nx * ny * ns and st.raysExtend + st.raysShadow == rays
+    assert np.abs(both - 0.5 * (halves[0] + halves[1])).max() <= 1e-5 * max(1.0, float(both.max()))
+    with crt.Frame(medium_scene, nx, ny, depth) as fr:
+        single = fr.run(ns)
+    assert abs(float(both.mean()) - float(single.mean())) <= 0.03 * float(single.mean())
