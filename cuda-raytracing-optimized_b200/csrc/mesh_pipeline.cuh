@@ -544,6 +544,13 @@ __global__ void __launch_bounds__(WIDE_TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wi
 #define tail (take < 32u)
 #define refillBelow (tail ? take : (unsigned int)st.traceMinActive)
     const unsigned int k3f = wideConst3F();
+#ifdef WIDE_SMEM_TOP
+    {   // the first nodes of the tree (breadth-first numbering: the root and the levels below it) copied into shared memory
+        uint4* top = (uint4*)(wideStackAll + wide.stackDepth * WIDE_TRACE_BLOCK);
+        for (unsigned int i = threadIdx.x; i < 6u * wide.topCount; i += WIDE_TRACE_BLOCK) top[i] = wide.nodes[i];
+        __syncthreads();
+    }
+#endif
 
     bool live = false;
     WideRay r;

@@ -611,16 +611,25 @@ static ShadeScene shadeScene(const RendererContext& c) {
 }
 
 
+#ifdef WIDE_SMEM_TOP
+#define WIDE_TRACE_EXTRA_SMEM (96u * WIDE_SMEM_TOP)
+#else
+#define WIDE_TRACE_EXTRA_SMEM 0u
+#endif
 template <int CUR>
 static void launchWideTrace(RendererContext& c, const MeshState& mp, cudaStream_t stream, int traceBlocks) {
-    const size_t smem = (size_t)c.wide.stackDepth * WIDE_TRACE_BLOCK * sizeof(uint2);
+    const size_t smem = (size_t)c.wide.stackDepth * WIDE_TRACE_BLOCK * sizeof(uint2) + WIDE_TRACE_EXTRA_SMEM;
     const bool certify = c.traversal != TRAVERSAL_WIDE_UNCERTIFIED;
+    WideView wv = c.wide;
+#ifdef WIDE_SMEM_TOP
+    wv.topCount = std::min<unsigned int>(WIDE_SMEM_TOP, c.wideStats.numNodes);
+#endif
     if (c.counting) {
-        if (certify) wideTraceKernel<true, CUR, true><<<traceBlocks, WIDE_TRACE_BLOCK, smem, stream>>>(mp, c.mesh, c.wide);
-        else wideTraceKernel<true, CUR, false><<<traceBlocks, WIDE_TRACE_BLOCK, smem, stream>>>(mp, c.mesh, c.wide);
+        if (certify) wideTraceKernel<true, CUR, true><<<traceBlocks, WIDE_TRACE_BLOCK, smem, stream>>>(mp, c.mesh, wv);
+        else wideTraceKernel<true, CUR, false><<<traceBlocks, WIDE_TRACE_BLOCK, smem, stream>>>(mp, c.mesh, wv);
     } else {
-        if (certify) wideTraceKernel<false, CUR, true><<<traceBlocks, WIDE_TRACE_BLOCK, smem, stream>>>(mp, c.mesh, c.wide);
-        else wideTraceKernel<false, CUR, false><<<traceBlocks, WIDE_TRACE_BLOCK, smem, stream>>>(mp, c.mesh, c.wide);
+        if (certify) wideTraceKernel<false, CUR, true><<<traceBlocks, WIDE_TRACE_BLOCK, smem, stream>>>(mp, c.mesh, wv);
+        else wideTraceKernel<false, CUR, false><<<traceBlocks, WIDE_TRACE_BLOCK, smem, stream>>>(mp, c.mesh, wv);
     }
     // what the wide walk could not certify, in the reference's order over the caller's tree (usually a handful of rays)
     traceKernel<false, CUR, true><<<c.numSMs, TRACE_BLOCK, 0, stream>>>(mp, c.mesh);
@@ -685,7 +694,7 @@ void crtRunMesh(RendererContext& c, int ns, bool resume) {
         c.traceBlocks = c.numSMs * (perSM > 0 ? perSM : 1); // persistent: exactly one resident wave
     }
     if (useWideTree(c) && !c.wideTraceBlocks) {
-        const size_t smem = (size_t)c.wide.stackDepth * WIDE_TRACE_BLOCK * sizeof(uint2);
+        const size_t smem = (size_t)c.wide.stackDepth * WIDE_TRACE_BLOCK * sizeof(uint2) + WIDE_TRACE_EXTRA_SMEM;
         auto prep = [&](auto kernel) { CRT_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); };
         prep(wideTraceKernel<false, 0, true>); prep(wideTraceKernel<false, 1, true>); prep(wideTraceKernel<false, 0, false>); prep(wideTraceKernel<false, 1, false>);
         prep(wideTraceKernel<true, 0, true>); prep(wideTraceKernel<true, 1, true>); prep(wideTraceKernel<true, 0, false>); prep(wideTraceKernel<true, 1, false>);

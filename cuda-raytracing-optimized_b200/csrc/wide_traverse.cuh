@@ -33,6 +33,7 @@ struct WideView {
     const float2* __restrict__ triB;   //                   {e2.z, caller's slot index}
     float rangeX, rangeY, rangeZ;      // |origin| limit of the fast path (WIDE_ORIGIN_RANGE x coordinate range)
     unsigned int stackDepth;           // entries per thread (>= wide tree depth); 0 = no wide tree: exact kernel only
+    unsigned int topCount;             // (WIDE_SMEM_TOP experiment: nodes the launching kernel staged in shared memory; else 0)
 };
 
 struct WideRay {
@@ -145,9 +146,18 @@ __device__ __forceinline__ void wideNodeStep(const WideView& w, const WideRay& r
     const unsigned int idx = s.ngx + __popc(s.ngy & ((1u << slot) - 1u) & 0xFFu);
     const char* rec = (const char*)w.nodes + 96ull * idx;
     uint4 h0, h1, q0, q1, q2, q3;
-    ldg256u(rec, h0, h1);        // p.xyz, e|imask, childBase, triBase, meta lo, meta hi
-    ldg256u(rec + 32, q0, q1);   // qlo x, x', y, y' | z, z', qhi x, x'
-    ldg256u(rec + 64, q2, q3);   // qhi y, y', z, z' | scale xyz, spare
+#ifdef WIDE_SMEM_TOP // (experiment, profiles/r02/neg_*: the first WIDE_SMEM_TOP nodes staged in shared memory by the kernel)
+    extern __shared__ uint2 wideStackAll[];
+    const uint4* top = (const uint4*)(wideStackAll + w.stackDepth * blockDim.x);
+    if (idx < w.topCount) {
+        h0 = top[6u * idx]; h1 = top[6u * idx + 1u]; q0 = top[6u * idx + 2u]; q1 = top[6u * idx + 3u]; q2 = top[6u * idx + 4u]; q3 = top[6u * idx + 5u];
+    } else
+#endif
+    {
+        ldg256u(rec, h0, h1);        // p.xyz, e|imask, childBase, triBase, meta lo, meta hi
+        ldg256u(rec + 32, q0, q1);   // qlo x, x', y, y' | z, z', qhi x, x'
+        ldg256u(rec + 64, q2, q3);   // qhi y, y', z, z' | scale xyz, spare
+    }
     const float ax = __uint_as_float(q3.x) * r.ix, ay = __uint_as_float(q3.y) * r.iy, az = __uint_as_float(q3.z) * r.iz;
     const float bx = __fmaf_rn(__uint_as_float(h0.x) - r.ox, r.ix, -ax);
     const float by = __fmaf_rn(__uint_as_float(h0.y) - r.oy, r.iy, -ay);
@@ -189,6 +199,15 @@ __device__ __forceinline__ void wideNodeStep(const WideView& w, const WideRay& r
     if (r.oct & 4u) prio = ((prio & 0x0Fu) << 4) | ((prio >> 4) & 0x0Fu);
     s.ngx = h1.x;
     s.ngy = (prio << 24) | imask;
+#ifdef WIDE_PREFETCH // (experiment, profiles/r02/neg_*: request the node that will be entered next into L1 now)
+    if (prio != 0u) {
+        const unsigned int nb = 31u - (unsigned int)__clz(prio << 24);
+        const unsigned int ns = (nb - 24u) ^ (r.oct & 7u);
+        const char* nrec = (const char*)w.nodes + 96ull * (h1.x + __popc(imask & ((1u << ns) - 1u)));
+        prefetchL1(nrec);
+        prefetchL1(nrec + 64);
+    }
+#endif
     // leaf hits: the slots go to the triangle group; their triangle ranges (meta = count << 5 | offset) are decoded in the
     // triangle phase, from the node's meta bytes parked in the thread's LAST stack entry (which the tree never reaches:
     // stackDepth > tree depth). Decoding here would make the lanes that continue with nodes wait for it.
