@@ -48,7 +48,9 @@ struct WideNode {
 };
 static_assert(sizeof(WideNode) == 96, "WideNode layout");
 
+#ifndef WIDE_MAX_LEAF_TRIS
 #define WIDE_MAX_LEAF_TRIS 3
+#endif
 #define WIDE_PAD_SCALE (1.0f / 262144.0f) // 2^-18 of the largest |coordinate| per axis (error bound: DESIGN.md)
 #define WIDE_ORIGIN_RANGE 4.0f            // rays whose |origin| exceeds this multiple of the coordinate range use the exact kernel
 
