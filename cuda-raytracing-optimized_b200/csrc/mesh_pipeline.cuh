@@ -663,7 +663,7 @@ __global__ void __launch_bounds__(WIDE_TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wi
             workMask = __ballot_sync(0xFFFFFFFFu, working);
             if (workMask == 0u) continue; // e.g. every new ray missed the scene bounds: retire them
         }
-        wideRound(wide, r, c, RT_EPSILON, working, s, stack, WIDE_TRACE_BLOCK, tail ? 1 : max(1, min(TRACE_NODE_QUORUM, __popc(workMask) >> 1)), k3f, nodeVisits, triTests);
+        wideRound(wide, r, c, RT_EPSILON, working, s, stack, WIDE_TRACE_BLOCK, tail ? 1 : max(1, min(WIDE_NODE_QUORUM, __popc(workMask) >> 1)), k3f, nodeVisits, triTests);
     }
 
     if (COUNT) {

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(WIDE_BATCH_BLOCK, 7) wideIntersectBatchKernel(
             if (exhausted) break;
             continue;
         }
-        wideRound(wide, r, c, invT.w, live, s, stack, WIDE_BATCH_BLOCK, max(1, min(TRACE_NODE_QUORUM, __popc(liveMask) >> 1)), k3f, nodeVisits, triTests);
+        wideRound(wide, r, c, invT.w, live, s, stack, WIDE_BATCH_BLOCK, max(1, min(WIDE_NODE_QUORUM, __popc(liveMask) >> 1)), k3f, nodeVisits, triTests);
         if (live && s.sp < 0) {
             float t = s.closest;
             unsigned int triId = __float_as_uint(c.rec.z);
