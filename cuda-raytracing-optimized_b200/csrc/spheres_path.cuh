@@ -78,6 +78,36 @@ __device__ __forceinline__ void testSphere(const SphereBvh& b, unsigned int k, c
     }
 }
 
+// The closest sphere along (o, d): {t, id} (FLT_MAX / ~0 = none).
+__device__ __forceinline__ void closestSphere(const SphereBvh& bvh, const f3& o, const f3& d, float& closest, unsigned int& id) {
+    const f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    closest = FLT_MAX;
+    id = 0xFFFFFFFFu;
+    for (unsigned int k = 0; k < bvh.numAlways; k++) testSphere(bvh, k, o, d, closest, id);
+    unsigned int node = 0;
+    while (node < bvh.numNodes) {
+        const float4 lo = __ldg(bvh.nodes + 2 * node);
+        const float4 hi = __ldg(bvh.nodes + 2 * node + 1);
+        // conservative slab test: fminf/fmaxf drop the NaN of 0 * inf (an axis the ray is parallel to)
+        const float x0 = (lo.x - o.x) * inv.x, x1 = (hi.x - o.x) * inv.x;
+        const float y0 = (lo.y - o.y) * inv.y, y1 = (hi.y - o.y) * inv.y;
+        const float z0 = (lo.z - o.z) * inv.z, z1 = (hi.z - o.z) * inv.z;
+        const float tEnter = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+        const float tExit = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+        const bool hitBox = tEnter <= tExit * 1.00001f + 1e-5f && tEnter <= closest;
+        const unsigned int leaf = __float_as_uint(hi.w);
+        if (!hitBox) {
+            node = __float_as_uint(lo.w); // skip the subtree
+        } else {
+            if (leaf != 0xFFFFFFFFu) {
+                const unsigned int first = leaf & 0xFFFFFFu, count = leaf >> 24;
+                for (unsigned int k = 0; k < count; k++) testSphere(bvh, first + k, o, d, closest, id);
+            }
+            node = node + 1;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(WF_BLOCK) extendSpheresBvhKernel(WfState st, const unsigned int* __restrict__ queue, SphereBvh bvh) {
     WfControl* ctl = st.ctl;
     const unsigned int n = ctl->countActive;
@@ -91,34 +121,9 @@ __global__ void __launch_bounds__(WF_BLOCK) extendSpheresBvhKernel(WfState st, c
             const unsigned int slot = queue[i];
             const float4 ro = st.rayO[slot];
             const float4 rd = st.rayD[slot];
-            const f3 o = xyz(ro);
-            const f3 d = unit(xyz(rd));
-            const f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-            float closest = FLT_MAX;
-            unsigned int id = 0xFFFFFFFFu;
-            for (unsigned int k = 0; k < bvh.numAlways; k++) testSphere(bvh, k, o, d, closest, id);
-            unsigned int node = 0;
-            while (node < bvh.numNodes) {
-                const float4 lo = __ldg(bvh.nodes + 2 * node);
-                const float4 hi = __ldg(bvh.nodes + 2 * node + 1);
-                // conservative slab test: fminf/fmaxf drop the NaN of 0 * inf (an axis the ray is parallel to)
-                const float x0 = (lo.x - o.x) * inv.x, x1 = (hi.x - o.x) * inv.x;
-                const float y0 = (lo.y - o.y) * inv.y, y1 = (hi.y - o.y) * inv.y;
-                const float z0 = (lo.z - o.z) * inv.z, z1 = (hi.z - o.z) * inv.z;
-                const float tEnter = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
-                const float tExit = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
-                const bool hitBox = tEnter <= tExit * 1.00001f + 1e-5f && tEnter <= closest;
-                const unsigned int leaf = __float_as_uint(hi.w);
-                if (!hitBox) {
-                    node = __float_as_uint(lo.w); // skip the subtree
-                } else {
-                    if (leaf != 0xFFFFFFFFu) {
-                        const unsigned int first = leaf & 0xFFFFFFu, count = leaf >> 24;
-                        for (unsigned int k = 0; k < count; k++) testSphere(bvh, first + k, o, d, closest, id);
-                    }
-                    node = node + 1;
-                }
-            }
+            float closest;
+            unsigned int id;
+            closestSphere(bvh, xyz(ro), unit(xyz(rd)), closest, id);
             st.hit[slot] = make_float4(closest, 0.0f, 0.0f, __uint_as_float(id));
         }
     }
@@ -127,20 +132,12 @@ __global__ void __launch_bounds__(WF_BLOCK) extendSpheresBvhKernel(WfState st, c
 // Shade + retire + regenerate + advance in one launch (an iteration is extend, then this): when a path ends its colour goes
 // into the pixel (col += p.color, kernels.cu:558, in sample order: one slot per pixel) and the slot's next sample starts
 // right here (kernels.cu:549-555) instead of in a separate raygen pass; the last block to finish swaps the queues.
-__global__ void __launch_bounds__(WF_BLOCK) shadeSpheresKernel(WfState st, const float4* __restrict__ mats, int maxDepth,
-                                                               const unsigned int* __restrict__ queue, unsigned int* __restrict__ nextQueue,
-                                                               CameraDev cam, int nx, int ny, int samplesPerSlot, int slotsPerPixel) {
-    WfControl* ctl = st.ctl;
-    const unsigned int n = ctl->countActive;
-    const unsigned int npix = (unsigned int)nx * (unsigned int)ny;
-    const unsigned int stride = gridDim.x * blockDim.x;
-    for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
-        const unsigned int i = base + laneId();
-        bool continues = false;
-        unsigned int slot = 0;
-        if (i < n) {
-            slot = queue[i];
-            const float4 h = st.hit[slot];
+// Everything between two closest-sphere queries of one path slot whose hit record is `h` (color()'s loop body, kernels.cu:402-531,
+// without light and shadow rays): sky gradient on a miss, scatter, Russian roulette; when the path ends, col += p.color and the
+// slot's next camera ray. Returns whether the slot has another ray to trace. Shared by shadeSpheresKernel and finishSpheresKernel.
+__device__ __forceinline__ bool shadeSphereSlot(const WfState& st, const float4* __restrict__ mats, int maxDepth, const CameraDev& cam, int nx, int ny,
+                                                int samplesPerSlot, int slotsPerPixel, unsigned int npix, unsigned int slot, const float4& h) {
+    bool continues = false;
             const float4 ro = st.rayO[slot];
             const float4 rd = st.rayD[slot];
             f3 origin = xyz(ro), dir = xyz(rd);
@@ -222,6 +219,23 @@ __global__ void __launch_bounds__(WF_BLOCK) shadeSpheresKernel(WfState st, const
                     continues = true;
                 }
             }
+    return continues;
+}
+
+__global__ void __launch_bounds__(WF_BLOCK) shadeSpheresKernel(WfState st, const float4* __restrict__ mats, int maxDepth,
+                                                               const unsigned int* __restrict__ queue, unsigned int* __restrict__ nextQueue,
+                                                               CameraDev cam, int nx, int ny, int samplesPerSlot, int slotsPerPixel) {
+    WfControl* ctl = st.ctl;
+    const unsigned int n = ctl->countActive;
+    const unsigned int npix = (unsigned int)nx * (unsigned int)ny;
+    const unsigned int stride = gridDim.x * blockDim.x;
+    for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        const unsigned int i = base + laneId();
+        bool continues = false;
+        unsigned int slot = 0;
+        if (i < n) {
+            slot = queue[i];
+            continues = shadeSphereSlot(st, mats, maxDepth, cam, nx, ny, samplesPerSlot, slotsPerPixel, npix, slot, st.hit[slot]);
         }
         const unsigned int posNext = warpAppend(continues, &ctl->countNext);
         if (continues) nextQueue[posNext] = slot;
@@ -244,6 +258,34 @@ __global__ void __launch_bounds__(WF_BLOCK) shadeSpheresKernel(WfState st, const
         ctl->blocksDone = 0;
     }
 }
+
+// The tail of a frame: when few slots are left (the heaviest pixels: every pixel's samples are one sequential chain,
+// kernels.cu:542-548), iterating two launches per bounce over a nearly empty queue is mostly launch latency (1011 iterations for
+// a 220-iteration bulk). One thread per remaining slot then runs the slot to its last sample with the same two device functions.
+__global__ void __launch_bounds__(128) finishSpheresKernel(WfState st, const float4* __restrict__ mats, int maxDepth, const unsigned int* __restrict__ queue,
+                                                           SphereBvh bvh, CameraDev cam, int nx, int ny, int samplesPerSlot, int slotsPerPixel) {
+    WfControl* ctl = st.ctl;
+    const unsigned int n = ctl->countActive;
+    const unsigned int npix = (unsigned int)nx * (unsigned int)ny;
+    unsigned long long rays = 0;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned int slot = queue[i];
+        bool continues = true;
+        while (continues) {
+            const float4 ro = st.rayO[slot];
+            const float4 rd = st.rayD[slot];
+            float closest;
+            unsigned int id;
+            closestSphere(bvh, xyz(ro), unit(xyz(rd)), closest, id);
+            rays++;
+            continues = shadeSphereSlot(st, mats, maxDepth, cam, nx, ny, samplesPerSlot, slotsPerPixel, npix, slot, make_float4(closest, 0.0f, 0.0f, __uint_as_float(id)));
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(0xFFFFFFFFu, rays, o);
+    if (laneId() == 0 && rays) atomicAdd(&ctl->raysExtend, rays);
+}
+
+__global__ void finishSpheresDoneKernel(WfControl* ctl) { ctl->countActive = 0; }
 
 // Host side of the sphere BVH (layout: SphereBvh above). Median split of the centroids along the longest axis.
 static SphereBvh g_sphereBvh;
@@ -378,6 +420,7 @@ void crtRunSpheres(RendererContext& c, int ns) {
         launches += 2;
         int batch = c.opts.megaBatch > 0 ? c.opts.megaBatch : 16;
         batch = (batch + 1) & ~1;
+        const unsigned int finishBelow = std::getenv("CRT_SPHERES_FINISH") ? (unsigned int)std::atoi(std::getenv("CRT_SPHERES_FINISH")) : 131072u; // 0: wavefront to the end (measured on config 2: 0 -> 70.6 ms, 16 Ki -> 57.8, 48 Ki -> 56.1, 128 Ki -> 53.6, 400 k -> 55.8)
         const long long key = ((long long)samplesPerSlot << 24) ^ ((long long)slotsPerPixel << 8) ^ batch ^ (1LL << 61) ^
                               ((long long)c.maxDepth << 40) ^ ((long long)g_spheresBrute << 58);
         if (!c.graphExec || c.graphKey != key) {
@@ -400,6 +443,15 @@ void crtRunSpheres(RendererContext& c, int ns) {
             CRT_CHECK(cudaMemcpyAsync(c.hostCtl, c.wf.ctl, sizeof(WfControl), cudaMemcpyDeviceToHost, stream));
             CRT_CHECK(cudaStreamSynchronize(stream));
             if (c.hostCtl->countActive == 0) break;
+            if (!g_spheresBrute && c.hostCtl->countActive <= finishBelow) { // the tail: one thread per remaining slot (batch is even: the live queue is queueA)
+                finishSpheresKernel<<<(c.hostCtl->countActive + 127) / 128, 128, 0, stream>>>(c.wf, c.materials, c.maxDepth, c.wf.queueA, g_sphereBvh, c.cam, c.nx,
+                                                                                            c.ny, samplesPerSlot, slotsPerPixel);
+                finishSpheresDoneKernel<<<1, 1, 0, stream>>>(c.wf.ctl);
+                launches += 2;
+                CRT_CHECK(cudaMemcpyAsync(c.hostCtl, c.wf.ctl, sizeof(WfControl), cudaMemcpyDeviceToHost, stream));
+                CRT_CHECK(cudaStreamSynchronize(stream));
+                break;
+            }
         }
     } else {
         CRT_CHECK(cudaMemcpyAsync(c.hostCtl, c.wf.ctl, sizeof(WfControl), cudaMemcpyDeviceToHost, stream));
