@@ -594,6 +594,9 @@ extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb,
         c.opts.sampleStream = c.opts.sampleStream * (unsigned int)crtRequestedGpus();
         pt.mark("init: worker devices");
     }
+    // the uploads and scene kernels above ran on the legacy stream (some from pageable memory); the frame runs on non-blocking
+    // streams, which do not order against it
+    CRT_CHECK(cudaDeviceSynchronize());
 }
 
 static bool useWideTree(const RendererContext& c) { return c.wide.stackDepth > 0 && c.traversal != TRAVERSAL_EXACT; }
@@ -1032,6 +1035,9 @@ extern "C" void setRendererAccumDevice(void* dAccum) {
     if (!c.initialised || !dAccum) return;
     c.wf.accum = (float4*)dAccum;
     c.ownsAccum = false;
+    // the captured graph bakes the accumulator pointer into its kernel nodes (MeshState by value): capture again
+    if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
+    c.graphKey = -1;
 }
 
 extern "C" void getRendererStats(renderer_stats* out) {
@@ -1211,6 +1217,7 @@ extern "C" void intersectBatch(const float* origins, const float* dirs, long lon
     CRT_CHECK(cudaMalloc((void**)&dM, (size_t)n * sizeof(int)));
     CRT_CHECK(cudaMemcpy(dO, o.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice));
     CRT_CHECK(cudaMemcpy(dD, d.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice));
+    CRT_CHECK(cudaDeviceSynchronize()); // (pageable copies: the query runs on a non-blocking stream)
     intersectBatchDevice(dO, dD, n, dH, dM);
     std::vector<float4> h((size_t)n);
     CRT_CHECK(cudaMemcpy(h.data(), dH, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));

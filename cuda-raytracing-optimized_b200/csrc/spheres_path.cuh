@@ -383,6 +383,7 @@ extern "C" void initRendererSpheres(const sphere* spheres, const material* mater
     buildSphereBvh(c, sp, n);
     c.materials = (float4*)arenaAlloc(mats.size() * sizeof(float4));
     CRT_CHECK(cudaMemcpy(c.materials, mats.data(), mats.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CRT_CHECK(cudaDeviceSynchronize()); // the uploads ran on the legacy stream, the frame runs on non-blocking streams
 }
 
 static bool g_spheresBrute = false; // CRT_SPHERES_BRUTE=1: all spheres from __constant__ for every ray (tests compare the two)
