@@ -576,14 +576,17 @@ __global__ void __launch_bounds__(WIDE_TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wi
                     if (!isShadow) {
                         st.hit[slot] = make_float4(s.closest, c.rec.x, c.rec.y, c.rec.z);
                     } else {
+                        // (the three records are requested together: which of the two colours is needed depends on the first)
                         const float4 l = st.shL[slot];
+                        const float4 carried = st.shC[slot];
+                        const float4 running = st.pcol[slot];
                         const bool unoccluded = !(s.closest < c.dir.w); // hit(...) false: p.color += p.lightContribution (kernels.cu:500-508)
                         if (__float_as_uint(l.w) & SHADOW_FLAG_FINAL) {
-                            float4 col = st.shC[slot];
+                            float4 col = carried;
                             if (unoccluded) { col.x += l.x; col.y += l.y; col.z += l.z; }
                             accumulatePixel(st, slotPixel(st, slot), col.x, col.y, col.z); // col += p.color (kernels.cu:558)
                         } else if (unoccluded) {
-                            float4 col = st.pcol[slot];
+                            float4 col = running;
                             col.x += l.x; col.y += l.y; col.z += l.z;
                             st.pcol[slot] = col;
                         }
