@@ -260,7 +260,8 @@ static void initCommon(RendererContext& c, const camera& cam, vec3** fb, int nx,
             int prLow = 0, prHigh = 0;
             CRT_CHECK(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
             CRT_CHECK(cudaStreamCreateWithPriority(&g_cache.streamFast, cudaStreamNonBlocking, prHigh));
-            for (auto& cs : g_cache.chaseStreams) CRT_CHECK(cudaStreamCreateWithPriority(&cs, cudaStreamNonBlocking, prHigh));
+            const bool chaseLow = std::getenv("CRT_CHASE_PRIORITY") && std::getenv("CRT_CHASE_PRIORITY")[0] == 'l'; // (experiment)
+            for (auto& cs : g_cache.chaseStreams) CRT_CHECK(cudaStreamCreateWithPriority(&cs, cudaStreamNonBlocking, chaseLow ? prLow : prHigh));
             CRT_CHECK(cudaEventCreateWithFlags(&g_cache.evLane, cudaEventDisableTiming));
             CRT_CHECK(cudaEventCreate(&g_cache.evStart));
             CRT_CHECK(cudaEventCreate(&g_cache.evStop));
