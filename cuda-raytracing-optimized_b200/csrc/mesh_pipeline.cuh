@@ -498,8 +498,10 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(
 // ------------------------------------------------------------- wide trace --
 // The same job as traceKernel over the renderer's own wide tree (wide_traverse.cuh): persistent warps, idle lanes refilled
 // from the queue with one atomic per warp, finished rays retired in batches. Every finished ray that found a triangle is
-// certified against the caller's tree; what cannot be certified (and rays the wide arithmetic does not cover) goes to
-// redoQ and is traced by traceKernel<.., REDO> right after this launch, before the iteration's shade kernel.
+// certified against the caller's tree. What cannot be certified is appended to the NEXT iteration's trace queue with
+// ENTRY_RESUME set; the lane that receives such an entry (or a ray the wide arithmetic does not cover) walks it right at the
+// refill in the reference's order over the caller's tree (travRound), so its slot is simply one iteration late. (A separate
+// launch for those ~14 rays per iteration put ~60 us of serial traversal latency on every iteration's critical path.)
 // There is no step budget and no parking: the traversal stack lives in shared memory (wide.stackDepth entries per thread).
 #ifndef WIDE_TRACE_BLOCK
 #define WIDE_TRACE_BLOCK 128
@@ -571,7 +573,7 @@ __global__ void __launch_bounds__(WIDE_TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wi
             bool redo = false;
             if (finished) {
                 const unsigned int winner = __float_as_uint(c.rec.z);
-                if (CERTIFY && winner != 0xFFFFFFFFu) redo = !wideCertify(mesh, r, xyz(invT), c.dir.w, s.closest, winner);
+                if (CERTIFY && winner != 0xFFFFFFFFu && !(r.oct & WIDE_FLAG_EXACT)) redo = !wideCertify(mesh, r, xyz(invT), c.dir.w, s.closest, winner);
                 if (!redo) {
                     if (!isShadow) {
                         st.hit[slot] = make_float4(s.closest, c.rec.x, c.rec.y, c.rec.z);
@@ -599,11 +601,13 @@ __global__ void __launch_bounds__(WIDE_TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wi
             const unsigned int mShade = __ballot_sync(0xFFFFFFFFu, toShade);
             const unsigned int mShadowDone = __ballot_sync(0xFFFFFFFFu, finished && !redo && isShadow);
             const unsigned int mRedo = __ballot_sync(0xFFFFFFFFu, redo);
+            const unsigned int mExactDone = __ballot_sync(0xFFFFFFFFu, finished && (r.oct & WIDE_FLAG_EXACT) != 0u);
             unsigned int baseShade = 0, baseRedo = 0;
             if (lane == 0) {
                 if (mShade) { baseShade = atomicAdd(&ctl->shadeCount[cur], __popc(mShade)); atomicAdd(&ctl->raysExtend, (unsigned long long)__popc(mShade)); }
                 if (mShadowDone) atomicAdd(&ctl->raysShadow, (unsigned long long)__popc(mShadowDone));
-                if (mRedo) baseRedo = atomicAdd(&ctl->redoCount, __popc(mRedo));
+                if (mRedo) baseRedo = atomicAdd(&ctl->traceCount[cur ^ 1], __popc(mRedo));
+                if (mExactDone) atomicAdd(&ctl->redone, (unsigned long long)__popc(mExactDone));
             }
             baseShade = __shfl_sync(0xFFFFFFFFu, baseShade, 0);
             baseRedo = __shfl_sync(0xFFFFFFFFu, baseRedo, 0);
@@ -612,7 +616,7 @@ __global__ void __launch_bounds__(WIDE_TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wi
                 shadeQ[baseShade + __popc(mShade & below)] = slot;
                 st.ready[slot] = 1;
             }
-            if (redo) st.redoQ[baseRedo + __popc(mRedo & below)] = entry;
+            if (redo) st.traceQ[cur ^ 1][baseRedo + __popc(mRedo & below)] = entry | ENTRY_RESUME; // next iteration, in the reference's order
 
             // ---- refill idle lanes, one atomic per warp
             if (!exhausted) {
@@ -624,10 +628,9 @@ __global__ void __launch_bounds__(WIDE_TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wi
                 if (base + count >= n) warpFlagSet(exhaustedBase); // warp-uniform: the tail of the queue has been handed out
                 const unsigned int rank = __popc(idle & below);
                 const unsigned int i = base + rank;
-                bool direct = false; // the ray goes to the exact kernel untraced
-                unsigned int e = 0;
+                bool exact = false, exactShadow = false; // this lane's ray is walked in the reference's order (below)
                 if (!live && rank < count && i < n) {
-                    e = queue[i];
+                    const unsigned int e = queue[i];
                     const unsigned int sl = e & ENTRY_SLOT_MASK;
                     const bool shadow = (e & ENTRY_SHADOW) != 0u;
                     const float4 ro = shadow ? st.shO[sl] : st.rayO[sl];
@@ -635,27 +638,36 @@ __global__ void __launch_bounds__(WIDE_TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wi
                     const float tMax = shadow ? rd.w : FLT_MAX;
                     const f3 d = unit(xyz(rd)); // hit(): ray(p.origin, dir) normalises again (kernels.cu:326)
                     c.dir = mk4(d, tMax);
-                    c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), __uint_as_float(e));
+                    c.rec = make_float4(0.0f, 0.0f, __uint_as_float(0xFFFFFFFFu), __uint_as_float(e & ~ENTRY_RESUME));
                     f3 inv;
                     const bool covered = wideSetup(wide, r, xyz(ro), d, shadow, inv);
                     invT = mk4(inv, 0.0f);
-                    if (!covered || (e & ENTRY_RESUME)) {
-                        direct = true;
-                    } else {
-                        wideStart(s, tMax);
-                        if (!wideHitsBounds(mesh, r, inv, tMax)) { // hitMesh: scene bounds first (kernels.cu:297)
-                            s.sp = -1;
-                            s.closest = FLT_MAX;
-                        }
-                        live = true;
+                    wideStart(s, tMax);
+                    if (!wideHitsBounds(mesh, r, inv, tMax)) { // hitMesh: scene bounds first (kernels.cu:297)
+                        s.sp = -1;
+                        s.closest = FLT_MAX;
+                    } else if (!covered || (e & ENTRY_RESUME)) {
+                        exact = true;
+                        exactShadow = shadow;
                     }
+                    live = true;
                 }
-                const unsigned int mDirect = __ballot_sync(0xFFFFFFFFu, direct);
-                if (mDirect) {
-                    unsigned int b = 0;
-                    if (lane == 0) b = atomicAdd(&ctl->redoCount, __popc(mDirect));
-                    b = __shfl_sync(0xFFFFFFFFu, b, 0);
-                    if (direct) st.redoQ[b + __popc(mDirect & below)] = e;
+                if (__any_sync(0xFFFFFFFFu, exact)) {
+                    // the rays the certificate rejected last iteration, and rays outside the wide arithmetic's range: the caller's
+                    // tree in the reference's order, by the lanes concerned, here and now (a handful per launch)
+                    RayHot rh;
+                    rh.ox = r.ox; rh.oy = r.oy; rh.oz = r.oz;
+                    rh.ix = invT.x; rh.iy = invT.y; rh.iz = invT.z;
+                    TravHot th;
+                    th.idx = exact ? 1u : 0u; th.bitStack = 1u; th.closest = c.dir.w;
+                    int steps = 0;
+                    while (__any_sync(0xFFFFFFFFu, th.idx != 0u))
+                        travRound<true>(mesh, rh, c, RT_EPSILON, exactShadow, th.idx != 0u, th, steps, 1, nodeVisits, triTests);
+                    if (exact) {
+                        s.closest = th.closest;
+                        s.sp = -1;
+                        r.oct |= WIDE_FLAG_EXACT;
+                    }
                 }
             }
             if (!__any_sync(0xFFFFFFFFu, live)) {

@@ -635,8 +635,6 @@ static void launchWideTrace(RendererContext& c, const MeshState& mp, cudaStream_
         if (certify) wideTraceKernel<false, CUR, true><<<traceBlocks, WIDE_TRACE_BLOCK, smem, stream>>>(mp, c.mesh, wv);
         else wideTraceKernel<false, CUR, false><<<traceBlocks, WIDE_TRACE_BLOCK, smem, stream>>>(mp, c.mesh, wv);
     }
-    // what the wide walk could not certify, in the reference's order over the caller's tree (usually a handful of rays)
-    traceKernel<false, CUR, true><<<c.numSMs, TRACE_BLOCK, 0, stream>>>(mp, c.mesh);
 }
 
 // One wavefront iteration on `stream`: trace (extend + shadow rays) -> shade (+ retire sample, + next camera ray).
@@ -722,7 +720,7 @@ void crtRunMesh(RendererContext& c, int ns, bool resume) {
         }
         if (std::getenv("CRT_TIMING")) std::fprintf(stderr, "[crt timing] wide trace: %d blocks/SM, %zu B shared per block, carve-out %d %%\n", perSM, (size_t)fa.sharedSizeBytes + smem, pct);
     }
-    const int kernelsPerIteration = useWideTree(c) ? 3 : 2;
+    const int kernelsPerIteration = 2;
     cudaStream_t stream = c.stream;
 
     std::memset(&c.stats, 0, sizeof(c.stats));

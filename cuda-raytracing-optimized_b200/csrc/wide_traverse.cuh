@@ -29,6 +29,7 @@
 #endif
 #define WIDE_FLAG_TIE 0x100u     // WideRay::oct: a second triangle within the margin of the current best was seen
 #define WIDE_FLAG_ANYHIT 0x200u
+#define WIDE_FLAG_EXACT 0x400u   // the record was produced by the order-exact walk: nothing to certify
 
 struct WideView {
     const uint4* __restrict__ nodes;   // 96-byte records (wide_bvh.h)
