@@ -509,6 +509,12 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(
 #ifndef WIDE_TRACE_BLOCKS_PER_SM
 #define WIDE_TRACE_BLOCKS_PER_SM 7 // 72 registers, no spills (256 x 4 = 64 registers spilled 24 bytes inside the node step; same speed)
 #endif
+#ifndef WIDE_ENDGAME
+#define WIDE_ENDGAME 24u
+#endif
+#ifndef WIDE_ENDGAME_MIN
+#define WIDE_ENDGAME_MIN 2u
+#endif
 #ifndef WIDE_TRACE_MIN_ACTIVE
 #define WIDE_TRACE_MIN_ACTIVE 14 // refill when fewer lanes than this hold a ray: a refill pass costs ~300 instructions (measured: 14 < 20 < 24 < 28)
 #endif
@@ -529,13 +535,14 @@ __global__ void __launch_bounds__(WIDE_TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wi
     // measure as in traceKernel: held in registers across the traversal loop they cost spills under the 64-register cap)
     __shared__ unsigned int takeShared, countShared;
     __shared__ unsigned char exhaustedShared[WIDE_TRACE_BLOCK / 32];
+    __shared__ unsigned int lastBaseShared[WIDE_TRACE_BLOCK / 32]; // the queue position this warp's last refill started at
     if (threadIdx.x == 0) {
         const unsigned int count = ctl->traceCount[cur];
         const unsigned int totalWarps = gridDim.x * (WIDE_TRACE_BLOCK / 32);
         countShared = count;
         takeShared = min(32u, max(1u, (count + totalWarps - 1) / totalWarps)); // short queue: spread the rays over all warps
     }
-    if (threadIdx.x < WIDE_TRACE_BLOCK / 32) exhaustedShared[threadIdx.x] = 0;
+    if (threadIdx.x < WIDE_TRACE_BLOCK / 32) { exhaustedShared[threadIdx.x] = 0; lastBaseShared[threadIdx.x] = 0u; }
     __syncthreads();
     const volatile unsigned int* takePtr = &takeShared;
     const volatile unsigned int* countPtr = &countShared;
@@ -621,10 +628,22 @@ __global__ void __launch_bounds__(WIDE_TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wi
             // ---- refill idle lanes, one atomic per warp
             if (!exhausted) {
                 const unsigned int idle = ~workMask;
-                const unsigned int count = tail ? min((unsigned int)__popc(idle), take - (unsigned int)__popc(workMask)) : (unsigned int)__popc(idle);
+                unsigned int count = tail ? min((unsigned int)__popc(idle), take - (unsigned int)__popc(workMask)) : (unsigned int)__popc(idle);
+#ifndef WIDE_NO_ENDGAME
+                {   // the end of the queue: when (by this warp's last look at the cursor) less than WIDE_ENDGAME rays per warp are left,
+                    // a warp takes its share of what is left instead of filling every idle lane, so that the warps run out of work
+                    // together and the launch does not wait for the few that took a full batch last
+                    const volatile unsigned int* lastBase = &lastBaseShared[threadIdx.x >> 5];
+                    const unsigned int left = n - min(n, *lastBase), warps = gridDim.x * (WIDE_TRACE_BLOCK / 32);
+                    if (left < WIDE_ENDGAME * warps) count = min(count, max(WIDE_ENDGAME_MIN, left / warps));
+                }
+#endif
                 unsigned int base = 0;
                 if (lane == 0) base = atomicAdd(&ctl->traceCursor, count);
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
+#ifndef WIDE_NO_ENDGAME
+                if (lane == 0) lastBaseShared[threadIdx.x >> 5] = base + count;
+#endif
                 if (base + count >= n) warpFlagSet(exhaustedBase); // warp-uniform: the tail of the queue has been handed out
                 const unsigned int rank = __popc(idle & below);
                 const unsigned int i = base + rank;
