@@ -737,8 +737,9 @@ __global__ void __launch_bounds__(WF_BLOCK, 4) meshShadeKernel(MeshState st, Sha
     unsigned int* __restrict__ nextShade = st.shadeQ[cur ^ 1];
     const unsigned int stride = gridDim.x * blockDim.x;
     unsigned int deferredCount = 0;
-    for (unsigned int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
-        const unsigned int i = base + laneId();
+    __shared__ unsigned int appendS[WF_BLOCK / 32], appendE[WF_BLOCK / 32], appendBase;
+    for (unsigned int blockBase = blockIdx.x * blockDim.x; blockBase < n; blockBase += stride) { // (same trip count for every warp of the block)
+        const unsigned int i = blockBase + threadIdx.x;
         bool traceNext = false, castsShadow = false, defer = false;
         unsigned int slot = 0;
         if (i < n) {
@@ -774,17 +775,26 @@ __global__ void __launch_bounds__(WF_BLOCK, 4) meshShadeKernel(MeshState st, Sha
         }
         const unsigned int posDefer = warpAppend(defer, &ctl->shadeCount[cur ^ 1]);
         if (defer) { nextShade[posDefer] = slot; deferredCount++; }
-        // extend and shadow entries of a warp go out with one atomic
+        // the extend and shadow entries of the BLOCK go out with one atomic, all its shadow entries first, then all its extend
+        // entries: runs of ~150 / ~250 rays of one kind, so that a refill of the trace kernel (14-18 lanes) gets rays of one kind --
+        // any-hit walks are a third as long as closest-hit walks, and lanes that finish early idle until the next refill
         const unsigned int mE = __ballot_sync(0xFFFFFFFFu, traceNext), mS = __ballot_sync(0xFFFFFFFFu, castsShadow);
-        const unsigned int total = __popc(mE) + __popc(mS);
-        if (total) {
-            unsigned int basePos = 0;
-            if (laneId() == 0) basePos = atomicAdd(&ctl->traceCount[cur ^ 1], total);
-            basePos = __shfl_sync(0xFFFFFFFFu, basePos, 0);
-            const unsigned int below = (1u << laneId()) - 1u;
-            if (castsShadow) nextTrace[basePos + __popc(mS & below)] = slot | ENTRY_SHADOW; // shadow rays first: they unblock the slot
-            if (traceNext) nextTrace[basePos + __popc(mS) + __popc(mE & below)] = slot;
+        const unsigned int warp = threadIdx.x >> 5;
+        if (laneId() == 0) { appendS[warp] = __popc(mS); appendE[warp] = __popc(mE); }
+        __syncthreads();
+        unsigned int totalS = 0, totalE = 0, beforeS = 0, beforeE = 0;
+#pragma unroll
+        for (unsigned int k = 0; k < WF_BLOCK / 32; k++) {
+            const unsigned int cs = appendS[k], ce = appendE[k];
+            if (k < warp) { beforeS += cs; beforeE += ce; }
+            totalS += cs; totalE += ce;
         }
+        if (threadIdx.x == 0 && totalS + totalE) appendBase = atomicAdd(&ctl->traceCount[cur ^ 1], totalS + totalE);
+        __syncthreads();
+        const unsigned int basePos = appendBase;
+        const unsigned int below = (1u << laneId()) - 1u;
+        if (castsShadow) nextTrace[basePos + beforeS + __popc(mS & below)] = slot | ENTRY_SHADOW; // shadow rays first: they unblock the slot
+        if (traceNext) nextTrace[basePos + totalS + beforeE + __popc(mE & below)] = slot;
     }
     if (deferredCount) atomicAdd(&ctl->deferred, (unsigned long long)deferredCount);
 
