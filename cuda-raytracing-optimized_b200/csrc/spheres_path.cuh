@@ -85,26 +85,30 @@ __device__ __forceinline__ void closestSphere(const SphereBvh& bvh, const f3& o,
     id = 0xFFFFFFFFu;
     for (unsigned int k = 0; k < bvh.numAlways; k++) testSphere(bvh, k, o, d, closest, id);
     unsigned int node = 0;
-    while (node < bvh.numNodes) {
-        const float4 lo = __ldg(bvh.nodes + 2 * node);
-        const float4 hi = __ldg(bvh.nodes + 2 * node + 1);
-        // conservative slab test: fminf/fmaxf drop the NaN of 0 * inf (an axis the ray is parallel to)
-        const float x0 = (lo.x - o.x) * inv.x, x1 = (hi.x - o.x) * inv.x;
-        const float y0 = (lo.y - o.y) * inv.y, y1 = (hi.y - o.y) * inv.y;
-        const float z0 = (lo.z - o.z) * inv.z, z1 = (hi.z - o.z) * inv.z;
-        const float tEnter = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
-        const float tExit = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
-        const bool hitBox = tEnter <= tExit * 1.00001f + 1e-5f && tEnter <= closest;
-        const unsigned int leaf = __float_as_uint(hi.w);
-        if (!hitBox) {
-            node = __float_as_uint(lo.w); // skip the subtree
-        } else {
-            if (leaf != 0xFFFFFFFFu) {
-                const unsigned int first = leaf & 0xFFFFFFu, count = leaf >> 24;
-                for (unsigned int k = 0; k < count; k++) testSphere(bvh, first + k, o, d, closest, id);
+    while (true) {
+        // box phase: every lane walks on until it stands in a leaf (or its walk ends); the leaves' sphere tests then run for all
+        // those lanes together instead of one lane at a time inside the walk
+        unsigned int leaf = 0u; // count << 24 | first; 0 = none
+        while (node < bvh.numNodes) {
+            const float4 lo = __ldg(bvh.nodes + 2 * node);
+            const float4 hi = __ldg(bvh.nodes + 2 * node + 1);
+            // conservative slab test: fminf/fmaxf drop the NaN of 0 * inf (an axis the ray is parallel to)
+            const float x0 = (lo.x - o.x) * inv.x, x1 = (hi.x - o.x) * inv.x;
+            const float y0 = (lo.y - o.y) * inv.y, y1 = (hi.y - o.y) * inv.y;
+            const float z0 = (lo.z - o.z) * inv.z, z1 = (hi.z - o.z) * inv.z;
+            const float tEnter = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+            const float tExit = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+            const bool hitBox = tEnter <= tExit * 1.00001f + 1e-5f && tEnter <= closest;
+            const unsigned int word = __float_as_uint(hi.w);
+            node = hitBox ? node + 1 : __float_as_uint(lo.w); // into the subtree, or past it
+            if (hitBox && word != 0xFFFFFFFFu) {
+                leaf = word;
+                break;
             }
-            node = node + 1;
         }
+        if (leaf == 0u) break;
+        const unsigned int first = leaf & 0xFFFFFFu, count = leaf >> 24;
+        for (unsigned int k = 0; k < count; k++) testSphere(bvh, first + k, o, d, closest, id);
     }
 }
 
@@ -129,96 +133,114 @@ __global__ void __launch_bounds__(WF_BLOCK) extendSpheresBvhKernel(WfState st, c
     }
 }
 
+// ---- one path, in registers ------------------------------------------------------------------------------------------
+// color()'s loop body (kernels.cu:402-531, without light and shadow rays) on a path held in registers; the wavefront kernels
+// load / store it around these two functions, the persistent kernel keeps it in registers for the whole pixel.
+struct SpherePath {
+    f3 origin, dir, att, col;
+    unsigned int rng, flags; // flags: PATH_BOUNCE_MASK | PATH_FLAG_*
+};
+
+// The next camera ray of `pixel` from the path's RNG stream (kernels.cu:549-555).
+__device__ __forceinline__ void startSpherePath(SpherePath& p, const CameraDev& cam, int nx, int ny, unsigned int pixel) {
+    const int px = (int)(pixel % (unsigned int)nx), py = (int)(pixel / (unsigned int)nx);
+    const float u = float(px + rnd(p.rng)) / float(nx);
+    const float v = float(py + rnd(p.rng)) / float(ny);
+    cameraRay(cam, u, v, p.rng, p.origin, p.dir);
+    p.flags = 0u; // bounce 0, specular = inside = false (kernels.cu:554-555)
+    p.att = mk3(1.0f, 1.0f, 1.0f);
+    p.col = mk3(0.0f, 0.0f, 0.0f);
+}
+
+// Everything between two closest-sphere queries of one path whose hit record is `h`: sky gradient on a miss, scatter, Russian
+// roulette. Returns whether the path has another ray to trace; when it has not, p.col is the sample's colour.
+__device__ __forceinline__ bool scatterSpherePath(SpherePath& p, const float4* __restrict__ mats, int maxDepth, const float4& h) {
+    if (!(h.x < FLT_MAX)) {
+        // sky gradient, kernels.cu:419-421
+        const float t = 0.5f * (p.dir.y + 1.0f);
+        const f3 c = (1.0f - t) * mk3(1.0f, 1.0f, 1.0f) + t * mk3(0.5f, 0.7f, 1.0f);
+        const f3 add = p.att * c;
+        p.col.x += add.x; p.col.y += add.y; p.col.z += add.z;
+        return false;
+    }
+    bool inside = (p.flags & PATH_FLAG_INSIDE) != 0u;
+    unsigned int bounce = p.flags & PATH_BOUNCE_MASK;
+    const unsigned int id = __float_as_uint(h.w);
+    const float4 sp = c_spheres[id];
+    const f3 rdir = unit(p.dir);
+    const f3 hp = p.origin + h.x * rdir; // point_at_parameter on the traced (normalised) ray
+    SurfacePoint s;
+    s.normal = (hp - xyz(sp)) / sp.w;
+    s.t = h.x;
+    s.inside = inside;
+    if (dot(rdir, s.normal) > 0.0f) s.normal = -s.normal;
+    const float4 m0 = __ldg(mats + 2 * id);
+    const float4 m1 = __ldg(mats + 2 * id + 1);
+    Scatter scat;
+    scat.specular = false;
+    scat.throughput = mk3(1.0f, 1.0f, 1.0f);
+    scat.refracted = false;
+    scat.t = h.x;
+    scat.wi = mk3(0.0f, 0.0f, 0.0f);
+    materialScatter(scat, s, p.dir, __float_as_int(m1.x), m0.w, xyz(m0), p.rng);
+    p.origin = p.origin + scat.t * p.dir;
+    p.dir = scat.wi;
+    p.att = p.att * scat.throughput;
+    inside = scat.refracted ? !inside : inside;
+    bool continues = true;
+    if (bounce > 3u) {
+        const float m = maxcomp(p.att);
+        if (rnd(p.rng) > m) continues = false;
+        else p.att = p.att * (1 / m);
+    }
+    if (continues) {
+        bounce = (bounce + 1u) & PATH_BOUNCE_MASK;
+        if (!((int)bounce < maxDepth)) continues = false;
+    }
+    p.flags = bounce | (scat.specular ? PATH_FLAG_SPECULAR : 0u) | (inside ? PATH_FLAG_INSIDE : 0u);
+    return continues;
+}
+
 // Shade + retire + regenerate + advance in one launch (an iteration is extend, then this): when a path ends its colour goes
 // into the pixel (col += p.color, kernels.cu:558, in sample order: one slot per pixel) and the slot's next sample starts
 // right here (kernels.cu:549-555) instead of in a separate raygen pass; the last block to finish swaps the queues.
-// Everything between two closest-sphere queries of one path slot whose hit record is `h` (color()'s loop body, kernels.cu:402-531,
-// without light and shadow rays): sky gradient on a miss, scatter, Russian roulette; when the path ends, col += p.color and the
-// slot's next camera ray. Returns whether the slot has another ray to trace. Shared by shadeSpheresKernel and finishSpheresKernel.
+// Returns whether the slot has another ray to trace. Shared by shadeSpheresKernel and finishSpheresKernel.
 __device__ __forceinline__ bool shadeSphereSlot(const WfState& st, const float4* __restrict__ mats, int maxDepth, const CameraDev& cam, int nx, int ny,
                                                 int samplesPerSlot, int slotsPerPixel, unsigned int npix, unsigned int slot, const float4& h) {
-    bool continues = false;
-            const float4 ro = st.rayO[slot];
-            const float4 rd = st.rayD[slot];
-            f3 origin = xyz(ro), dir = xyz(rd);
-            unsigned int rng = __float_as_uint(ro.w);
-            unsigned int flags = __float_as_uint(rd.w);
-            bool inside = (flags & PATH_FLAG_INSIDE) != 0u;
-            unsigned int bounce = flags & PATH_BOUNCE_MASK;
-            const float4 att4 = st.atten[slot];
-            f3 att = xyz(att4);
-            float4 pc = st.pcol[slot];
-            if (!(h.x < FLT_MAX)) {
-                // sky gradient, kernels.cu:419-421
-                const float t = 0.5f * (dir.y + 1.0f);
-                const f3 c = (1.0f - t) * mk3(1.0f, 1.0f, 1.0f) + t * mk3(0.5f, 0.7f, 1.0f);
-                const f3 add = att * c;
-                pc.x += add.x; pc.y += add.y; pc.z += add.z;
-            } else {
-                const unsigned int id = __float_as_uint(h.w);
-                const float4 sp = c_spheres[id];
-                const f3 rdir = unit(dir);
-                const f3 p = origin + h.x * rdir; // point_at_parameter on the traced (normalised) ray
-                SurfacePoint s;
-                s.normal = (p - xyz(sp)) / sp.w;
-                s.t = h.x;
-                s.inside = inside;
-                if (dot(rdir, s.normal) > 0.0f) s.normal = -s.normal;
-                const float4 m0 = __ldg(mats + 2 * id);
-                const float4 m1 = __ldg(mats + 2 * id + 1);
-                Scatter scat;
-                scat.specular = false;
-                scat.throughput = mk3(1.0f, 1.0f, 1.0f);
-                scat.refracted = false;
-                scat.t = h.x;
-                scat.wi = mk3(0.0f, 0.0f, 0.0f);
-                materialScatter(scat, s, dir, __float_as_int(m1.x), m0.w, xyz(m0), rng);
-                origin = origin + scat.t * dir;
-                dir = scat.wi;
-                att = att * scat.throughput;
-                inside = scat.refracted ? !inside : inside;
-                continues = true;
-                if (bounce > 3u) {
-                    const float m = maxcomp(att);
-                    if (rnd(rng) > m) continues = false;
-                    else att = att * (1 / m);
-                }
-                if (continues) {
-                    bounce = (bounce + 1u) & PATH_BOUNCE_MASK;
-                    if (!((int)bounce < maxDepth)) continues = false;
-                }
-                flags = bounce | (scat.specular ? PATH_FLAG_SPECULAR : 0u) | (inside ? PATH_FLAG_INSIDE : 0u);
-            }
-            if (continues) {
-                st.rayO[slot] = mk4(origin, __uint_as_float(rng));
-                st.rayD[slot] = mk4(dir, __uint_as_float(flags));
-                st.atten[slot] = mk4(att, att4.w);
-            } else {
-                // the sample is finished: col += p.color (kernels.cu:558), then the slot's next sample
-                const unsigned int pixel = slot % npix;
-                if (slotsPerPixel == 1) {
-                    float4 a = st.accum[pixel];
-                    a.x += pc.x; a.y += pc.y; a.z += pc.z;
-                    st.accum[pixel] = a;
-                } else {
-                    atomicAdd(&st.accum[pixel].x, pc.x);
-                    atomicAdd(&st.accum[pixel].y, pc.y);
-                    atomicAdd(&st.accum[pixel].z, pc.z);
-                }
-                const int sample = __float_as_int(att4.w) + 1;
-                if (sample < samplesPerSlot) {
-                    const int px = (int)(pixel % (unsigned int)nx), py = (int)(pixel / (unsigned int)nx);
-                    const float u = float(px + rnd(rng)) / float(nx);
-                    const float v = float(py + rnd(rng)) / float(ny);
-                    f3 o, d;
-                    cameraRay(cam, u, v, rng, o, d);
-                    st.rayO[slot] = mk4(o, __uint_as_float(rng));
-                    st.rayD[slot] = mk4(d, __uint_as_float(0u)); // bounce 0, specular = inside = false (kernels.cu:554-555)
-                    st.atten[slot] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(sample));
-                    st.pcol[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    continues = true;
-                }
-            }
+    const float4 ro = st.rayO[slot];
+    const float4 rd = st.rayD[slot];
+    const float4 att4 = st.atten[slot];
+    const float4 pc = st.pcol[slot];
+    SpherePath p;
+    p.origin = xyz(ro); p.dir = xyz(rd); p.att = xyz(att4); p.col = xyz(pc);
+    p.rng = __float_as_uint(ro.w);
+    p.flags = __float_as_uint(rd.w);
+    int sample = __float_as_int(att4.w);
+    bool continues = scatterSpherePath(p, mats, maxDepth, h);
+    if (!continues) {
+        // the sample is finished: col += p.color (kernels.cu:558), then the slot's next sample
+        const unsigned int pixel = slot % npix;
+        if (slotsPerPixel == 1) {
+            float4 a = st.accum[pixel];
+            a.x += p.col.x; a.y += p.col.y; a.z += p.col.z;
+            st.accum[pixel] = a;
+        } else {
+            atomicAdd(&st.accum[pixel].x, p.col.x);
+            atomicAdd(&st.accum[pixel].y, p.col.y);
+            atomicAdd(&st.accum[pixel].z, p.col.z);
+        }
+        sample += 1;
+        if (sample < samplesPerSlot) {
+            startSpherePath(p, cam, nx, ny, pixel);
+            st.pcol[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            continues = true;
+        }
+    }
+    if (continues) {
+        st.rayO[slot] = mk4(p.origin, __uint_as_float(p.rng));
+        st.rayD[slot] = mk4(p.dir, __uint_as_float(p.flags));
+        st.atten[slot] = mk4(p.att, __int_as_float(sample));
+    }
     return continues;
 }
 
@@ -286,6 +308,83 @@ __global__ void __launch_bounds__(128) finishSpheresKernel(WfState st, const flo
 }
 
 __global__ void finishSpheresDoneKernel(WfControl* ctl) { ctl->countActive = 0; }
+
+// ---- the persistent kernel ---------------------------------------------------------------------------------------------
+// In this scene a path slot ALWAYS has a next ray until its pixel is finished (no shadow rays, a finished sample starts the
+// next one), so the wavefront's queues have nothing to compact but finished pixels -- and every bounce pays a round trip of
+// the path state through memory, two launches, and a tail of 1 011 nearly empty iterations for the heaviest pixel (its samples
+// are one sequential chain, kernels.cu:542-548). Here a LANE owns a work item (one slot of one pixel) from its first camera
+// ray to its last sample with the path in registers, and takes the next item from a global cursor the moment it is done:
+// lanes never wait for a pixel other than their own, the frame ends when the last started item ends. Same device functions,
+// same per-pixel order of every floating-point operation as the wavefront kernels (tests compare the frames bit for bit).
+#define SPH_MEGA_BLOCK 128
+#define SPH_MEGA_BLOCKS_PER_SM 8
+
+__global__ void __launch_bounds__(SPH_MEGA_BLOCK, SPH_MEGA_BLOCKS_PER_SM)
+spheresMegaKernel(WfState st, const float4* __restrict__ mats, int maxDepth, SphereBvh bvh, CameraDev cam, int nx, int ny, int samplesPerSlot,
+                  int slotsPerPixel, unsigned int streamBase, unsigned int numItems) {
+    WfControl* ctl = st.ctl;
+    const unsigned int npix = (unsigned int)nx * (unsigned int)ny;
+    SpherePath p;
+    f3 sum = mk3(0.0f, 0.0f, 0.0f);
+    unsigned int pixel = 0;
+    int sample = 0;
+    bool live = false, exhausted = false;
+    unsigned long long rays = 0, trips = 0;
+    while (true) {
+        if (!exhausted) {
+            const unsigned int need = __ballot_sync(0xFFFFFFFFu, !live);
+            if (need) {
+                const unsigned int leader = __ffs(need) - 1;
+                unsigned int base = 0;
+                if (laneId() == leader) base = atomicAdd(&ctl->cursorExtend, (unsigned int)__popc(need));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                if (!live) {
+                    const unsigned int item = base + __popc(need & ((1u << laneId()) - 1u));
+                    if (item < numItems) {
+                        live = true;
+                        pixel = item % npix;
+                        const unsigned int stream = streamBase * (unsigned int)slotsPerPixel + item / npix;
+                        p.rng = pathSeed(pixel + stream * npix); // kernels.cu:541-542 (stream 0)
+                        sample = 0;
+                        sum = mk3(0.0f, 0.0f, 0.0f);
+                        startSpherePath(p, cam, nx, ny, pixel);
+                    }
+                }
+                exhausted = base + (unsigned int)__popc(need) >= numItems;
+            }
+        }
+        if (!__any_sync(0xFFFFFFFFu, live)) break;
+        trips++;
+        if (live) {
+            float closest;
+            unsigned int id;
+            closestSphere(bvh, p.origin, unit(p.dir), closest, id);
+            rays++;
+            if (!scatterSpherePath(p, mats, maxDepth, make_float4(closest, 0.0f, 0.0f, __uint_as_float(id)))) {
+                sum.x += p.col.x; sum.y += p.col.y; sum.z += p.col.z; // col += p.color, in sample order (kernels.cu:558)
+                sample++;
+                if (sample < samplesPerSlot) {
+                    startSpherePath(p, cam, nx, ny, pixel);
+                } else {
+                    if (slotsPerPixel == 1) {
+                        st.accum[pixel] = make_float4(sum.x, sum.y, sum.z, 0.0f);
+                    } else {
+                        atomicAdd(&st.accum[pixel].x, sum.x);
+                        atomicAdd(&st.accum[pixel].y, sum.y);
+                        atomicAdd(&st.accum[pixel].z, sum.z);
+                    }
+                    live = false;
+                }
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(0xFFFFFFFFu, rays, o);
+    if (laneId() == 0) {
+        if (rays) atomicAdd(&ctl->raysExtend, rays);
+        atomicMax(&ctl->iterations, trips); // the longest chain of rays any warp walked
+    }
+}
 
 // Host side of the sphere BVH (layout: SphereBvh above). Median split of the centroids along the longest axis.
 static SphereBvh g_sphereBvh;
@@ -413,7 +512,14 @@ void crtRunSpheres(RendererContext& c, int ns) {
     CRT_CHECK(cudaMemsetAsync(c.wf.accum, 0, (size_t)npix * sizeof(float4), stream));
     CRT_CHECK(cudaMemsetAsync(c.wf.ctl, 0, sizeof(WfControl), stream));
     unsigned long long launches = 0;
-    if (npix > 0 && ns > 0 && c.maxDepth > 0) {
+    const bool wavefront = g_spheresBrute || (std::getenv("CRT_SPHERES_WAVEFRONT") && std::getenv("CRT_SPHERES_WAVEFRONT")[0] == '1');
+    if (npix > 0 && ns > 0 && c.maxDepth > 0 && !wavefront) {
+        // the product path: one persistent launch (the wavefront kernels below stay as its checker: CRT_SPHERES_WAVEFRONT=1)
+        spheresMegaKernel<<<c.numSMs * SPH_MEGA_BLOCKS_PER_SM, SPH_MEGA_BLOCK, 0, stream>>>(c.wf, c.materials, c.maxDepth, g_sphereBvh, c.cam, c.nx, c.ny, samplesPerSlot,
+                                                                                          slotsPerPixel, c.opts.sampleStream, npix * (unsigned int)slotsPerPixel);
+        launches += 1;
+        CRT_CHECK(cudaMemcpyAsync(c.hostCtl, c.wf.ctl, sizeof(WfControl), cudaMemcpyDeviceToHost, stream));
+    } else if (npix > 0 && ns > 0 && c.maxDepth > 0) {
         const int grid = c.numSMs * 8;
         raygenKernel<true><<<grid, WF_BLOCK, 0, stream>>>(c.wf, c.cam, c.wf.queueA, c.nx, c.ny, samplesPerSlot, slotsPerPixel,
                                                           c.opts.sampleStream);

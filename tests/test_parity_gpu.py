@@ -165,6 +165,24 @@ def test_sphere_bvh_equals_the_brute_force_loop(crt, monkeypatch):
     assert np.array_equal(bvh, brute)
 
 
+def test_sphere_persistent_kernel_equals_the_wavefront(crt, monkeypatch):
+    """The persistent kernel (a lane owns a pixel from its first camera ray to its last sample, path in registers) and the
+    wavefront kernels (extend / shade launches over queues) run the same device functions in the same per-pixel order: frames
+    are bit-identical, ray counts equal -- with the sphere BVH and, for the wavefront, the brute-force loop beneath."""
+    nx, ny, ns = 300, 200, 8
+    monkeypatch.setenv("CRT_SPHERES_WAVEFRONT", "1")
+    with crt.Frame(crt.rtiow_scene(1), nx, ny, 50) as fr:
+        wave = fr.run(ns)
+        rays_wave = crt.stats().raysExtend
+    monkeypatch.delenv("CRT_SPHERES_WAVEFRONT")
+    with crt.Frame(crt.rtiow_scene(1), nx, ny, 50) as fr:
+        mega = fr.run(ns)
+        st = crt.stats()
+        again = fr.run(ns)
+    assert st.raysExtend == rays_wave and st.kernelLaunches <= 2
+    assert np.array_equal(mega, wave) and np.array_equal(mega, again)
+
+
 def test_ray_batch_vs_golden_hitmesh(crt, small_scene):
     z = np.load(os.path.join(G, "rays_8192.npz"))
     with crt.Frame(small_scene, 8, 8, 1):

@@ -10,5 +10,7 @@ import crt_b200 as crt  # noqa: E402
 ns = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 with crt.Frame(crt.rtiow_scene(1), 1200, 800, 50) as fr:
     fr.run(ns, copy=False)
-    st = crt.stats()
-    print("ms", st.msTotal, "Mrays/s", (st.raysExtend + st.raysShadow) / (st.msTotal * 1e3), "iterations", st.iterations)
+    for _ in range(int(sys.argv[2]) if len(sys.argv) > 2 else 1):
+        fr.run(ns, copy=False)
+        st = crt.stats()
+        print("ms", st.msTotal, "Mrays/s", (st.raysExtend + st.raysShadow) / (st.msTotal * 1e3), "iterations", st.iterations, "launches", st.kernelLaunches)
