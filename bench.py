@@ -40,6 +40,8 @@ BATCH_BYTES_PER_RAY = 52    # 32 in, 16 + 4 out
 # the renderer's own tree costs 8 x (6 fused multiply-adds + 4 min/max + 1 subtraction) + 12 of per-node setup = 148; a triangle
 # test 48; 3 per ray for the reciprocal direction.
 FLOPS_PER_DUAL_VISIT, FLOPS_PER_WIDE_VISIT, FLOPS_PER_TRI_TEST, FLOPS_PER_RAY = 36.0, 148.0, 48.0, 3.0
+# sphere scenes (20 flops per sphere test): slab test of one box 6 sub + 6 mul + 6 min/max = 18; shading ~150 per ray
+FLOPS_PER_BOX_TEST, FLOPS_PER_SPHERE_TEST, SPHERE_SHADE_FLOPS = 18, 20, 150
 NCU_FILE = os.path.join(ROOT, "profiles", "r02", "trace_ncu.json")  # DRAM bytes of the dominant kernel's bulk launch (ncu --set full)
 
 
@@ -359,13 +361,29 @@ def run_ours(args, rank, world, local_rank):
                                                  build_ms_inside_initRenderer=float(wide.buildMs), built_on="device" if wide.buildThreads == 0 else "host",
                                                  rays_retraced_in_reference_order=int(wide.lastFrameRedo)))
     elif rank == 0:
-        # sphere scenes: the extend kernel walks a sphere BVH (20 flops per sphere test, ~25 per node); report the byte side and the
-        # flop side of the frame as a whole (no per-kernel event timing in this pipeline)
-        bytes_frame = 150.0 * total_rays  # ~150 B of queue traffic per ray in a wavefront
+        # sphere scenes: ONE persistent launch per frame (spheresMegaKernel: a lane owns a pixel, the path lives in registers, the
+        # 488 spheres and their BVH are L1-resident), so the kernel's launch time is the step time and the byte side is the frame
+        # it writes; the flop side counts the box and sphere tests of one extra counting step (untimed)
+        import ctypes as C
+        L.setRendererCounting(1)
+        L.runRenderer(ns, 8, 8)
+        L.setRendererCounting(0)
+        nb, nt = C.c_ulonglong(), C.c_ulonglong()
+        L.getRendererTraversalCounts(C.byref(nb), C.byref(nt))
+        rays_mine = max(rays_step, 1)
+        flops = (3.0 + SPHERE_SHADE_FLOPS) * rays_mine + FLOPS_PER_BOX_TEST * nb.value + FLOPS_PER_SPHERE_TEST * nt.value
+        fp32_achieved = flops / (ms_per_step * 1e-3) / 1e12
+        bytes_frame = 16.0 * nx * ny + 32.0 * nx * ny  # float4 sums written once, finalize reads them and writes the frame
         hbm_achieved = bytes_frame / (ms_per_step * 1e-3) / 1e9
-        roof = dict(bound="hbm", kernel="extendSpheresBvhKernel + shadeSpheresKernel (whole frame)", achieved=hbm_achieved, peak=pk["hbm_gbs"], unit="GB/s",
-                    frac=hbm_achieved / pk["hbm_gbs"], traffic=None, peak_source=pk["src"],
-                    note="whole-frame figure from the SURVEY 8d byte model (150 B per ray); latency-bound gathers, no ncu capture committed for this path")
+        roof = dict(bound="fp32", kernel="spheresMegaKernel<false> (whole frame: one launch)", achieved=fp32_achieved, peak=fp32_peak, unit="TFLOP/s",
+                    frac=fp32_achieved / fp32_peak, traffic=None, peak_source="SMs x 128 lanes x 2 x sm_max_mhz (cudaGetDeviceProperties, MEASURED_PEAKS.json)",
+                    binding_resource="instruction issue at low lane use (profiles/r02/sph_mega_ncu_summary.txt: issue active 80 %, 9-10 of 32 lanes per "
+                                     "instruction): walks of different length inside a warp; no queue traffic at all, the scene is L1-resident",
+                    hbm=dict(achieved=hbm_achieved, peak=pk["hbm_gbs"], unit="GB/s", frac=hbm_achieved / pk["hbm_gbs"], peak_source=pk["src"],
+                             algorithmic_bytes_per_launch=bytes_frame),
+                    fp32=dict(achieved=fp32_achieved, peak=fp32_peak, unit="TFLOP/s", frac=fp32_achieved / fp32_peak,
+                              box_tests_per_ray=nb.value / rays_mine, sphere_tests_per_ray=nt.value / rays_mine,
+                              formula="(3 + %d)*rays + %d*box tests + %d*sphere tests" % (SPHERE_SHADE_FLOPS, FLOPS_PER_BOX_TEST, FLOPS_PER_SPHERE_TEST)))
     fr.close()
 
     # ---- e2e: host buffers -> frame on the host, through the reference-facing entry points, every step

@@ -54,16 +54,19 @@ __global__ void __launch_bounds__(WF_BLOCK) extendSpheresKernel(WfState st, cons
 // the sphere's first root in (t_min, inf) (sphereHit, intersections.h:85-104, tries the near root, then the far one), ties
 // going to the lowest index (the loop accepts on strict `<` in index order). That is a property of the set of spheres, not
 // of the loop, so any traversal that (a) never skips a sphere whose r_s could win and (b) breaks ties by index returns the
-// same bits. The spheres are put into a small BVH at init (host, median split, <= 4 per leaf, boxes padded by 1 % of the
+// same bits. The spheres are put into a small BVH at init (host, median split, one sphere per leaf, boxes padded by 1 % of the
 // radius + 1e-3: three orders of magnitude more than the rounding of r_s for these sizes); spheres too large for that
 // margin (radius > 100: the ground sphere, whose roots lose ~1e-3 to cancellation) stay in a list that every ray tests.
-// The tree is stored depth-first with skip links (no stack): node i's subtree is [i+1, skip_i).
+// The tree is stored depth-first with skip links (no stack): node i's subtree is [i+1, skip_i) -- once per ray octant, each
+// threading visiting the child on the ray's near side of the split axis first, so that a hit found early culls the far side
+// (8 x 243 nodes x 32 B: L1-resident).
 struct SphereBvh {
     const float4* __restrict__ nodes;   // 2 per node: {bmin.xyz, skip}{bmax.xyz, first | count << 24 (0xFFFFFFFF = internal)}
     const float4* __restrict__ spheres; // leaf order: {center.xyz, radius}
     const unsigned int* __restrict__ ids; // leaf order -> index the caller gave the sphere
     unsigned int numNodes;
     unsigned int numAlways;             // spheres[0 .. numAlways) are tested by every ray
+    unsigned int octantMask;            // 7: nodes[] holds 8 threadings of the tree, one per ray octant (near child first); 0: one
 };
 
 __device__ __forceinline__ void testSphere(const SphereBvh& b, unsigned int k, const f3& o, const f3& d, float& closest, unsigned int& id) {
@@ -79,19 +82,24 @@ __device__ __forceinline__ void testSphere(const SphereBvh& b, unsigned int k, c
 }
 
 // The closest sphere along (o, d): {t, id} (FLT_MAX / ~0 = none).
-__device__ __forceinline__ void closestSphere(const SphereBvh& bvh, const f3& o, const f3& d, float& closest, unsigned int& id) {
+__device__ __forceinline__ void closestSphere(const SphereBvh& bvh, const f3& o, const f3& d, float& closest, unsigned int& id, unsigned int& boxTests,
+                                              unsigned int& sphereTests) {
     const f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
     closest = FLT_MAX;
     id = 0xFFFFFFFFu;
     for (unsigned int k = 0; k < bvh.numAlways; k++) testSphere(bvh, k, o, d, closest, id);
+    sphereTests += bvh.numAlways;
+    const unsigned int octant = ((d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u)) & bvh.octantMask;
+    const float4* __restrict__ nodes = bvh.nodes + (size_t)octant * 2u * bvh.numNodes;
     unsigned int node = 0;
     while (true) {
         // box phase: every lane walks on until it stands in a leaf (or its walk ends); the leaves' sphere tests then run for all
         // those lanes together instead of one lane at a time inside the walk
         unsigned int leaf = 0u; // count << 24 | first; 0 = none
         while (node < bvh.numNodes) {
-            const float4 lo = __ldg(bvh.nodes + 2 * node);
-            const float4 hi = __ldg(bvh.nodes + 2 * node + 1);
+            const float4 lo = __ldg(nodes + 2 * node);
+            const float4 hi = __ldg(nodes + 2 * node + 1);
+            boxTests++;
             // conservative slab test: fminf/fmaxf drop the NaN of 0 * inf (an axis the ray is parallel to)
             const float x0 = (lo.x - o.x) * inv.x, x1 = (hi.x - o.x) * inv.x;
             const float y0 = (lo.y - o.y) * inv.y, y1 = (hi.y - o.y) * inv.y;
@@ -108,8 +116,15 @@ __device__ __forceinline__ void closestSphere(const SphereBvh& bvh, const f3& o,
         }
         if (leaf == 0u) break;
         const unsigned int first = leaf & 0xFFFFFFu, count = leaf >> 24;
-        for (unsigned int k = 0; k < count; k++) testSphere(bvh, first + k, o, d, closest, id);
+        testSphere(bvh, first, o, d, closest, id); // (leaves hold one sphere unless CRT_SPHERES_LEAF says otherwise)
+        if (count > 1u) for (unsigned int k = 1; k < count; k++) testSphere(bvh, first + k, o, d, closest, id);
+        sphereTests += count;
     }
+}
+
+__device__ __forceinline__ void closestSphere(const SphereBvh& bvh, const f3& o, const f3& d, float& closest, unsigned int& id) {
+    unsigned int boxTests = 0, sphereTests = 0; // (never read: the compiler drops the counting)
+    closestSphere(bvh, o, d, closest, id, boxTests, sphereTests);
 }
 
 __global__ void __launch_bounds__(WF_BLOCK) extendSpheresBvhKernel(WfState st, const unsigned int* __restrict__ queue, SphereBvh bvh) {
@@ -317,9 +332,16 @@ __global__ void finishSpheresDoneKernel(WfControl* ctl) { ctl->countActive = 0; 
 // ray to its last sample with the path in registers, and takes the next item from a global cursor the moment it is done:
 // lanes never wait for a pixel other than their own, the frame ends when the last started item ends. Same device functions,
 // same per-pixel order of every floating-point operation as the wavefront kernels (tests compare the frames bit for bit).
-#define SPH_MEGA_BLOCK 128
+#define SPH_MEGA_BLOCK 128 // (64 x 16, 256 x 4 and 32 x 32 measure the same; 128 x 6 with 80 registers is 5 % slower)
 #define SPH_MEGA_BLOCKS_PER_SM 8
 
+// The shape of closestSphere's loops matters more than their content: the same walk written as "at most N box steps, then look
+// what the lane needs" (a counted inner loop) ran at HALF the speed (73 ms) -- ptxas then no longer re-joins the lanes before
+// the leaf tests. Keep the plain nested loops.
+// (Measured and not kept, profiles/r02/ab_summary.json: a per-lane state machine that runs, each turn, whichever piece -- box
+// steps, leaf tests, shading -- most lanes of the warp wait for. Lane use rises, the scheduling ballots and the wider live state
+// cost more than that returns: 42-45 ms against 34 ms for the plain loop below.)
+template <bool COUNT>
 __global__ void __launch_bounds__(SPH_MEGA_BLOCK, SPH_MEGA_BLOCKS_PER_SM)
 spheresMegaKernel(WfState st, const float4* __restrict__ mats, int maxDepth, SphereBvh bvh, CameraDev cam, int nx, int ny, int samplesPerSlot,
                   int slotsPerPixel, unsigned int streamBase, unsigned int numItems) {
@@ -330,7 +352,8 @@ spheresMegaKernel(WfState st, const float4* __restrict__ mats, int maxDepth, Sph
     unsigned int pixel = 0;
     int sample = 0;
     bool live = false, exhausted = false;
-    unsigned long long rays = 0, trips = 0;
+    unsigned int rays = 0, trips = 0;
+    unsigned long long boxTests = 0, sphereTests = 0; // COUNT only
     while (true) {
         if (!exhausted) {
             const unsigned int need = __ballot_sync(0xFFFFFFFFu, !live);
@@ -359,8 +382,16 @@ spheresMegaKernel(WfState st, const float4* __restrict__ mats, int maxDepth, Sph
         if (live) {
             float closest;
             unsigned int id;
-            closestSphere(bvh, p.origin, unit(p.dir), closest, id);
+            if (COUNT) {
+                unsigned int nb = 0, ns = 0;
+                closestSphere(bvh, p.origin, unit(p.dir), closest, id, nb, ns);
+                boxTests += nb;
+                sphereTests += ns;
+            } else {
+                closestSphere(bvh, p.origin, unit(p.dir), closest, id);
+            }
             rays++;
+            p.col = mk3(0.0f, 0.0f, 0.0f); // a sphere path only collects light when it ends (the sky): nothing to carry between rays
             if (!scatterSpherePath(p, mats, maxDepth, make_float4(closest, 0.0f, 0.0f, __uint_as_float(id)))) {
                 sum.x += p.col.x; sum.y += p.col.y; sum.z += p.col.z; // col += p.color, in sample order (kernels.cu:558)
                 sample++;
@@ -379,10 +410,21 @@ spheresMegaKernel(WfState st, const float4* __restrict__ mats, int maxDepth, Sph
             }
         }
     }
-    for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(0xFFFFFFFFu, rays, o);
+    unsigned long long warpRays = rays;
+    for (int o = 16; o > 0; o >>= 1) warpRays += __shfl_xor_sync(0xFFFFFFFFu, warpRays, o);
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) {
+            boxTests += __shfl_xor_sync(0xFFFFFFFFu, boxTests, o);
+            sphereTests += __shfl_xor_sync(0xFFFFFFFFu, sphereTests, o);
+        }
+        if (laneId() == 0) {
+            atomicAdd(&ctl->nodeVisits, boxTests);
+            atomicAdd(&ctl->triTests, sphereTests);
+        }
+    }
     if (laneId() == 0) {
-        if (rays) atomicAdd(&ctl->raysExtend, rays);
-        atomicMax(&ctl->iterations, trips); // the longest chain of rays any warp walked
+        if (warpRays) atomicAdd(&ctl->raysExtend, warpRays);
+        atomicMax(&ctl->iterations, (unsigned long long)trips); // rays of the busiest warp's longest lane chain
     }
 }
 
@@ -392,34 +434,42 @@ static SphereBvh g_sphereBvh;
 static void buildSphereBvh(RendererContext& c, const std::vector<float4>& sp, int n) {
     std::vector<unsigned int> always, rest;
     for (int i = 0; i < n; i++) (sp[i].w > 100.0f ? always : rest).push_back((unsigned int)i);
-    std::vector<float4> nodes, leafSpheres;
+    std::vector<float4> leafSpheres;
     std::vector<unsigned int> leafIds;
     for (unsigned int i : always) { leafSpheres.push_back(sp[i]); leafIds.push_back(i); }
+    const size_t maxLeaf = std::getenv("CRT_SPHERES_LEAF") ? (size_t)std::max(1, std::atoi(std::getenv("CRT_SPHERES_LEAF"))) : 1; // measured on config 2: 1 -> 34.0 ms, 2 -> 35.0, 4 -> 36.9
+    const bool ordered = !(std::getenv("CRT_SPHERES_ORDERED") && std::getenv("CRT_SPHERES_ORDERED")[0] == '0');
+    // the tree, then one depth-first threading of it per ray octant
+    struct Node { float bmin[3], bmax[3]; int left, right, axis; unsigned int leafWord; };
+    std::vector<Node> tree;
     struct Builder {
         const std::vector<float4>& sp;
-        std::vector<float4>& nodes;
+        std::vector<Node>& tree;
         std::vector<float4>& leafSpheres;
         std::vector<unsigned int>& leafIds;
-        void build(std::vector<unsigned int>& idx, size_t lo, size_t hi) {
-            float bmin[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, bmax[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        size_t maxLeaf;
+        int build(std::vector<unsigned int>& idx, size_t lo, size_t hi) {
+            Node nd;
             float cmin[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, cmax[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            for (int a = 0; a < 3; a++) { nd.bmin[a] = FLT_MAX; nd.bmax[a] = -FLT_MAX; }
             for (size_t k = lo; k < hi; k++) {
                 const float4 s = sp[idx[k]];
                 const float ce[3] = {s.x, s.y, s.z};
                 for (int a = 0; a < 3; a++) {
                     const float pad = s.w * 1.01f + 1e-3f + 1e-5f * std::fabs(ce[a]);
-                    bmin[a] = std::min(bmin[a], ce[a] - pad);
-                    bmax[a] = std::max(bmax[a], ce[a] + pad);
+                    nd.bmin[a] = std::min(nd.bmin[a], ce[a] - pad);
+                    nd.bmax[a] = std::max(nd.bmax[a], ce[a] + pad);
                     cmin[a] = std::min(cmin[a], ce[a]);
                     cmax[a] = std::max(cmax[a], ce[a]);
                 }
             }
-            const size_t me = nodes.size() / 2;
-            nodes.push_back(make_float4(bmin[0], bmin[1], bmin[2], 0.0f));
-            nodes.push_back(make_float4(bmax[0], bmax[1], bmax[2], 0.0f));
-            unsigned int leafWord = 0xFFFFFFFFu;
-            if (hi - lo <= 4) {
-                leafWord = (unsigned int)leafSpheres.size() | ((unsigned int)(hi - lo) << 24);
+            nd.left = nd.right = -1;
+            nd.axis = 0;
+            nd.leafWord = 0xFFFFFFFFu;
+            const int me = (int)tree.size();
+            tree.push_back(nd);
+            if (hi - lo <= maxLeaf) {
+                tree[me].leafWord = (unsigned int)leafSpheres.size() | ((unsigned int)(hi - lo) << 24);
                 for (size_t k = lo; k < hi; k++) { leafSpheres.push_back(sp[idx[k]]); leafIds.push_back(idx[k]); }
             } else {
                 int axis = 0;
@@ -430,15 +480,40 @@ static void buildSphereBvh(RendererContext& c, const std::vector<float4>& sp, in
                     const float b = axis == 0 ? sp[q].x : axis == 1 ? sp[q].y : sp[q].z;
                     return a < b || (a == b && p < q);
                 });
-                build(idx, lo, mid);
-                build(idx, mid, hi);
+                const int l = build(idx, lo, mid), r = build(idx, mid, hi);
+                tree[me].left = l; tree[me].right = r; tree[me].axis = axis;
             }
-            const unsigned int skip = (unsigned int)(nodes.size() / 2);
-            std::memcpy(&nodes[2 * me].w, &skip, 4);
-            std::memcpy(&nodes[2 * me + 1].w, &leafWord, 4);
+            return me;
         }
-    } builder{sp, nodes, leafSpheres, leafIds};
+    } builder{sp, tree, leafSpheres, leafIds, maxLeaf};
     if (!rest.empty()) builder.build(rest, 0, rest.size());
+    const unsigned int numNodes = (unsigned int)tree.size();
+    const unsigned int numOrders = ordered ? 8u : 1u;
+    std::vector<float4> nodes;
+    struct Emitter {
+        const std::vector<Node>& tree;
+        std::vector<float4>& nodes;
+        unsigned int octant;
+        size_t base;
+        void emit(int t) { // the lower side first, unless the ray travels towards lower coordinates on the split axis
+            const Node& nd = tree[t];
+            const size_t me = nodes.size();
+            nodes.push_back(make_float4(nd.bmin[0], nd.bmin[1], nd.bmin[2], 0.0f));
+            nodes.push_back(make_float4(nd.bmax[0], nd.bmax[1], nd.bmax[2], 0.0f));
+            if (nd.left >= 0) {
+                const bool flip = ((octant >> nd.axis) & 1u) != 0u;
+                emit(flip ? nd.right : nd.left);
+                emit(flip ? nd.left : nd.right);
+            }
+            const unsigned int skip = (unsigned int)((nodes.size() - base) / 2);
+            std::memcpy(&nodes[me].w, &skip, 4);
+            std::memcpy(&nodes[me + 1].w, &nd.leafWord, 4);
+        }
+    };
+    for (unsigned int oct = 0; oct < numOrders; oct++) {
+        Emitter e{tree, nodes, oct, nodes.size()};
+        if (numNodes) e.emit(0);
+    }
     if (leafSpheres.empty()) { leafSpheres.push_back(make_float4(0, 0, 0, 0)); leafIds.push_back(0); }
     if (nodes.empty()) { nodes.push_back(make_float4(0, 0, 0, 0)); nodes.push_back(make_float4(0, 0, 0, 0)); }
     float4* dNodes = (float4*)arenaAlloc(nodes.size() * sizeof(float4));
@@ -450,8 +525,9 @@ static void buildSphereBvh(RendererContext& c, const std::vector<float4>& sp, in
     g_sphereBvh.nodes = dNodes;
     g_sphereBvh.spheres = dSpheres;
     g_sphereBvh.ids = dIds;
-    g_sphereBvh.numNodes = rest.empty() ? 0u : (unsigned int)(nodes.size() / 2);
+    g_sphereBvh.numNodes = numNodes;
     g_sphereBvh.numAlways = (unsigned int)always.size();
+    g_sphereBvh.octantMask = ordered ? 7u : 0u;
     (void)c;
 }
 
@@ -515,8 +591,13 @@ void crtRunSpheres(RendererContext& c, int ns) {
     const bool wavefront = g_spheresBrute || (std::getenv("CRT_SPHERES_WAVEFRONT") && std::getenv("CRT_SPHERES_WAVEFRONT")[0] == '1');
     if (npix > 0 && ns > 0 && c.maxDepth > 0 && !wavefront) {
         // the product path: one persistent launch (the wavefront kernels below stay as its checker: CRT_SPHERES_WAVEFRONT=1)
-        spheresMegaKernel<<<c.numSMs * SPH_MEGA_BLOCKS_PER_SM, SPH_MEGA_BLOCK, 0, stream>>>(c.wf, c.materials, c.maxDepth, g_sphereBvh, c.cam, c.nx, c.ny, samplesPerSlot,
-                                                                                          slotsPerPixel, c.opts.sampleStream, npix * (unsigned int)slotsPerPixel);
+        const int grid = c.numSMs * SPH_MEGA_BLOCKS_PER_SM;
+        if (c.counting) // setRendererCounting: box and sphere tests per ray for the bench's flop model (not a timed configuration)
+            spheresMegaKernel<true><<<grid, SPH_MEGA_BLOCK, 0, stream>>>(c.wf, c.materials, c.maxDepth, g_sphereBvh, c.cam, c.nx, c.ny, samplesPerSlot, slotsPerPixel,
+                                                                         c.opts.sampleStream, npix * (unsigned int)slotsPerPixel);
+        else
+            spheresMegaKernel<false><<<grid, SPH_MEGA_BLOCK, 0, stream>>>(c.wf, c.materials, c.maxDepth, g_sphereBvh, c.cam, c.nx, c.ny, samplesPerSlot, slotsPerPixel,
+                                                                          c.opts.sampleStream, npix * (unsigned int)slotsPerPixel);
         launches += 1;
         CRT_CHECK(cudaMemcpyAsync(c.hostCtl, c.wf.ctl, sizeof(WfControl), cudaMemcpyDeviceToHost, stream));
     } else if (npix > 0 && ns > 0 && c.maxDepth > 0) {
@@ -572,6 +653,8 @@ void crtRunSpheres(RendererContext& c, int ns) {
     CRT_CHECK(cudaGetLastError());
     CRT_CHECK(cudaEventElapsedTime(&c.stats.msTotal, c.evStart, c.evStop));
     c.stats.raysExtend = c.hostCtl->raysExtend;
+    c.lastNodeVisits = c.hostCtl->nodeVisits; // box tests / sphere tests of a counted frame (getRendererTraversalCounts)
+    c.lastTriTests = c.hostCtl->triTests;
     c.stats.raysShadow = 0;
     c.stats.iterations = c.hostCtl->iterations;
     c.stats.kernelLaunches = launches;

@@ -43,11 +43,11 @@ for r in rows:
     d = dict(zip(hdr, r))
     s = num(d['# Samples'])
     tot += s
-    items.append((s, cur, d['Line No'], num(d['Instructions Executed']), num(d['Avg. Threads Executed'], float),
+    items.append((s, cur, d['Line No'], num(d['Instructions Executed']), (num(d.get('Thread Instructions Executed')) / max(1, num(d['Instructions Executed']))),
                   num(d.get('stall_long_sb')), num(d.get('stall_wait')), num(d.get('stall_math')),
                   num(d.get('stall_branch_resolving')), num(d.get('stall_short_sb')), num(d.get('stall_not_selected')), r[1].strip()[:90]))
 items.sort(reverse=True)
 print('total samples', tot)
-print('samples  %    file:line   inst  thr | long_sb wait math branch short_sb not_sel | source')
+print('samples  %    file:line   warp-inst  lanes | long_sb wait math branch short_sb not_sel | source')
 for s, f, l, inst, thr, lsb, w, m, b, ssb, ns, src in items[:top]:
     print(f"{s:7d} {100 * s / tot:4.1f} {f}:{l} {inst:10d} {thr:4.1f} | {lsb:6d} {w:6d} {m:5d} {b:5d} {ssb:5d} {ns:5d} | {src}")

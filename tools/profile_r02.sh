@@ -17,6 +17,7 @@ ncu --set full --import-source on --clock-control none -k regex:chaseKernel --la
 python tools/prof_batch.py 1.0 22 0 3 > gpurun_out/prof_plain.log 2>&1 || exit 1
 ncu --set full --import-source on --clock-control none -k regex:wideIntersectBatch -s 1 -c 1 -f -o gpurun_out/prof_widebatch_r02 python tools/prof_batch.py 1.0 22 0 3 > gpurun_out/ncu_4.log 2>&1
 python tools/render_spheres_once.py > gpurun_out/rs_plain.log 2>&1 || exit 1
-ncu --set full --import-source on --clock-control none -k regex:extendSpheresBvhKernel --launch-skip 20 --launch-count 1 -f -o gpurun_out/prof_sph_extend_r02 python tools/render_spheres_once.py > gpurun_out/ncu_5.log 2>&1
-ncu --set full --import-source on --clock-control none -k regex:shadeSpheresKernel --launch-skip 20 --launch-count 1 -f -o gpurun_out/prof_sph_shade_r02 python tools/render_spheres_once.py > gpurun_out/ncu_6.log 2>&1
-tail -2 gpurun_out/ncu_6.log
+ncu --set full --import-source on --clock-control none -k regex:spheresMegaKernel --launch-skip 1 --launch-count 1 -f -o gpurun_out/prof_sph_mega_r02 python tools/render_spheres_once.py 100 1 > gpurun_out/ncu_5.log 2>&1
+CRT_SPHERES_WAVEFRONT=1 ncu --set full --import-source on --clock-control none -k regex:extendSpheresBvhKernel --launch-skip 20 --launch-count 1 -f -o gpurun_out/prof_sph_extend_r02 python tools/render_spheres_once.py > gpurun_out/ncu_6.log 2>&1
+CRT_SPHERES_WAVEFRONT=1 ncu --set full --import-source on --clock-control none -k regex:shadeSpheresKernel --launch-skip 20 --launch-count 1 -f -o gpurun_out/prof_sph_shade_r02 python tools/render_spheres_once.py > gpurun_out/ncu_7.log 2>&1
+tail -2 gpurun_out/ncu_7.log
