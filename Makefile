@@ -6,12 +6,12 @@ PKG   := cuda-raytracing-optimized_b200
 ARCH  := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -Iinclude -I$(PKG)/csrc
 CSRC  := $(wildcard $(PKG)/csrc/*.inc $(PKG)/csrc/*.cu $(PKG)/csrc/*.cuh $(PKG)/csrc/*.h $(PKG)/csrc/*.cpp) include/kernels.h include/rt_types.h
-HOSTSRC := $(PKG)/host/host_api.cpp $(PKG)/host/bvh_builder.cpp
+HOSTSRC := $(PKG)/host/host_api.cpp $(PKG)/host/bvh_builder.cpp $(PKG)/host/png_reader.cpp
 
 .PHONY: all oracle clean
 all: build/libcrt_host.so build/libcrt_b200.so build/crt_render
 
-build/libcrt_host.so: $(HOSTSRC) $(PKG)/host/host_api.h $(PKG)/host/bvh_builder.h include/rt_types.h
+build/libcrt_host.so: $(HOSTSRC) $(PKG)/host/host_api.h $(PKG)/host/bvh_builder.h $(PKG)/host/png_reader.h include/rt_types.h
 	@mkdir -p build
 	$(CXX) -O2 -std=c++17 -fPIC -shared -Iinclude -I$(PKG)/host $(HOSTSRC) -o $@
 

@@ -18,9 +18,11 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <string>
 #include <vector>
 
 #include "bvh_builder.h"
+#include "png_reader.h"
 
 namespace {
 
@@ -438,6 +440,57 @@ crt_scene* crtSceneFromTriangles(const triangle* tris, int n, int primsPerLeaf, 
 }
 
 void crtSceneDestroy(crt_scene* s) { delete s; }
+
+// loadTexture, staircase_scene.h:103-118: decode as RGB with the rows flipped (stbi_set_flip_vertically_on_load(true), :120),
+// every byte / 255.0f. The scene keeps the floats; the device library uploads them at the next initRenderer.
+int crtSceneLoadTexturePNG(crt_scene* s, int index, const char* path) {
+    if (!s || index < 0 || index >= (int)s->textures.size()) return -1;
+    int w = 0, h = 0;
+    std::vector<uint8_t> rgb;
+    if (!crt::readPngFile(path, true, w, h, rgb)) return -1;
+    std::vector<float>& dst = s->texData[index];
+    dst.resize(rgb.size());
+    for (size_t i = 0; i < rgb.size(); i++) dst[i] = rgb[i] / 255.0f;
+    s->textures[index].data = dst.data();
+    s->textures[index].width = w;
+    s->textures[index].height = h;
+    return 0;
+}
+
+// The nine files load_scene reads, in its order (staircase_scene.h:125-133), from `dir`. Returns how many were loaded; the
+// others keep their procedural stand-ins.
+int crtSceneLoadTextureDir(crt_scene* s, const char* dir) {
+    static const char* kNames[9] = {"WoodFloor.png", "Wallpaper.png", "Woodpanel.png", "Painting1.png", "Painting2.png",
+                                    "Painting3.png", "WoodChair.png", "Fabric.png", "BrushedAluminium.png"};
+    int loaded = 0;
+    for (int i = 0; i < 9; i++) {
+        const std::string path = std::string(dir) + "/" + kNames[i];
+        if (crtSceneLoadTexturePNG(s, i, path.c_str()) == 0) loaded++;
+    }
+    return loaded;
+}
+
+int crtDecodePNG(const unsigned char* bytes, unsigned long long n, int flipVertically, int* width, int* height, unsigned char* rgbOut,
+                 unsigned long long capacity) {
+    int w = 0, h = 0;
+    std::vector<uint8_t> rgb;
+    if (!crt::decodePng(bytes, (size_t)n, flipVertically != 0, w, h, rgb)) return -1;
+    if (width) *width = w;
+    if (height) *height = h;
+    if (rgbOut) {
+        if (capacity < rgb.size()) return -2;
+        std::memcpy(rgbOut, rgb.data(), rgb.size());
+    }
+    return 0;
+}
+
+int crtSceneTextureInfo(const crt_scene* s, int index, int* width, int* height, const float** data) {
+    if (!s || index < 0 || index >= (int)s->textures.size()) return -1;
+    if (width) *width = s->textures[index].width;
+    if (height) *height = s->textures[index].height;
+    if (data) *data = s->textures[index].data;
+    return 0;
+}
 
 int crtSceneSaveBVH(const crt_scene* s, const char* path) { return crt::saveBvhFile(path, s->built) ? 0 : -1; }
 

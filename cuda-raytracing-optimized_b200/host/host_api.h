@@ -34,6 +34,14 @@ crt_scene* crtSceneCreateStaircaseEx(float detail, int texSize, int primsPerLeaf
 crt_scene* crtSceneLoadBVH(const char* path, int texSize);
 // Scene from caller triangles (copied); builds the BVH. materials/textures = staircase tables.
 crt_scene* crtSceneFromTriangles(const triangle* tris, int n, int primsPerLeaf, int texSize);
+// Textures from PNG files (loadTexture, staircase_scene.h:103-118: RGB, rows flipped, byte / 255.0f; decoder: host/png_reader.cpp).
+// index 0..8 = WoodFloor, Wallpaper, Woodpanel, Painting1-3, WoodChair, Fabric, BrushedAluminium (staircase_scene.h:125-133).
+int crtSceneLoadTexturePNG(crt_scene* s, int index, const char* path); // 0 on success, -1: unreadable / not a PNG (texture unchanged)
+int crtSceneLoadTextureDir(crt_scene* s, const char* dir);             // the nine file names of load_scene; returns how many loaded
+int crtSceneTextureInfo(const crt_scene* s, int index, int* width, int* height, const float** data);
+// PNG image in memory -> width, height and (when rgbOut != NULL) width*height*3 bytes; -1: malformed, -2: capacity too small.
+int crtDecodePNG(const unsigned char* bytes, unsigned long long n, int flipVertically, int* width, int* height, unsigned char* rgbOut,
+                 unsigned long long capacity);
 void crtSceneDestroy(crt_scene* s);
 int crtSceneSaveBVH(const crt_scene* s, const char* path); // 0 on success
 const kernel_scene* crtSceneKernelScene(const crt_scene* s);

@@ -4,12 +4,13 @@
 // PPM on stdout / file -> optional RMSE against a REF_00.01 frame -> cleanupRenderer.
 //
 //   crt_render [--scene staircase|rtiow|file.bvh] [--nx N] [--ny N] [--ns N] [--depth N] [--detail F]
-//              [--tex N] [--ppm out.ppm|-] [--ref frame.ref] [--save-ref frame.ref] [--bvh-out file.bvh] [--gpus N] [--frames K]
+//              [--tex N] [--textures DIR] [--ppm out.ppm|-] [--ref frame.ref] [--save-ref frame.ref] [--bvh-out file.bvh] [--gpus N] [--frames K]
 //   (the reference's single positional argument, maxDepth, is still accepted: main.cpp:73-74)
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <iostream>
 #include <string>
 #include <vector>
 
@@ -20,7 +21,7 @@ int main(int argc, char** argv) {
     int nx = 640, ny = 800, ns = 256, maxDepth = 64, tx = 8, ty = 8, texSize = 1024; // main.cpp:65-70
     float detail = 1.0f;
     int gpus = 1, frames = 1;
-    std::string scene = "staircase", ppm, refIn, refOut, bvhOut;
+    std::string scene = "staircase", ppm, refIn, refOut, bvhOut, textureDir;
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { return i + 1 < argc ? argv[++i] : ""; };
@@ -31,6 +32,7 @@ int main(int argc, char** argv) {
         else if (a == "--depth") maxDepth = std::atoi(next());
         else if (a == "--detail") detail = (float)std::atof(next());
         else if (a == "--tex") texSize = std::atoi(next());
+        else if (a == "--textures") textureDir = next(); // directory with the nine PNG files of staircase_scene.h:125-133
         else if (a == "--ppm") ppm = next();
         else if (a == "--ref") refIn = next();
         else if (a == "--save-ref") refOut = next();
@@ -55,6 +57,10 @@ int main(int argc, char** argv) {
         const bool isFile = scene.size() > 4 && scene.compare(scene.size() - 4, 4, ".bvh") == 0;
         sc = isFile ? crtSceneLoadBVH(scene.c_str(), texSize) : crtSceneCreateStaircase(detail, texSize, 5);
         if (!sc) { std::fprintf(stderr, "Failed to setup kernel scene\n"); return -1; }
+        if (!textureDir.empty() && crtSceneLoadTextureDir(sc, textureDir.c_str()) != 9) {
+            std::cerr << "Failed to load textures" << std::endl; // staircase_scene.h:134-137
+            return -1;
+        }
         const kernel_scene* ksc = crtSceneKernelScene(sc);
         std::fprintf(stderr, " there are %u triangles, and %d bvh nodes\n numPrimitivesPerNode %d\n", ksc->m->numTris, ksc->m->numBvhNodes,
                      ksc->numPrimitivesPerLeaf); // staircase_scene.h:177-179

@@ -105,6 +105,10 @@ def host_lib():
         L.crtSceneFromTriangles.argtypes = [C.POINTER(Triangle), C.c_int, C.c_int, C.c_int]
         L.crtSceneDestroy.argtypes = [C.c_void_p]
         L.crtSceneSaveBVH.argtypes = [C.c_void_p, C.c_char_p]
+        L.crtSceneLoadTexturePNG.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
+        L.crtSceneLoadTextureDir.argtypes = [C.c_void_p, C.c_char_p]
+        L.crtSceneTextureInfo.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_float))]
+        L.crtDecodePNG.argtypes = [C.c_char_p, C.c_ulonglong, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p, C.c_ulonglong]
         L.crtSceneKernelScene.restype = C.POINTER(KernelScene)
         L.crtSceneKernelScene.argtypes = [C.c_void_p]
         L.crtSceneNumRealTriangles.argtypes = [C.c_void_p]
@@ -222,6 +226,21 @@ class Scene:
 
     def save_bvh(self, path):
         return host_lib().crtSceneSaveBVH(self.handle, os.fsencode(path))
+
+    def load_texture_png(self, index, path):
+        """loadTexture (staircase_scene.h:103-118): texture `index` from a PNG file; 0 on success."""
+        return host_lib().crtSceneLoadTexturePNG(self.handle, index, os.fsencode(path))
+
+    def load_texture_dir(self, path):
+        """The nine file names of load_scene (staircase_scene.h:125-133) from a directory; returns how many loaded."""
+        return host_lib().crtSceneLoadTextureDir(self.handle, os.fsencode(path))
+
+    def texture(self, index):
+        """Texture `index` as the floats the device library uploads: (height, width, 3) float32."""
+        w, h, d = C.c_int(), C.c_int(), C.POINTER(C.c_float)()
+        if host_lib().crtSceneTextureInfo(self.handle, index, C.byref(w), C.byref(h), C.byref(d)) != 0:
+            raise IndexError(index)
+        return np.ctypeslib.as_array(d, shape=(h.value, w.value, 3)).copy()
 
     @property
     def num_slots(self):
@@ -353,6 +372,16 @@ def write_ppm(path, img):
 def write_ref(path, img):
     img = np.ascontiguousarray(img, dtype=np.float32)
     return host_lib().crtWriteRef(os.fsencode(path), img.shape[1], img.shape[0], img.ctypes.data)
+
+
+def decode_png(data, flip=False):
+    """PNG bytes -> (height, width, 3) uint8 through the host library's decoder; None when it rejects the stream."""
+    w, h = C.c_int(), C.c_int()
+    if host_lib().crtDecodePNG(data, len(data), 1 if flip else 0, C.byref(w), C.byref(h), None, 0) != 0:
+        return None
+    out = np.zeros((h.value, w.value, 3), np.uint8)
+    rc = host_lib().crtDecodePNG(data, len(data), 1 if flip else 0, C.byref(w), C.byref(h), out.ctypes.data, out.size)
+    return out if rc == 0 else None
 
 
 def read_ref(path, nx, ny):
