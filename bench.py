@@ -404,37 +404,55 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- BASELINE config 4 (strong scaling): ONE frame of 3840x2160 at 1024 spp IN TOTAL, the samples split over the ranks
     # (1024 / N each, rank g on RNG stream g), the un-normalised sums reduced once to rank 0. Not part of `value`; no warm-up.
-    c4 = None
+    c4, c4_tp = None, None
     if args.c4 and not spheres:
         nx4, ny4, total4 = 3840, 2160, 1024
-        mine = shard_samples(total4, world)[rank]
-        acc4 = torch.zeros(ny4 * nx4, 4, device="cuda") if world > 1 else None
-        crt.set_options(device=local_rank, sample_stream=rank, defer_finalize=1 if world > 1 else 0, slots_per_pixel=args.slots)
-        fr4 = crt.Frame(scene, nx4, ny4, depth)
-        if world > 1:
-            L.setRendererAccumDevice(acc4.data_ptr())
-        barrier()
-        t0 = time.perf_counter()
-        L.runRenderer(mine, 8, 8)
-        st4 = crt.stats()
-        ms4 = st4.msTotal
-        if world > 1:
-            ev0.record()
-            dist.reduce(acc4, dst=0, op=dist.ReduceOp.SUM)
-            ev1.record()
-            torch.cuda.synchronize()
-            ms4 += ev0.elapsed_time(ev1)
+        frames4 = {}
+
+        def render_c4(slots):
+            mine = shard_samples(total4, world)[rank]
+            acc4 = torch.zeros(ny4 * nx4, 4, device="cuda") if world > 1 else None
+            crt.set_options(device=local_rank, sample_stream=rank, defer_finalize=1 if world > 1 else 0, slots_per_pixel=slots)
+            fr4 = crt.Frame(scene, nx4, ny4, depth)
+            if world > 1:
+                L.setRendererAccumDevice(acc4.data_ptr())
+            barrier()
+            t0 = time.perf_counter()
+            L.runRenderer(mine, 8, 8)
+            st4 = crt.stats()
+            ms4 = st4.msTotal
+            if world > 1:
+                ev0.record()
+                dist.reduce(acc4, dst=0, op=dist.ReduceOp.SUM)
+                ev1.record()
+                torch.cuda.synchronize()
+                ms4 += ev0.elapsed_time(ev1)
+                if rank == 0:
+                    L.finalizeFrame(total4)
+            barrier()
+            wall4 = (time.perf_counter() - t0) * 1e3
+            ms4 = allmax(ms4)
+            rays4 = allsum(st4.raysExtend + st4.raysShadow)
             if rank == 0:
-                L.finalizeFrame(total4)
-        barrier()
-        wall4 = (time.perf_counter() - t0) * 1e3
-        ms4 = allmax(ms4)
-        rays4 = allsum(st4.raysExtend + st4.raysShadow)
-        fr4.close()
-        del acc4
-        c4 = dict(ms=ms4, wall_ms=wall4, mrays_per_s=rays4 / (ms4 * 1e3), msamples_per_s=nx4 * ny4 * total4 / (ms4 * 1e3), rays=int(rays4),
-                  spp_per_gpu=shard_samples(total4, world), frame="3840x2160", total_spp=total4, scaling="strong",
-                  note="device time of runRenderer (max over ranks) + the NCCL reduce of %d MB per rank + finalize on rank 0" % (nx4 * ny4 * 16 >> 20))
+                frames4[slots] = fr4.frame(copy=True)
+            fr4.close()
+            del acc4
+            return dict(ms=ms4, wall_ms=wall4, mrays_per_s=rays4 / (ms4 * 1e3), msamples_per_s=nx4 * ny4 * total4 / (ms4 * 1e3), rays=int(rays4),
+                        spp_per_gpu=shard_samples(total4, world), frame="3840x2160", total_spp=total4, scaling="strong", slots_per_pixel=max(slots, 1),
+                        note="device time of runRenderer (max over ranks) + the NCCL reduce of %d MB per rank + finalize on rank 0" % (nx4 * ny4 * 16 >> 20))
+
+        c4 = render_c4(args.slots)
+        if args.c4_throughput and args.slots <= 1 and min(shard_samples(total4, world)) % 4 == 0:
+            # the same frame in throughput mode (4 path slots per pixel, each its own RNG stream: no per-pixel serial chain): other
+            # noise, same expectation -- the two frames are compared below
+            c4_tp = render_c4(4)
+            if rank == 0:
+                import numpy as np
+                a, b = frames4[args.slots].astype(np.float64), frames4[4].astype(np.float64)
+                c4_tp["vs_parity_mode"] = dict(speedup=c4["ms"] / c4_tp["ms"], rmse=float(np.sqrt(((a - b) ** 2).mean())), mean_parity=float(a.mean()),
+                                               mean_throughput=float(b.mean()), relative_mean_difference=float(abs(a.mean() - b.mean()) / a.mean()),
+                                               note="two independent 1024-spp estimates of the same frame: rmse is the noise of their difference")
+        frames4.clear()
 
     if rank != 0:
         if dist:
@@ -469,7 +487,7 @@ def run_ours(args, rank, world, local_rank):
                 clocks=clocks, e2e=dict(value=e2e_value, unit="Mrays/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                                         ms_per_step=e2e_ms, steps=e2e_steps,
                                         note="initRenderer (scene upload from caller-owned host memory) + runRenderer + frame read + cleanupRenderer, per step"),
-                gpu_launches=launches, roofline=roof, cpu_baseline=cpu, c4_strong=c4, **extra)
+                gpu_launches=launches, roofline=roof, cpu_baseline=cpu, c4_strong=c4, c4_strong_throughput=c4_tp, **extra)
     print(json.dumps(line))
     if dist:
         dist.destroy_process_group()
@@ -553,6 +571,9 @@ def main():
     ap.add_argument("--detail", type=float, default=1.0)
     ap.add_argument("--tex", type=int, default=1024)
     ap.add_argument("--rays", type=int, default=1 << 26)
+    ap.add_argument("--c4-throughput", dest="c4_throughput", action="store_true",
+                    help="render config 4 a second time with 4 path slots per pixel and compare the two frames (profiles/r02/bench_c3.json: 23.9 s vs 23.1 s "
+                         "in parity mode, means equal to 4e-7: not faster any more, so parity mode stays the default)")
     ap.add_argument("--slots", type=int, default=0, help="path slots per pixel (0/1 = reference RNG streams)")
     ap.add_argument("--no-c4", dest="c4", action="store_false", help="skip the BASELINE config 4 frame (3840x2160, 1024 spp in total: ~30 s on one GPU)")
     ap.add_argument("--bvh", default="median", choices=["median", "sah"],

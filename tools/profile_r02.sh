@@ -2,7 +2,7 @@
 # GPU-box recipe behind profiles/r02/*: every command runs plain first (must exit 0), then under ncu (B200_PROFILING.md).
 cd $GRAFT_REPO_ROOT
 set -x
-python bench.py --steps 3 --warmup 3 > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err || exit 1
+python bench.py --steps 3 --warmup 3 --c4-throughput > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err || exit 1
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_c3_reference.json 2>/dev/null
 python bench.py --workload rtiow --spp 10 --steps 5 --warmup 3 > gpurun_out/bench_c1_rtiow10.json 2>/dev/null
 python bench.py --workload rtiow --spp 100 --steps 5 --warmup 3 > gpurun_out/bench_c2_rtiow100.json 2>/dev/null
