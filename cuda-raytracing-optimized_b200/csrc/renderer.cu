@@ -118,6 +118,9 @@ static T* devAlloc(size_t count) {
 
 // Streams, events and pinned host buffers, created once per process (per device).
 #define CHASE_STREAMS 16
+#define UPLOAD_THREADS 8           // host threads staging one upload (at most; CRT_UPLOAD_THREADS)
+#define UPLOAD_SLOTS 2             // pinned chunks per thread (one being filled while the other is on the bus)
+#define UPLOAD_CHUNK (4u << 20)    // bytes per chunk
 struct HostCache {
     int device = -1;
     cudaStream_t stream = nullptr, streamFast = nullptr;
@@ -127,6 +130,10 @@ struct HostCache {
     void* hostCtlFast = nullptr;  // pinned
     void* fb = nullptr;           // pinned + mapped frame buffer
     size_t fbBytes = 0;
+    // uploads from the caller's pageable memory (hostUpload below)
+    unsigned char* upPinned = nullptr;
+    cudaStream_t upStreams[UPLOAD_THREADS] = {};
+    cudaEvent_t upDone[UPLOAD_THREADS][UPLOAD_SLOTS] = {};
 };
 static thread_local HostCache g_cache;
 
@@ -136,6 +143,13 @@ static void releaseCaches() {
         cudaEventDestroy(g_cache.evLane); cudaEventDestroy(g_cache.evStart); cudaEventDestroy(g_cache.evStop);
         cudaStreamDestroy(g_cache.streamFast); cudaStreamDestroy(g_cache.stream);
         for (auto& cs : g_cache.chaseStreams) cudaStreamDestroy(cs);
+        if (g_cache.upPinned) {
+            cudaFreeHost(g_cache.upPinned);
+            for (int t = 0; t < UPLOAD_THREADS; t++) {
+                cudaStreamDestroy(g_cache.upStreams[t]);
+                for (int k = 0; k < UPLOAD_SLOTS; k++) cudaEventDestroy(g_cache.upDone[t][k]);
+            }
+        }
     }
     g_cache = HostCache();
     arenaFreeAll();
@@ -146,6 +160,94 @@ static void releaseCaches() {
 extern "C" void rendererReleaseCaches() {
     if (g_ctx.initialised) return; // the live frame owns arena memory: call after cleanupRenderer
     releaseCaches();
+}
+
+// Host-to-device copy of caller-owned PAGEABLE memory (the ABI hands over plain host pointers: kernels.h). cudaMemcpy stages such
+// a copy through the driver's own pinned buffer on the calling thread: ~11 GB/s measured on the benchmark scene's 137 MB, i.e.
+// 12.5 of initRenderer's 16.5 ms. Here UPLOAD_THREADS host threads copy alternate chunks into pinned buffers of the library
+// (cached per process like the streams) and send each chunk on a stream of their own, so staging and bus transfers overlap.
+// Blocking: returns when the bytes are on the device. Small copies take the plain path.
+static void uploadResources(HostCache& hc) {
+    if (hc.upPinned) return;
+    CRT_CHECK(cudaMallocHost(&hc.upPinned, (size_t)UPLOAD_THREADS * UPLOAD_SLOTS * UPLOAD_CHUNK));
+    for (int t = 0; t < UPLOAD_THREADS; t++) {
+        CRT_CHECK(cudaStreamCreateWithFlags(&hc.upStreams[t], cudaStreamNonBlocking));
+        for (int k = 0; k < UPLOAD_SLOTS; k++) CRT_CHECK(cudaEventCreateWithFlags(&hc.upDone[t][k], cudaEventDisableTiming));
+    }
+}
+
+static void hostUpload(HostCache& hc, void* dst, const void* src, size_t bytes) {
+    static const int threads = std::getenv("CRT_UPLOAD_THREADS") ? std::max(1, std::min(UPLOAD_THREADS, std::atoi(std::getenv("CRT_UPLOAD_THREADS")))) : 6; // (measured on the benchmark scene, init in ms: 2 -> 10.3, 4 -> 8.0, 6 -> 7.3, 8 -> 7.4)
+    static const size_t chunk = std::getenv("CRT_UPLOAD_CHUNK_KB") ? std::max((size_t)64 << 10, std::min((size_t)UPLOAD_CHUNK, (size_t)std::atoi(std::getenv("CRT_UPLOAD_CHUNK_KB")) << 10)) : (size_t)1 << 20; // (1 MB chunks: 7.3 ms, 4 MB: 9.1)
+    if (bytes < 2 * chunk) {
+        if (bytes) CRT_CHECK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+        return;
+    }
+    uploadResources(hc);
+    int dev = 0;
+    CRT_CHECK(cudaGetDevice(&dev));
+    const size_t chunks = (bytes + chunk - 1) / chunk;
+    auto work = [&hc, dst, src, bytes, chunks, dev](int t) {
+        CRT_CHECK(cudaSetDevice(dev));
+        unsigned int turn = 0;
+        for (size_t ch = (size_t)t; ch < chunks; ch += (size_t)threads, turn++) {
+            const int slot = (int)(turn % UPLOAD_SLOTS);
+            unsigned char* stage = hc.upPinned + ((size_t)t * UPLOAD_SLOTS + slot) * UPLOAD_CHUNK;
+            if (turn >= UPLOAD_SLOTS) CRT_CHECK(cudaEventSynchronize(hc.upDone[t][slot])); // the chunk sent from this buffer two turns ago
+            const size_t off = ch * chunk, len = std::min(chunk, bytes - off);
+            std::memcpy(stage, (const unsigned char*)src + off, len);
+            CRT_CHECK(cudaMemcpyAsync((unsigned char*)dst + off, stage, len, cudaMemcpyHostToDevice, hc.upStreams[t]));
+            CRT_CHECK(cudaEventRecord(hc.upDone[t][slot], hc.upStreams[t]));
+        }
+        CRT_CHECK(cudaStreamSynchronize(hc.upStreams[t]));
+    };
+    std::thread helpers[UPLOAD_THREADS - 1];
+    for (int t = 1; t < threads; t++) helpers[t - 1] = std::thread(work, t);
+    work(0);
+    for (int t = 1; t < threads; t++) helpers[t - 1].join();
+}
+
+// The way back: device memory into the caller's pageable memory, same buffers and threads. Per thread the bus transfer of chunk
+// k + 1 runs while chunk k is copied out of its pinned buffer. The caller orders `dSrc` (device-synchronised) beforehand.
+static void hostDownload(HostCache& hc, void* dst, const void* dSrc, size_t bytes) {
+    static const int threads = std::getenv("CRT_UPLOAD_THREADS") ? std::max(1, std::min(UPLOAD_THREADS, std::atoi(std::getenv("CRT_UPLOAD_THREADS")))) : 6;
+    const size_t chunk = (size_t)1 << 20;
+    if (bytes < 2 * chunk) {
+        if (bytes) CRT_CHECK(cudaMemcpy(dst, dSrc, bytes, cudaMemcpyDeviceToHost));
+        return;
+    }
+    uploadResources(hc);
+    int dev = 0;
+    CRT_CHECK(cudaGetDevice(&dev));
+    const size_t chunks = (bytes + chunk - 1) / chunk;
+    auto work = [&hc, dst, dSrc, bytes, chunks, chunk, dev](int t) {
+        CRT_CHECK(cudaSetDevice(dev));
+        unsigned int turn = 0;
+        size_t prevOff = 0, prevLen = 0;
+        for (size_t ch = (size_t)t; ch < chunks; ch += (size_t)threads, turn++) {
+            const int slot = (int)(turn % UPLOAD_SLOTS);
+            unsigned char* stage = hc.upPinned + ((size_t)t * UPLOAD_SLOTS + slot) * UPLOAD_CHUNK;
+            const size_t off = ch * chunk, len = std::min(chunk, bytes - off);
+            CRT_CHECK(cudaMemcpyAsync(stage, (const unsigned char*)dSrc + off, len, cudaMemcpyDeviceToHost, hc.upStreams[t]));
+            CRT_CHECK(cudaEventRecord(hc.upDone[t][slot], hc.upStreams[t]));
+            if (turn > 0) { // the previous chunk has landed in the other buffer: hand it to the caller while this one travels
+                const int prev = (int)((turn - 1) % UPLOAD_SLOTS);
+                CRT_CHECK(cudaEventSynchronize(hc.upDone[t][prev]));
+                std::memcpy((unsigned char*)dst + prevOff, hc.upPinned + ((size_t)t * UPLOAD_SLOTS + prev) * UPLOAD_CHUNK, prevLen);
+            }
+            prevOff = off;
+            prevLen = len;
+        }
+        if (turn > 0) {
+            const int prev = (int)((turn - 1) % UPLOAD_SLOTS);
+            CRT_CHECK(cudaEventSynchronize(hc.upDone[t][prev]));
+            std::memcpy((unsigned char*)dst + prevOff, hc.upPinned + ((size_t)t * UPLOAD_SLOTS + prev) * UPLOAD_CHUNK, prevLen);
+        }
+    };
+    std::thread helpers[UPLOAD_THREADS - 1];
+    for (int t = 1; t < threads; t++) helpers[t - 1] = std::thread(work, t);
+    work(0);
+    for (int t = 1; t < threads; t++) helpers[t - 1].join();
 }
 
 static void freeWavefront(RendererContext& c) { // everything sized by the slot count; `accum` is per pixel and stays
@@ -436,9 +538,24 @@ extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb,
     std::thread wideBuilder;
     if (hostBuild && c.traversal != TRAVERSAL_EXACT && numSlots > 0)
         wideBuilder = std::thread([&] { wideBuilt = buildWideBvh(m->tris, numSlots, 0, wideHost); });
+    // textures: float RGB, nearest lookup (kernels.cu:620-645). They are most of the scene's bytes (113 of 137 MB on the benchmark);
+    // uploaded below, after the geometry, while the device re-tiles it.
+    c.numTextures = sc.numTextures;
+    std::vector<float*> texPtr(sc.numTextures > 0 ? sc.numTextures : 1, nullptr);
+    std::vector<int> texW(texPtr.size(), 0), texH(texPtr.size(), 0);
+    for (int i = 0; i < sc.numTextures; i++) {
+        const stexture& t = sc.textures[i];
+        texW[i] = t.width;
+        texH[i] = t.height;
+        texPtr[i] = (float*)arenaAlloc((size_t)t.width * t.height * 3 * sizeof(float));
+    }
+    c.texPtrHost = texPtr;
+    c.texData = devAlloc<float*>(texPtr.size());
+    c.texWidth = devAlloc<int>(texPtr.size());
+    c.texHeight = devAlloc<int>(texPtr.size());
     // triangles: upload the caller's 64-byte records once, re-tile on the device, drop the staging copy
     float* staging = (float*)arenaAlloc((size_t)(numSlots ? numSlots : 1) * sizeof(triangle));
-    CRT_CHECK(cudaMemcpy(staging, m->tris, (size_t)numSlots * sizeof(triangle), cudaMemcpyHostToDevice));
+    hostUpload(g_cache, staging, m->tris, (size_t)numSlots * sizeof(triangle));
     const unsigned int primsPerLeaf = sc.numPrimitivesPerLeaf > 0 ? (unsigned int)sc.numPrimitivesPerLeaf : 1u;
     const unsigned int leafBytes = 32u * primsPerLeaf + 32u * ((primsPerLeaf + 7u) / 8u);
     const size_t numLeaves = ((size_t)numSlots + primsPerLeaf - 1) / primsPerLeaf;
@@ -457,14 +574,26 @@ extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb,
     const size_t nodeBytes = (size_t)m->numBvhNodes * sizeof(bvh_node);
     const unsigned int firstLeaf = (unsigned int)(m->numBvhNodes / 2); // kernels.cu:614
     float* nodeStaging = (float*)arenaAlloc(nodeBytes + 64);
-    CRT_CHECK(cudaMemcpy(nodeStaging, m->bvh, nodeBytes, cudaMemcpyHostToDevice));
+    hostUpload(g_cache, nodeStaging, m->bvh, nodeBytes);
     c.nodes = devAlloc<float4>(4 * (size_t)(firstLeaf ? firstLeaf : 1) + 8);
     if (firstLeaf) {
         swizzleNodesKernel<<<(firstLeaf + 255) / 256, 256>>>(nodeStaging, firstLeaf, c.nodes);
         CRT_CHECK(cudaGetLastError());
     }
-    CRT_CHECK(cudaDeviceSynchronize()); // the re-tiling kernels ran on the default stream, the frame runs on c.stream
     pt.mark("init: nodes");
+    // the textures go up from a helper thread (with this thread's upload buffers, which this thread does not touch again before
+    // the join) while this thread builds the tree: the build is kernels + small read-backs, the upload is host memcpy + bus
+    HostCache* uploadCache = &g_cache;
+    int uploadDevice = 0;
+    CRT_CHECK(cudaGetDevice(&uploadDevice));
+    std::thread texUploader([&sc, &texPtr, uploadCache, uploadDevice] {
+        CRT_CHECK(cudaSetDevice(uploadDevice));
+        for (int i = 0; i < sc.numTextures; i++) {
+            const stexture& t = sc.textures[i];
+            hostUpload(*uploadCache, texPtr[i], t.data, (size_t)t.width * t.height * 3 * sizeof(float));
+        }
+    });
+    CRT_CHECK(cudaDeviceSynchronize()); // the re-tiling kernels ran on the default stream, the frame runs on c.stream
 
     c.mesh.nodes = c.nodes;
     c.mesh.tris = c.triGeom;
@@ -489,27 +618,11 @@ extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb,
     c.materials = devAlloc<float4>(mats.size());
     CRT_CHECK(cudaMemcpy(c.materials, mats.data(), mats.size() * sizeof(float4), cudaMemcpyHostToDevice));
 
-    // textures: float RGB, nearest lookup (kernels.cu:620-645)
-    c.numTextures = sc.numTextures;
-    std::vector<float*> texPtr(sc.numTextures > 0 ? sc.numTextures : 1, nullptr);
-    std::vector<int> texW(texPtr.size(), 0), texH(texPtr.size(), 0);
-    for (int i = 0; i < sc.numTextures; i++) {
-        const stexture& t = sc.textures[i];
-        texW[i] = t.width;
-        texH[i] = t.height;
-        const size_t bytes = (size_t)t.width * t.height * 3 * sizeof(float);
-        texPtr[i] = (float*)arenaAlloc(bytes);
-        CRT_CHECK(cudaMemcpy(texPtr[i], t.data, bytes, cudaMemcpyHostToDevice));
-    }
-    c.texPtrHost = texPtr;
-    c.texData = devAlloc<float*>(texPtr.size());
-    c.texWidth = devAlloc<int>(texPtr.size());
-    c.texHeight = devAlloc<int>(texPtr.size());
     CRT_CHECK(cudaMemcpy(c.texData, texPtr.data(), texPtr.size() * sizeof(float*), cudaMemcpyHostToDevice));
     CRT_CHECK(cudaMemcpy(c.texWidth, texW.data(), texW.size() * sizeof(int), cudaMemcpyHostToDevice));
     CRT_CHECK(cudaMemcpy(c.texHeight, texH.data(), texH.size() * sizeof(int), cudaMemcpyHostToDevice));
 
-    pt.mark("init: materials+textures");
+    pt.mark("init: materials");
 
     // the wide tree: built on the device from the staged triangles (or by the host builder), leaf triangles re-tiled on the device
     c.wide = WideView{};
@@ -597,6 +710,8 @@ extern "C" void initRenderer(const kernel_scene sc, const camera cam, vec3** fb,
     }
     // the uploads and scene kernels above ran on the legacy stream (some from pageable memory); the frame runs on non-blocking
     // streams, which do not order against it
+    texUploader.join();
+    pt.mark("init: textures (helper thread) joined");
     CRT_CHECK(cudaDeviceSynchronize());
 }
 
@@ -1214,13 +1329,13 @@ extern "C" void intersectBatch(const float* origins, const float* dirs, long lon
     CRT_CHECK(cudaMalloc((void**)&dD, (size_t)n * sizeof(float4)));
     CRT_CHECK(cudaMalloc((void**)&dH, (size_t)n * sizeof(float4)));
     CRT_CHECK(cudaMalloc((void**)&dM, (size_t)n * sizeof(int)));
-    CRT_CHECK(cudaMemcpy(dO, o.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice));
-    CRT_CHECK(cudaMemcpy(dD, d.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice));
-    CRT_CHECK(cudaDeviceSynchronize()); // (pageable copies: the query runs on a non-blocking stream)
+    hostUpload(g_cache, dO, o.data(), (size_t)n * sizeof(float4));
+    hostUpload(g_cache, dD, d.data(), (size_t)n * sizeof(float4));
+    CRT_CHECK(cudaDeviceSynchronize()); // (the query runs on a non-blocking stream)
     intersectBatchDevice(dO, dD, n, dH, dM);
     std::vector<float4> h((size_t)n);
-    CRT_CHECK(cudaMemcpy(h.data(), dH, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));
-    if (outMeshId) CRT_CHECK(cudaMemcpy(outMeshId, dM, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    hostDownload(g_cache, h.data(), dH, (size_t)n * sizeof(float4));
+    if (outMeshId) hostDownload(g_cache, outMeshId, dM, (size_t)n * sizeof(int));
     for (long long i = 0; i < n; i++) {
         if (outT) outT[i] = h[i].x;
         if (outTriId) std::memcpy(&outTriId[i], &h[i].w, 4);
@@ -1268,10 +1383,11 @@ extern "C" void* rendererDeviceAlloc(size_t bytes) {
 }
 extern "C" void rendererDeviceFree(void* p) { cudaFree(p); }
 extern "C" void rendererCopyToHost(void* dst, const void* dSrc, size_t bytes) {
-    CRT_CHECK(cudaMemcpy(dst, dSrc, bytes, cudaMemcpyDeviceToHost));
+    CRT_CHECK(cudaDeviceSynchronize()); // (what a pageable cudaMemcpy on the legacy stream implied for the caller's earlier work)
+    hostDownload(g_cache, dst, dSrc, bytes);
 }
 extern "C" void rendererCopyToDevice(void* dDst, const void* src, size_t bytes) {
-    CRT_CHECK(cudaMemcpy(dDst, src, bytes, cudaMemcpyHostToDevice));
+    hostUpload(g_cache, dDst, src, bytes);
 }
 
 #include "spheres_path.cuh"
