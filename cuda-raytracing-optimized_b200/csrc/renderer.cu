@@ -906,17 +906,37 @@ void crtRunMesh(RendererContext& c, int ns, bool resume) {
                                   ((long long)c.counting << 60) ^ ((long long)c.maxDepth << 40) ^ ((long long)mp.streamBase << 48) ^
                                   ((long long)mp.traceBudget << 12) ^ ((long long)mp.traceMinActive << 4) ^ ((long long)chase << 59) ^
                                   ((long long)blocksA << 30) ^ ((long long)shadeBlocksA << 17) ^ ((long long)(useWideTree(c) ? 1 + c.traversal : 0) << 56);
-            if (!c.graphExec || c.graphKey != key) {
+            // A captured graph carries its launch arguments BY VALUE (the whole MeshState with its queue and accumulator pointers,
+            // the scene views, the camera), so it is re-used only when every one of those bytes is what it was at capture time --
+            // a caller that changes the accumulator, the slot layout or an option between two runRenderer calls gets a new graph.
+            std::vector<unsigned char> signature;
+            {
+                const ShadeScene sceneNow = shadeScene(c);
+                const int scalars[6] = {batch, blocksA, shadeBlocksA, c.wideTraceBlocks, (int)c.counting, useWideTree(c) ? 1 + (int)c.traversal : 0};
+                auto put = [&signature](const void* p, size_t n) { signature.insert(signature.end(), (const unsigned char*)p, (const unsigned char*)p + n); };
+                put(&mp, sizeof(mp)); put(&c.mesh, sizeof(c.mesh)); put(&c.wide, sizeof(c.wide)); put(&sceneNow, sizeof(sceneNow)); put(&c.cam, sizeof(c.cam));
+                put(scalars, sizeof(scalars));
+            }
+            if (!c.graphExec || c.graphKey != key || c.graphSignature != signature) {
                 if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
                 c.graphExec = captureMeshBatch(c, mp, stream, batch, blocksA, shadeBlocksA);
                 c.graphKey = key;
+                c.graphSignature.swap(signature);
                 pt.mark("run: graph capture");
             }
             const ChaseRing ring = c.ring;
             const ShadeScene scene = shadeScene(c);
             int wave = 0;
             auto launchWave = [&](int blocks) { // after a hand-over: the wave starts once the commit kernel of `stream` has run
-                cudaStream_t on = g_cache.chaseStreams[wave++ % CHASE_STREAMS];
+                // a stream whose previous wave has finished, if there is one (a wave can run for most of the frame: the next wave
+                // must not queue behind it); else round robin
+                cudaStream_t on = g_cache.chaseStreams[wave % CHASE_STREAMS];
+                for (int k = 0; k < CHASE_STREAMS; k++) {
+                    cudaStream_t candidate = g_cache.chaseStreams[(wave + k) % CHASE_STREAMS];
+                    if (cudaStreamQuery(candidate) == cudaSuccess) { on = candidate; break; }
+                }
+                cudaGetLastError(); // (cudaErrorNotReady of a busy stream is not an error)
+                wave++;
                 CRT_CHECK(cudaEventRecord(c.evLane, stream));
                 CRT_CHECK(cudaStreamWaitEvent(on, c.evLane, 0));
                 if (useWideTree(c)) {

@@ -68,6 +68,7 @@ struct RendererContext {
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     cudaGraphExec_t graphExec = nullptr;
     long long graphKey = -1;
+    std::vector<unsigned char> graphSignature; // bytes of every argument the captured launches carry (crtRunMesh compares before re-using the graph)
 
     int samplesDone = 0; // samples per pixel in the sums (runRenderer sets, continueRenderer adds)
     int traceBlocks = 0; // persistent grid of traceKernel: one resident wave

@@ -560,6 +560,29 @@ def _gpu_count():
         return 0
 
 
+def test_changing_the_accumulator_between_runs_gets_a_fresh_graph(crt, medium_scene):
+    """The captured CUDA graph carries the accumulator pointer by value (round-1 advisor finding): a caller that hands in its own
+    device buffer AFTER a first runRenderer of the same initRenderer must still get the frame in that buffer, not in the old one."""
+    L = crt.device_lib()
+    nx, ny, ns = 96, 64, 4
+    crt.set_options(defer_finalize=1)
+    with crt.Frame(medium_scene, nx, ny, 16) as fr:
+        L.runRenderer(ns, 8, 8)
+        L.finalizeFrame(ns)
+        first = fr.frame(copy=True)
+        own = L.rendererDeviceAlloc(16 * nx * ny)
+        L.setRendererAccumDevice(own)
+        L.runRenderer(ns, 8, 8)
+        sums = np.zeros((ny * nx, 4), np.float32)
+        L.rendererCopyToHost(sums.ctypes.data, own, sums.nbytes)
+        L.finalizeFrame(ns)
+        second = fr.frame(copy=True)
+        L.rendererDeviceFree(own)
+    crt.set_options()
+    assert np.array_equal(first, second)
+    assert np.array_equal((sums[:, :3] / np.float32(ns)).reshape(ny, nx, 3), first)
+
+
 @pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs in the box")
 def test_multi_gpu_inside_the_library(crt, medium_scene):
     """setRendererGpus(2): one host thread per device inside libcrt_b200.so, sample streams 0 and 1, one ncclReduce, fb on device 0.
