@@ -727,7 +727,10 @@ __global__ void __launch_bounds__(WIDE_TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wi
 // those whose `ready` flag is set -- the same set, but state loads and stores are coalesced, neighbouring lanes are
 // neighbouring pixels (same materials, same texture lines), and the trace queue it writes comes out in slot order, so the
 // next trace launch gets coalesced refills and rays of neighbouring pixels in one warp.
-__global__ void __launch_bounds__(WF_BLOCK, 4) meshShadeKernel(MeshState st, ShadeScene sc, CameraDev cam, int cur) {
+#ifndef SHADE_BLOCKS_PER_SM
+#define SHADE_BLOCKS_PER_SM 4
+#endif
+__global__ void __launch_bounds__(WF_BLOCK, SHADE_BLOCKS_PER_SM) meshShadeKernel(MeshState st, ShadeScene sc, CameraDev cam, int cur) {
     MeshControl* ctl = st.ctl;
     const unsigned int queued = ctl->shadeCount[cur];
     const bool dense = queued > st.numSlots / SHADE_DENSE_FRACTION;
