@@ -162,6 +162,14 @@ extern "C" void rendererReleaseCaches() {
     releaseCaches();
 }
 
+// fb = sums / ns (kernels.cu:568) on `stream`: the division on the device, then one bulk copy into the caller's pinned frame buffer.
+void finalizeFrameTo(RendererContext& c, const float4* accum, float ns, cudaStream_t stream) {
+    const unsigned int npix = (unsigned int)c.nx * (unsigned int)c.ny;
+    if (!npix) return;
+    finalizeKernel<<<(npix + 255) / 256, 256, 0, stream>>>(accum, c.fbDevice, npix, ns);
+    CRT_CHECK(cudaMemcpyAsync(c.fb, c.fbDevice, (size_t)npix * 3 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+}
+
 // Host-to-device copy of caller-owned PAGEABLE memory (the ABI hands over plain host pointers: kernels.h). cudaMemcpy stages such
 // a copy through the driver's own pinned buffer on the calling thread: ~11 GB/s measured on the benchmark scene's 137 MB, i.e.
 // 12.5 of initRenderer's 16.5 ms. Here UPLOAD_THREADS host threads copy alternate chunks into pinned buffers of the library
@@ -384,16 +392,19 @@ static void initCommon(RendererContext& c, const camera& cam, vec3** fb, int nx,
     c.batchScratch = devAlloc<unsigned long long>(8);
     const size_t npix = (size_t)nx * ny;
     // The frame buffer the caller reads after runRenderer (kernels.cu:578-580 uses managed memory; main.cpp:105,119 only
-    // ever dereferences it on the host): pinned, device-mapped host memory that finalizeKernel writes directly, so the frame
-    // needs no page-fault migration (7.4 ms for 1200x800) and no extra copy.
+    // ever dereferences it on the host): pinned host memory, so the frame needs no page-fault migration (7.4 ms for 1200x800).
+    // finalizeKernel writes the normalised frame into device memory and ONE bulk copy takes it across the bus: round 1 let the
+    // kernel store straight into the mapped buffer, which the ncu launch list showed at 3.3 ms for 11.5 MB (4-byte stores over
+    // PCIe) in every frame of every path -- the copy engine needs 0.25 ms.
     const size_t fbBytes = (npix ? npix : 1) * sizeof(vec3);
     if (g_cache.fbBytes < fbBytes) {
         if (g_cache.fb) CRT_CHECK(cudaFreeHost(g_cache.fb));
-        CRT_CHECK(cudaHostAlloc(&g_cache.fb, fbBytes, cudaHostAllocMapped));
+        CRT_CHECK(cudaHostAlloc(&g_cache.fb, fbBytes, cudaHostAllocDefault));
         g_cache.fbBytes = fbBytes;
     }
     c.fb = (vec3*)g_cache.fb;
     if (fb) *fb = c.fb;
+    c.fbDevice = devAlloc<float>(3 * (npix ? npix : 1));
     c.wf.accum = devAlloc<float4>(npix);
     c.ownsAccum = true;
     std::memset(&c.stats, 0, sizeof(c.stats));
@@ -1036,7 +1047,7 @@ void crtRunMesh(RendererContext& c, int ns, bool resume) {
 
     if (npix > 0 && ns > 0 && c.maxDepth > 0) c.samplesDone += ns;
     if (!c.opts.deferFinalize) {
-        if (npix) finalizeKernel<<<(npix + 255) / 256, 256, 0, stream>>>(mp.accum, (float*)c.fb, npix, float(resume ? c.samplesDone : ns));
+        finalizeFrameTo(c, mp.accum, float(resume ? c.samplesDone : ns), stream);
         launches += 1;
     }
     CRT_CHECK(cudaEventRecord(c.evStop, stream));
@@ -1156,8 +1167,7 @@ extern "C" int loadRendererCheckpoint(const char* path) {
 extern "C" void finalizeFrame(int nsTotal) {
     RendererContext& c = g_ctx;
     if (!c.initialised) return;
-    const unsigned int npix = (unsigned int)c.nx * (unsigned int)c.ny;
-    if (npix) finalizeKernel<<<(npix + 255) / 256, 256, 0, c.stream>>>(c.wf.accum, (float*)c.fb, npix, float(nsTotal));
+    finalizeFrameTo(c, c.wf.accum, float(nsTotal), c.stream);
     CRT_CHECK(cudaGetLastError());
     CRT_CHECK(cudaStreamSynchronize(c.stream));
 }

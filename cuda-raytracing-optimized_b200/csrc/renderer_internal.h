@@ -26,7 +26,8 @@ struct RendererContext {
     int nx = 0, ny = 0, maxDepth = 0;
     CameraDev cam;
     LightDesc light;
-    vec3* fb = nullptr; // pinned, device-mapped host memory handed to the caller (kernels.cu:578-580 uses managed memory)
+    vec3* fb = nullptr; // pinned host memory handed to the caller (kernels.cu:578-580 uses managed memory)
+    float* fbDevice = nullptr; // the normalised frame on the device: finalizeFrameTo() writes it, one bulk copy takes it to `fb`
 
     // mesh scene
     float4* triGeom = nullptr;
@@ -86,3 +87,4 @@ extern thread_local renderer_options g_opts;
 
 void crtRunMesh(RendererContext& c, int ns, bool resume);
 void crtRunSpheres(RendererContext& c, int ns);
+void finalizeFrameTo(RendererContext& c, const float4* accum, float ns, cudaStream_t stream); // fb = sums / ns, on the device, then one bulk copy

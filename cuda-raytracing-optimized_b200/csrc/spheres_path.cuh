@@ -334,6 +334,9 @@ __global__ void finishSpheresDoneKernel(WfControl* ctl) { ctl->countActive = 0; 
 // same per-pixel order of every floating-point operation as the wavefront kernels (tests compare the frames bit for bit).
 #define SPH_MEGA_BLOCK 128 // (64 x 16, 256 x 4 and 32 x 32 measure the same; 128 x 6 with 80 registers is 5 % slower)
 #define SPH_MEGA_BLOCKS_PER_SM 8
+#ifndef SPH_ITEM_CHUNK
+#define SPH_ITEM_CHUNK 32u // (config 2: 8 -> 28.4 ms, 16 -> 26.8, 32 -> 26.9, 64 -> 29.5, 128 -> 33.3; one atomic per need: 28.7)
+#endif
 
 // The shape of closestSphere's loops matters more than their content: the same walk written as "at most N box steps, then look
 // what the lane needs" (a counted inner loop) ran at HALF the speed (73 ms) -- ptxas then no longer re-joins the lanes before
@@ -352,29 +355,41 @@ spheresMegaKernel(WfState st, const float4* __restrict__ mats, int maxDepth, Sph
     unsigned int pixel = 0;
     int sample = 0;
     bool live = false, exhausted = false;
+    unsigned int poolBase = 0, poolLeft = 0; // the warp's pool of work items (warp-uniform)
     unsigned int rays = 0, trips = 0;
     unsigned long long boxTests = 0, sphereTests = 0; // COUNT only
     while (true) {
-        if (!exhausted) {
-            const unsigned int need = __ballot_sync(0xFFFFFFFFu, !live);
-            if (need) {
-                const unsigned int leader = __ffs(need) - 1;
-                unsigned int base = 0;
-                if (laneId() == leader) base = atomicAdd(&ctl->cursorExtend, (unsigned int)__popc(need));
-                base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                if (!live) {
-                    const unsigned int item = base + __popc(need & ((1u << laneId()) - 1u));
-                    if (item < numItems) {
-                        live = true;
-                        pixel = item % npix;
-                        const unsigned int stream = streamBase * (unsigned int)slotsPerPixel + item / npix;
-                        p.rng = pathSeed(pixel + stream * npix); // kernels.cu:541-542 (stream 0)
-                        sample = 0;
-                        sum = mk3(0.0f, 0.0f, 0.0f);
-                        startSpherePath(p, cam, nx, ny, pixel);
-                    }
+        // work items come from the global cursor SPH_ITEM_CHUNK at a time into a pool of the warp; lanes draw from the pool with a
+        // ballot (at 10 spp some lane of a warp finishes a pixel in almost every turn: one global atomic per turn, with its round
+        // trip in front of every lane, halved the ray rate of config 1)
+        if (!exhausted || poolLeft != 0u) {
+            unsigned int need = __ballot_sync(0xFFFFFFFFu, !live);
+            while (need != 0u) {
+                if (poolLeft == 0u) {
+                    if (exhausted) break;
+                    unsigned int base = 0;
+                    if (laneId() == 0) base = atomicAdd(&ctl->cursorExtend, SPH_ITEM_CHUNK);
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    exhausted = base + SPH_ITEM_CHUNK >= numItems;
+                    if (base >= numItems) break;
+                    poolBase = base;
+                    poolLeft = min(SPH_ITEM_CHUNK, numItems - base);
                 }
-                exhausted = base + (unsigned int)__popc(need) >= numItems;
+                const unsigned int take = min((unsigned int)__popc(need), poolLeft);
+                const unsigned int rank = __popc(need & ((1u << laneId()) - 1u));
+                if (!live && rank < take) {
+                    const unsigned int item = poolBase + rank;
+                    live = true;
+                    pixel = item % npix;
+                    const unsigned int stream = streamBase * (unsigned int)slotsPerPixel + item / npix;
+                    p.rng = pathSeed(pixel + stream * npix); // kernels.cu:541-542 (stream 0)
+                    sample = 0;
+                    sum = mk3(0.0f, 0.0f, 0.0f);
+                    startSpherePath(p, cam, nx, ny, pixel);
+                }
+                poolBase += take;
+                poolLeft -= take;
+                need = __ballot_sync(0xFFFFFFFFu, !live);
             }
         }
         if (!__any_sync(0xFFFFFFFFu, live)) break;
@@ -448,6 +463,7 @@ static void buildSphereBvh(RendererContext& c, const std::vector<float4>& sp, in
         std::vector<float4>& leafSpheres;
         std::vector<unsigned int>& leafIds;
         size_t maxLeaf;
+        bool sah;
         int build(std::vector<unsigned int>& idx, size_t lo, size_t hi) {
             Node nd;
             float cmin[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, cmax[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
@@ -472,20 +488,49 @@ static void buildSphereBvh(RendererContext& c, const std::vector<float4>& sp, in
                 tree[me].leafWord = (unsigned int)leafSpheres.size() | ((unsigned int)(hi - lo) << 24);
                 for (size_t k = lo; k < hi; k++) { leafSpheres.push_back(sp[idx[k]]); leafIds.push_back(idx[k]); }
             } else {
+                // split: the plane of least surface-area cost over all three axes and all positions (a few hundred spheres: the full
+                // sweep costs nothing); CRT_SPHERES_SAH=0: the median of the longest axis (round 1's tree)
                 int axis = 0;
                 for (int a = 1; a < 3; a++) if (cmax[a] - cmin[a] > cmax[axis] - cmin[axis]) axis = a;
-                const size_t mid = (lo + hi) / 2;
-                std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](unsigned int p, unsigned int q) {
-                    const float a = axis == 0 ? sp[p].x : axis == 1 ? sp[p].y : sp[p].z;
-                    const float b = axis == 0 ? sp[q].x : axis == 1 ? sp[q].y : sp[q].z;
-                    return a < b || (a == b && p < q);
-                });
+                size_t mid = (lo + hi) / 2;
+                auto key = [&](unsigned int p, int a) { return a == 0 ? sp[p].x : a == 1 ? sp[p].y : sp[p].z; };
+                if (sah) {
+                    const size_t n = hi - lo;
+                    double best = 1e300;
+                    std::vector<unsigned int> order(idx.begin() + lo, idx.begin() + hi), bestOrder;
+                    std::vector<double> rightArea(n + 1, 0.0);
+                    for (int a = 0; a < 3; a++) {
+                        std::sort(order.begin(), order.end(), [&](unsigned int p, unsigned int q) { return key(p, a) < key(q, a) || (key(p, a) == key(q, a) && p < q); });
+                        auto grow = [&](float* mn, float* mx, unsigned int p) {
+                            const float4 s4 = sp[p];
+                            const float ce[3] = {s4.x, s4.y, s4.z};
+                            for (int d = 0; d < 3; d++) { mn[d] = std::min(mn[d], ce[d] - s4.w); mx[d] = std::max(mx[d], ce[d] + s4.w); }
+                        };
+                        auto area = [](const float* mn, const float* mx) {
+                            const double ex = mx[0] - mn[0], ey = mx[1] - mn[1], ez = mx[2] - mn[2];
+                            return ex * ey + ey * ez + ez * ex;
+                        };
+                        float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+                        for (size_t k = n; k-- > 1;) { grow(mn, mx, order[k]); rightArea[k] = area(mn, mx); }
+                        float ln[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, lx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+                        for (size_t k = 1; k < n; k++) {
+                            grow(ln, lx, order[k - 1]);
+                            const double cost = area(ln, lx) * (double)k + rightArea[k] * (double)(n - k);
+                            if (cost < best) { best = cost; mid = lo + k; axis = a; bestOrder = order; }
+                        }
+                    }
+                    std::copy(bestOrder.begin(), bestOrder.end(), idx.begin() + lo);
+                } else {
+                    std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](unsigned int p, unsigned int q) {
+                        return key(p, axis) < key(q, axis) || (key(p, axis) == key(q, axis) && p < q);
+                    });
+                }
                 const int l = build(idx, lo, mid), r = build(idx, mid, hi);
                 tree[me].left = l; tree[me].right = r; tree[me].axis = axis;
             }
             return me;
         }
-    } builder{sp, tree, leafSpheres, leafIds, maxLeaf};
+    } builder{sp, tree, leafSpheres, leafIds, maxLeaf, !(std::getenv("CRT_SPHERES_SAH") && std::getenv("CRT_SPHERES_SAH")[0] == '0')};
     if (!rest.empty()) builder.build(rest, 0, rest.size());
     const unsigned int numNodes = (unsigned int)tree.size();
     const unsigned int numOrders = ordered ? 8u : 1u;
@@ -645,7 +690,7 @@ void crtRunSpheres(RendererContext& c, int ns) {
         CRT_CHECK(cudaMemcpyAsync(c.hostCtl, c.wf.ctl, sizeof(WfControl), cudaMemcpyDeviceToHost, stream));
     }
     if (!c.opts.deferFinalize) {
-        if (npix) finalizeKernel<<<(npix + 255) / 256, 256, 0, stream>>>(c.wf.accum, (float*)c.fb, npix, float(ns));
+        finalizeFrameTo(c, c.wf.accum, float(ns), stream);
         launches += 1;
     }
     CRT_CHECK(cudaEventRecord(c.evStop, stream));
