@@ -81,8 +81,9 @@ const uint8_t kLengthExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2
 const uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
 const uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 
-bool inflateBlock(BitReader& br, const Huffman& lit, const Huffman& dist, std::vector<uint8_t>& out) {
+bool inflateBlock(BitReader& br, const Huffman& lit, const Huffman& dist, std::vector<uint8_t>& out, size_t limit) {
     while (true) {
+        if (out.size() > limit) return false; // more data than the image header allows: not a texture, stop inflating
         const int sym = lit.decode(br);
         if (sym < 0) return false;
         if (sym < 256) {
@@ -105,7 +106,8 @@ bool inflateBlock(BitReader& br, const Huffman& lit, const Huffman& dist, std::v
 }
 
 // zlib stream (RFC 1950) holding deflate blocks (RFC 1951).
-bool inflateZlib(const uint8_t* data, size_t n, std::vector<uint8_t>& out) {
+// `limit`: the largest output the caller accepts (the scanline bytes the PNG header implies); a stream that inflates to more fails.
+bool inflateZlib(const uint8_t* data, size_t n, std::vector<uint8_t>& out, size_t limit) {
     if (n < 6) return false;
     if ((data[0] & 0x0F) != 8 || ((data[0] << 8) | data[1]) % 31 != 0 || (data[1] & 0x20)) return false; // deflate, check bits, no preset dictionary
     BitReader br{data + 2, n - 2};
@@ -118,7 +120,7 @@ bool inflateZlib(const uint8_t* data, size_t n, std::vector<uint8_t>& out) {
             if (br.pos + 4 > br.n) return false;
             const uint32_t len = br.p[br.pos] | (br.p[br.pos + 1] << 8), nlen = br.p[br.pos + 2] | (br.p[br.pos + 3] << 8);
             br.pos += 4;
-            if ((len ^ 0xFFFFu) != nlen || br.pos + len > br.n) return false;
+            if ((len ^ 0xFFFFu) != nlen || br.pos + len > br.n || out.size() + len > limit + 258) return false;
             out.insert(out.end(), br.p + br.pos, br.p + br.pos + len);
             br.pos += len;
         } else if (type == 1) { // fixed codes (3.2.6)
@@ -131,7 +133,7 @@ bool inflateZlib(const uint8_t* data, size_t n, std::vector<uint8_t>& out) {
             Huffman lit, dist;
             lit.build(l, 288);
             dist.build(d, 30);
-            if (!inflateBlock(br, lit, dist, out)) return false;
+            if (!inflateBlock(br, lit, dist, out, limit)) return false;
         } else if (type == 2) { // dynamic codes (3.2.7)
             const int nlit = (int)br.take(5) + 257, ndist = (int)br.take(5) + 1, ncode = (int)br.take(4) + 4;
             if (nlit > 286 || ndist > 30) return false;
@@ -166,7 +168,7 @@ bool inflateZlib(const uint8_t* data, size_t n, std::vector<uint8_t>& out) {
             if (lengths[256] == 0) return false; // no end-of-block code
             Huffman lit, dist;
             if (!lit.build(lengths, nlit) || !dist.build(lengths + nlit, ndist)) return false;
-            if (!inflateBlock(br, lit, dist, out)) return false;
+            if (!inflateBlock(br, lit, dist, out, limit)) return false;
         } else {
             return false;
         }
@@ -294,9 +296,13 @@ bool decodePng(const uint8_t* bytes, size_t n, bool flipVertically, int& width, 
                          ((h.colour == 2 || h.colour == 4 || h.colour == 6) && (h.depth == 8 || h.depth == 16));
     if (!depthOk || (h.colour == 3 && palette.empty())) return false;
 
-    std::vector<uint8_t> raw;
-    if (!inflateZlib(idat.data(), idat.size(), raw)) return false;
     const size_t bitsPerPixel = (size_t)h.depth * h.channels();
+    // scanline bytes the header implies (filter byte + packed row, per row; Adam7: 1.875 filter bytes per image row and at most one
+    // partial byte per pass row, i.e. under 4 more bytes per image row): what the zlib stream may inflate to
+    const size_t rawLimit = (((size_t)h.width * bitsPerPixel + 7) / 8 + 1) * h.height + (h.interlace ? 4 * (size_t)h.height + 64 : 0);
+    std::vector<uint8_t> raw;
+    raw.reserve(rawLimit);
+    if (!inflateZlib(idat.data(), idat.size(), raw, rawLimit)) return false;
     const size_t bpp = bitsPerPixel >= 8 ? bitsPerPixel / 8 : 1;
     rgb.assign((size_t)h.width * h.height * 3, 0);
     if (!h.interlace) {

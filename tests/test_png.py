@@ -140,6 +140,9 @@ def test_malformed_streams_are_rejected(crt):
     assert crt.decode_png(good.replace(b"IDAT", b"IDAX")) is None          # no image data
     bad_filter = encode_png(img, 4, 4, 8, 2, types=(7,))
     assert crt.decode_png(bad_filter) is None
+    # a stream that inflates to far more than the header's 4x4 pixels allow (a "zip bomb") is cut off, not expanded
+    bomb = good[:good.index(b"IDAT") - 4] + chunk(b"IDAT", zlib.compress(bytes(64 << 20), 9)) + chunk(b"IEND", b"")
+    assert crt.decode_png(bomb) is None
     broken = bytearray(good)
     i = good.index(b"IDAT") + 4
     broken[i] = 0x79                                                       # zlib header check bits
