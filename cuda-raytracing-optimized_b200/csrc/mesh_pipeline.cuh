@@ -33,7 +33,8 @@
 #define SHADOW_FLAG_LAST 2u   // ... and it was the slot's last sample: this shadow ray is all that is left of the slot
 
 struct MeshControl {
-    unsigned int traceCount[2];  // entries in traceQ[k]
+    unsigned int traceCount[2];  // entries at the FRONT of traceQ[k] (extend rays, resumed / re-traced rays)
+    unsigned int traceBack[2];   // entries at the BACK of traceQ[k], from its last element downwards (shadow rays): traceEntry()
     unsigned int shadeCount[2];  // entries in shadeQ[k]
     unsigned int traceCursor;    // dynamic fetch cursor of the running traceKernel
     unsigned int blocksDone;     // shadeKernel's last block resets the consumed queues
@@ -80,7 +81,15 @@ struct MeshState {
     unsigned int streamBase;
     int traceBudget;    // steps per ray per launch before it is parked
     int traceMinActive; // refill a warp when fewer lanes than this still traverse
+    unsigned int traceCap; // elements of traceQ[k]
 };
+
+// Entry i of a trace queue with `front` entries at its front and the rest at its back. The shade kernel appends extend rays at the
+// front and shadow rays at the back, so that a trace launch walks all its closest-hit rays first (the long walks start early:
+// the launch ends when its last ray ends) and then all its any-hit rays (a third as long), each kind among its own.
+__device__ __forceinline__ unsigned int traceEntry(const unsigned int* __restrict__ q, unsigned int cap, unsigned int front, unsigned int i) {
+    return q[i < front ? i : cap - 1u - (i - front)];
+}
 
 // The pixel a slot renders. Slots are numbered tile by tile (8 wide, 4 high) when the frame divides into such tiles, so that
 // the 32 lanes of a warp -- consecutive slots wherever queues are in slot order -- are a compact patch of the image: their
@@ -333,11 +342,13 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(
     // rays are spread over all warps, so that no ray waits in lockstep for a longer one in the same warp.
     // (`take` is a launch constant, but under the 48-register cap ptxas spilled it to local memory; it lives in shared
     // memory instead, read through a volatile pointer where it is used: local-memory traffic of this kernel is zero.)
-    __shared__ unsigned int takeShared, countShared;
+    __shared__ unsigned int takeShared, countShared, frontShared;
     __shared__ unsigned char exhaustedShared[TRACE_BLOCK / 32]; // per warp: the queue has no more entries for this warp
     if (threadIdx.x == 0) {
-        const unsigned int count = REDO ? ctl->redoCount : ctl->traceCount[cur];
+        const unsigned int front = REDO ? ctl->redoCount : ctl->traceCount[cur];
+        const unsigned int count = REDO ? front : front + ctl->traceBack[cur];
         const unsigned int totalWarps = gridDim.x * (TRACE_BLOCK / 32);
+        frontShared = front;
         countShared = count;
         takeShared = min(32u, max(1u, (count + totalWarps - 1) / totalWarps));
     }
@@ -436,7 +447,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, TRACE_BLOCKS_PER_SM) traceKernel(
                 const unsigned int rank = __popc(idle & below);
                 const unsigned int i = base + rank;
                 if (!live && rank < count && i < n) {
-                    const unsigned int e = queue[i];
+                    const unsigned int e = traceEntry(queue, st.traceCap, *(const volatile unsigned int*)&frontShared, i);
                     const unsigned int sl = e & ENTRY_SLOT_MASK;
                     isShadow = (e & ENTRY_SHADOW) != 0u;
                     const float4 ro = isShadow ? st.shO[sl] : st.rayO[sl];
@@ -533,12 +544,13 @@ __global__ void __launch_bounds__(WIDE_TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wi
     const unsigned int lane = laneId();
     // launch constants and the per-warp "queue exhausted" flag live in shared memory, read where they are used (the same
     // measure as in traceKernel: held in registers across the traversal loop they cost spills under the 64-register cap)
-    __shared__ unsigned int takeShared, countShared;
+    __shared__ unsigned int takeShared, countShared, frontShared;
     __shared__ unsigned char exhaustedShared[WIDE_TRACE_BLOCK / 32];
     __shared__ unsigned int lastBaseShared[WIDE_TRACE_BLOCK / 32]; // the queue position this warp's last refill started at
     if (threadIdx.x == 0) {
-        const unsigned int count = ctl->traceCount[cur];
+        const unsigned int count = ctl->traceCount[cur] + ctl->traceBack[cur];
         const unsigned int totalWarps = gridDim.x * (WIDE_TRACE_BLOCK / 32);
+        frontShared = ctl->traceCount[cur];
         countShared = count;
         takeShared = min(32u, max(1u, (count + totalWarps - 1) / totalWarps)); // short queue: spread the rays over all warps
     }
@@ -649,7 +661,7 @@ __global__ void __launch_bounds__(WIDE_TRACE_BLOCK, WIDE_TRACE_BLOCKS_PER_SM) wi
                 const unsigned int i = base + rank;
                 bool exact = false, exactShadow = false; // this lane's ray is walked in the reference's order (below)
                 if (!live && rank < count && i < n) {
-                    const unsigned int e = queue[i];
+                    const unsigned int e = traceEntry(queue, st.traceCap, *(const volatile unsigned int*)&frontShared, i);
                     const unsigned int sl = e & ENTRY_SLOT_MASK;
                     const bool shadow = (e & ENTRY_SHADOW) != 0u;
                     const float4 ro = shadow ? st.shO[sl] : st.rayO[sl];
@@ -740,7 +752,7 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_BLOCKS_PER_SM) meshShadeKernel
     unsigned int* __restrict__ nextShade = st.shadeQ[cur ^ 1];
     const unsigned int stride = gridDim.x * blockDim.x;
     unsigned int deferredCount = 0;
-    __shared__ unsigned int appendS[WF_BLOCK / 32], appendE[WF_BLOCK / 32], appendBase;
+    __shared__ unsigned int appendS[WF_BLOCK / 32], appendE[WF_BLOCK / 32], appendBaseE, appendBaseS;
     for (unsigned int blockBase = blockIdx.x * blockDim.x; blockBase < n; blockBase += stride) { // (same trip count for every warp of the block)
         const unsigned int i = blockBase + threadIdx.x;
         bool traceNext = false, castsShadow = false, defer = false;
@@ -792,12 +804,14 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_BLOCKS_PER_SM) meshShadeKernel
             if (k < warp) { beforeS += cs; beforeE += ce; }
             totalS += cs; totalE += ce;
         }
-        if (threadIdx.x == 0 && totalS + totalE) appendBase = atomicAdd(&ctl->traceCount[cur ^ 1], totalS + totalE);
+        if (threadIdx.x == 0) { // extend entries at the front of the queue, shadow entries at its back (traceEntry)
+            if (totalE) appendBaseE = atomicAdd(&ctl->traceCount[cur ^ 1], totalE);
+            if (totalS) appendBaseS = atomicAdd(&ctl->traceBack[cur ^ 1], totalS);
+        }
         __syncthreads();
-        const unsigned int basePos = appendBase;
         const unsigned int below = (1u << laneId()) - 1u;
-        if (castsShadow) nextTrace[basePos + beforeS + __popc(mS & below)] = slot | ENTRY_SHADOW; // shadow rays first: they unblock the slot
-        if (traceNext) nextTrace[basePos + totalS + beforeE + __popc(mE & below)] = slot;
+        if (castsShadow) nextTrace[st.traceCap - 1u - (appendBaseS + beforeS + __popc(mS & below))] = slot | ENTRY_SHADOW;
+        if (traceNext) nextTrace[appendBaseE + beforeE + __popc(mE & below)] = slot;
     }
     if (deferredCount) atomicAdd(&ctl->deferred, (unsigned long long)deferredCount);
 
@@ -810,8 +824,9 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_BLOCKS_PER_SM) meshShadeKernel
     }
     __syncthreads();
     if (isLast && threadIdx.x == 0) {
-        if (ctl->traceCount[cur] | ctl->shadeCount[cur]) ctl->iterations += 1;
+        if (ctl->traceCount[cur] | ctl->traceBack[cur] | ctl->shadeCount[cur]) ctl->iterations += 1;
         ctl->traceCount[cur] = 0;
+        ctl->traceBack[cur] = 0;
         ctl->shadeCount[cur] = 0;
         ctl->traceCursor = 0;
         ctl->blocksDone = 0;
@@ -1178,13 +1193,13 @@ __global__ void __launch_bounds__(CHASE_BLOCK, CHASE_MIN_BLOCKS) chaseKernel(Mes
 //   sums[3]           slots whose sample index is below factor * (mean of the previous hand-over, sums[4])
 //   sums[4]           that mean, as float bits (written by laneCommitKernel; survives from hand-over to hand-over)
 __global__ void laneStatsKernel(MeshState a, ChaseRing ring, unsigned long long* sums, float factor) {
-    const unsigned int n1 = a.ctl->traceCount[0], n2 = a.ctl->shadeCount[0];
+    const unsigned int front = a.ctl->traceCount[0], n1 = front + a.ctl->traceBack[0], n2 = a.ctl->shadeCount[0];
     if (blockIdx.x == 0 && threadIdx.x == 0)
         sums[2] = (unsigned long long)(ring.ctl[2] - ldVolatile(&ring.ctl[4])) + (unsigned long long)(ring.ctl[8 + 2] - ldVolatile(&ring.ctl[8 + 4]));
     const float prevThreshold = factor * __uint_as_float((unsigned int)sums[4]);
     unsigned long long sum = 0, cnt = 0, under = 0;
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += gridDim.x * blockDim.x) {
-        const unsigned int entry = i < n1 ? a.traceQ[0][i] : a.shadeQ[0][i - n1];
+        const unsigned int entry = i < n1 ? traceEntry(a.traceQ[0], a.traceCap, front, i) : a.shadeQ[0][i - n1];
         if (entry & ENTRY_SHADOW) continue; // count every live slot once: by its extend entry or its deferred shade entry
         const int sample = __float_as_int(a.atten[entry & ENTRY_SLOT_MASK].w);
         sum += (unsigned long long)sample;
@@ -1208,7 +1223,7 @@ __global__ void laneStatsKernel(MeshState a, ChaseRing ring, unsigned long long*
 // left (SHADOW_FLAG_LAST).
 __global__ void lanePartitionKernel(MeshState a, ChaseRing ring, const unsigned long long* sums, float factor, float exclusiveFactor, int minMean,
                                     unsigned int moveAllBelow, unsigned int capacity, unsigned int salt) {
-    const unsigned int n1 = a.ctl->traceCount[0], n2 = a.ctl->shadeCount[0];
+    const unsigned int front = a.ctl->traceCount[0], n1 = front + a.ctl->traceBack[0], n2 = a.ctl->shadeCount[0];
     const float mean = sums[1] ? (float)((double)sums[0] / (double)sums[1]) : 0.0f;
     const bool moveAll = n1 + n2 <= moveAllBelow;
     const bool started = mean >= (float)minMean;
@@ -1224,7 +1239,7 @@ __global__ void lanePartitionKernel(MeshState a, ChaseRing ring, const unsigned 
         unsigned int entry = 0;
         bool lag = false, lagX = false;
         if (valid) {
-            entry = isTrace ? a.traceQ[0][i] : a.shadeQ[0][i - n1];
+            entry = isTrace ? traceEntry(a.traceQ[0], a.traceCap, front, i) : a.shadeQ[0][i - n1];
             const unsigned int slot = entry & ENTRY_SLOT_MASK;
             const float sample = (float)__float_as_int(a.atten[slot].w);
             lagX = started && sample < thresholdX;
@@ -1241,18 +1256,24 @@ __global__ void lanePartitionKernel(MeshState a, ChaseRing ring, const unsigned 
         pos = warpAppend(toRing && lagX, &ring.ctl[8 + 2]);
         if (toRing && lagX) ring.entries[1][pos] = ringEntry;
         if (toRing && !isTrace) a.ready[entry & ENTRY_SLOT_MASK] = 0; // the wavefront's dense shade sweep must not see the slot any more
-        pos = warpAppend(valid && isTrace && !lag, &a.ctl->traceCount[1]);
-        if (valid && isTrace && !lag) a.traceQ[1][pos] = entry;
+        pos = warpAppend(valid && isTrace && !lag && !isShadowEntry, &a.ctl->traceCount[1]);
+        if (valid && isTrace && !lag && !isShadowEntry) a.traceQ[1][pos] = entry;
+        pos = warpAppend(valid && isTrace && !lag && isShadowEntry, &a.ctl->traceBack[1]); // shadow entries stay at the back
+        if (valid && isTrace && !lag && isShadowEntry) a.traceQ[1][a.traceCap - 1u - pos] = entry;
         pos = warpAppend(valid && !isTrace && !lag, &a.ctl->shadeCount[1]);
         if (valid && !isTrace && !lag) a.shadeQ[1][pos] = entry;
     }
 }
 
 __global__ void laneCopyBackKernel(MeshState a) {
-    const unsigned int n1 = a.ctl->traceCount[1], n2 = a.ctl->shadeCount[1];
+    const unsigned int front = a.ctl->traceCount[1], n1 = front + a.ctl->traceBack[1], n2 = a.ctl->shadeCount[1];
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += gridDim.x * blockDim.x) {
-        if (i < n1) a.traceQ[0][i] = a.traceQ[1][i];
-        else a.shadeQ[0][i - n1] = a.shadeQ[1][i - n1];
+        if (i < n1) {
+            const unsigned int at = i < front ? i : a.traceCap - 1u - (i - front); // both ends keep their places
+            a.traceQ[0][at] = a.traceQ[1][at];
+        } else {
+            a.shadeQ[0][i - n1] = a.shadeQ[1][i - n1];
+        }
     }
 }
 
@@ -1261,8 +1282,10 @@ __global__ void laneCopyBackKernel(MeshState a) {
 __global__ void laneCommitKernel(MeshControl* ctl, ChaseRing ring, unsigned long long* sums) {
     sums[4] = (unsigned long long)__float_as_uint(sums[1] ? (float)((double)sums[0] / (double)sums[1]) : 0.0f);
     ctl->traceCount[0] = ctl->traceCount[1];
+    ctl->traceBack[0] = ctl->traceBack[1];
     ctl->shadeCount[0] = ctl->shadeCount[1];
     ctl->traceCount[1] = 0;
+    ctl->traceBack[1] = 0;
     ctl->shadeCount[1] = 0;
     __threadfence();
     *(volatile unsigned int*)&ring.ctl[1] = ring.ctl[2];

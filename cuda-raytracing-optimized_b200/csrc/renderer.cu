@@ -314,9 +314,10 @@ static void allocMeshPipeline(RendererContext& c, unsigned int numSlots) {
     s.ready = devAlloc<unsigned char>(numSlots);
     s.rngOut = devAlloc<unsigned int>(numSlots);
     for (int k = 0; k < 2; k++) {
-        s.traceQ[k] = devAlloc<unsigned int>(2 * (size_t)numSlots); // at most one extend and one shadow entry per slot
+        s.traceQ[k] = devAlloc<unsigned int>(2 * (size_t)numSlots); // at most one extend entry (front) and one shadow entry (back) per slot
         s.shadeQ[k] = devAlloc<unsigned int>(numSlots);
     }
+    s.traceCap = 2u * numSlots;
     s.redoQ = devAlloc<unsigned int>(2 * (size_t)numSlots);
     s.ctl = devAlloc<MeshControl>(1);
     c.ring.entries[0] = devAlloc<unsigned int>(numSlots);
@@ -885,13 +886,13 @@ void crtRunMesh(RendererContext& c, int ns, bool resume) {
                     float msT, msS;
                     cudaEventElapsedTime(&msT, ev[0], ev[1]); c.stats.msTrace += msT;
                     cudaEventElapsedTime(&msS, ev[1], ev[2]); c.stats.msShade += msS;
-                    if (dump) std::fprintf(stderr, "iter %llu trace %u deferred %u  trace_ms %.4f shade_ms %.4f\n", iter, host->traceCount[cur],
+                    if (dump) std::fprintf(stderr, "iter %llu trace %u deferred %u  trace_ms %.4f shade_ms %.4f\n", iter, host->traceCount[cur] + host->traceBack[cur],
                                            host->shadeCount[cur], msT, msS);
                     iter++;
                 }
                 CRT_CHECK(cudaMemcpyAsync(host, mp.ctl, sizeof(MeshControl), cudaMemcpyDeviceToHost, stream));
                 CRT_CHECK(cudaStreamSynchronize(stream));
-                if (host->traceCount[0] == 0 && host->shadeCount[0] == 0) break;
+                if (host->traceCount[0] == 0 && host->traceBack[0] == 0 && host->shadeCount[0] == 0) break;
             }
             for (auto& e : ev) cudaEventDestroy(e);
         } else {
@@ -1006,11 +1007,11 @@ void crtRunMesh(RendererContext& c, int ns, bool resume) {
                         c.stats.msShade += msS;
                     }
                 }
-                const unsigned int live = host->traceCount[0] + host->shadeCount[0];
+                const unsigned int live = host->traceCount[0] + host->traceBack[0] + host->shadeCount[0];
                 if (dumpLanes) {
                     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
                     std::fprintf(stderr, "lanes t=%.2f ms  wavefront: trace %u shade %u iters %llu   chaser shared: %u/%u finished %u  exclusive: %u/%u finished %u  lag %.2f\n",
-                                 ms, host->traceCount[0], host->shadeCount[0], host->iterations, chase ? hostRing[0] : 0u, chase ? hostRing[1] : 0u,
+                                 ms, host->traceCount[0] + host->traceBack[0], host->shadeCount[0], host->iterations, chase ? hostRing[0] : 0u, chase ? hostRing[1] : 0u,
                                  chase ? hostRing[4] : 0u, chase ? hostRing[8] : 0u, chase ? hostRing[9] : 0u, chase ? hostRing[12] : 0u, lagFactor);
                 }
                 if (live == 0) break;
