@@ -752,10 +752,10 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_BLOCKS_PER_SM) meshShadeKernel
     unsigned int* __restrict__ nextShade = st.shadeQ[cur ^ 1];
     const unsigned int stride = gridDim.x * blockDim.x;
     unsigned int deferredCount = 0;
-    __shared__ unsigned int appendS[WF_BLOCK / 32], appendE[WF_BLOCK / 32], appendBaseE, appendBaseS;
+    __shared__ unsigned int appendS[WF_BLOCK / 32], appendE[WF_BLOCK / 32], appendC[WF_BLOCK / 32], appendBaseE, appendBaseS;
     for (unsigned int blockBase = blockIdx.x * blockDim.x; blockBase < n; blockBase += stride) { // (same trip count for every warp of the block)
         const unsigned int i = blockBase + threadIdx.x;
-        bool traceNext = false, castsShadow = false, defer = false;
+        bool traceNext = false, castsShadow = false, defer = false, cameraRay = false;
         unsigned int slot = 0;
         if (i < n) {
             // every load the entry needs is issued before the first one is looked at: `ready`, `pending` and the five state records
@@ -785,33 +785,36 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_BLOCKS_PER_SM) meshShadeKernel
                 traceNext = r.traceNext;
                 castsShadow = r.castsShadow;
                 if (traceNext) storePath(st, slot, p, !r.continued);
+                cameraRay = traceNext && !r.continued; // the slot's next sample starts: a camera ray
                 st.ready[slot] = 0;
             }
         }
         const unsigned int posDefer = warpAppend(defer, &ctl->shadeCount[cur ^ 1]);
         if (defer) { nextShade[posDefer] = slot; deferredCount++; }
-        // the extend and shadow entries of the BLOCK go out with one atomic, all its shadow entries first, then all its extend
-        // entries: runs of ~150 / ~250 rays of one kind, so that a refill of the trace kernel (14-18 lanes) gets rays of one kind --
-        // any-hit walks are a third as long as closest-hit walks, and lanes that finish early idle until the next refill
-        const unsigned int mE = __ballot_sync(0xFFFFFFFFu, traceNext), mS = __ballot_sync(0xFFFFFFFFu, castsShadow);
+        // the entries of the BLOCK go out with one atomic per end of the trace queue: shadow entries to the back; to the front the
+        // block's camera rays (first rays of new samples: neighbouring pixels, coherent walks) and then its bounce rays, so that a
+        // refill of the trace kernel (14-18 lanes) gets rays of one kind (measured: camera rays first -1 %)
+        const bool bounceRay = traceNext && !cameraRay;
+        const unsigned int mE = __ballot_sync(0xFFFFFFFFu, bounceRay), mS = __ballot_sync(0xFFFFFFFFu, castsShadow), mC = __ballot_sync(0xFFFFFFFFu, cameraRay);
         const unsigned int warp = threadIdx.x >> 5;
-        if (laneId() == 0) { appendS[warp] = __popc(mS); appendE[warp] = __popc(mE); }
+        if (laneId() == 0) { appendS[warp] = __popc(mS); appendE[warp] = __popc(mE); appendC[warp] = __popc(mC); }
         __syncthreads();
-        unsigned int totalS = 0, totalE = 0, beforeS = 0, beforeE = 0;
+        unsigned int totalS = 0, totalE = 0, totalC = 0, beforeS = 0, beforeE = 0, beforeC = 0;
 #pragma unroll
         for (unsigned int k = 0; k < WF_BLOCK / 32; k++) {
-            const unsigned int cs = appendS[k], ce = appendE[k];
-            if (k < warp) { beforeS += cs; beforeE += ce; }
-            totalS += cs; totalE += ce;
+            const unsigned int cs = appendS[k], ce = appendE[k], cc = appendC[k];
+            if (k < warp) { beforeS += cs; beforeE += ce; beforeC += cc; }
+            totalS += cs; totalE += ce; totalC += cc;
         }
         if (threadIdx.x == 0) { // extend entries at the front of the queue, shadow entries at its back (traceEntry)
-            if (totalE) appendBaseE = atomicAdd(&ctl->traceCount[cur ^ 1], totalE);
+            if (totalE + totalC) appendBaseE = atomicAdd(&ctl->traceCount[cur ^ 1], totalE + totalC);
             if (totalS) appendBaseS = atomicAdd(&ctl->traceBack[cur ^ 1], totalS);
         }
         __syncthreads();
         const unsigned int below = (1u << laneId()) - 1u;
         if (castsShadow) nextTrace[st.traceCap - 1u - (appendBaseS + beforeS + __popc(mS & below))] = slot | ENTRY_SHADOW;
-        if (traceNext) nextTrace[appendBaseE + beforeE + __popc(mE & below)] = slot;
+        if (cameraRay) nextTrace[appendBaseE + beforeC + __popc(mC & below)] = slot; // the block's camera rays (neighbouring pixels) first
+        if (bounceRay) nextTrace[appendBaseE + totalC + beforeE + __popc(mE & below)] = slot;
     }
     if (deferredCount) atomicAdd(&ctl->deferred, (unsigned long long)deferredCount);
 
