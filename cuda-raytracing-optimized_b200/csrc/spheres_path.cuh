@@ -175,7 +175,8 @@ __device__ __forceinline__ void startSpherePath(SpherePath& p, const CameraDev& 
 
 // Everything between two closest-sphere queries of one path whose hit record is `h`: sky gradient on a miss, scatter, Russian
 // roulette. Returns whether the path has another ray to trace; when it has not, p.col is the sample's colour.
-__device__ __forceinline__ bool scatterSpherePath(SpherePath& p, const float4* __restrict__ mats, int maxDepth, const float4& h) {
+// `rdir` = unit(p.dir), the direction the ray was traced along (the caller has it already).
+__device__ __forceinline__ bool scatterSpherePath(SpherePath& p, const float4* __restrict__ mats, int maxDepth, const float4& h, const f3& rdir) {
     if (!(h.x < FLT_MAX)) {
         // sky gradient, kernels.cu:419-421
         const float t = 0.5f * (p.dir.y + 1.0f);
@@ -188,7 +189,6 @@ __device__ __forceinline__ bool scatterSpherePath(SpherePath& p, const float4* _
     unsigned int bounce = p.flags & PATH_BOUNCE_MASK;
     const unsigned int id = __float_as_uint(h.w);
     const float4 sp = c_spheres[id];
-    const f3 rdir = unit(p.dir);
     const f3 hp = p.origin + h.x * rdir; // point_at_parameter on the traced (normalised) ray
     SurfacePoint s;
     s.normal = (hp - xyz(sp)) / sp.w;
@@ -237,7 +237,7 @@ __device__ __forceinline__ bool shadeSphereSlot(const WfState& st, const float4*
     p.rng = __float_as_uint(ro.w);
     p.flags = __float_as_uint(rd.w);
     int sample = __float_as_int(att4.w);
-    bool continues = scatterSpherePath(p, mats, maxDepth, h);
+    bool continues = scatterSpherePath(p, mats, maxDepth, h, unit(p.dir));
     if (!continues) {
         // the sample is finished: col += p.color (kernels.cu:558), then the slot's next sample
         const unsigned int pixel = slot % npix;
@@ -403,17 +403,18 @@ spheresMegaKernel(WfState st, const float4* __restrict__ mats, int maxDepth, Sph
         if (live) {
             float closest;
             unsigned int id;
+            const f3 rdir = unit(p.dir); // once per ray: the walk and the shading both use it
             if (COUNT) {
                 unsigned int nb = 0, ns = 0;
-                closestSphere(bvh, p.origin, unit(p.dir), closest, id, nb, ns);
+                closestSphere(bvh, p.origin, rdir, closest, id, nb, ns);
                 boxTests += nb;
                 sphereTests += ns;
             } else {
-                closestSphere(bvh, p.origin, unit(p.dir), closest, id);
+                closestSphere(bvh, p.origin, rdir, closest, id);
             }
             rays++;
             p.col = mk3(0.0f, 0.0f, 0.0f); // a sphere path only collects light when it ends (the sky): nothing to carry between rays
-            if (!scatterSpherePath(p, mats, maxDepth, make_float4(closest, 0.0f, 0.0f, __uint_as_float(id)))) {
+            if (!scatterSpherePath(p, mats, maxDepth, make_float4(closest, 0.0f, 0.0f, __uint_as_float(id)), rdir)) {
                 sum.x += p.col.x; sum.y += p.col.y; sum.z += p.col.z; // col += p.color, in sample order (kernels.cu:558)
                 sample++;
                 if (sample < samplesPerSlot) {
