@@ -800,8 +800,7 @@ __global__ void __launch_bounds__(WF_BLOCK, SHADE_BLOCKS_PER_SM) meshShadeKernel
         if (laneId() == 0) { appendS[warp] = __popc(mS); appendE[warp] = __popc(mE); appendC[warp] = __popc(mC); }
         __syncthreads();
         unsigned int totalS = 0, totalE = 0, totalC = 0, beforeS = 0, beforeE = 0, beforeC = 0;
-#pragma unroll
-        for (unsigned int k = 0; k < WF_BLOCK / 32; k++) {
+        for (unsigned int k = 0; k < (blockDim.x >> 5); k++) {
             const unsigned int cs = appendS[k], ce = appendE[k], cc = appendC[k];
             if (k < warp) { beforeS += cs; beforeE += ce; beforeC += cc; }
             totalS += cs; totalE += ce; totalC += cc;

@@ -779,6 +779,13 @@ static void launchMeshIteration(RendererContext& c, const MeshState& mp, cudaStr
         else traceKernel<false, 0><<<traceBlocks, TRACE_BLOCK, 0, stream>>>(mp, c.mesh);
     }
     if (ev) cudaEventRecord(ev[1], stream);
+    {
+        // threads per shade block (the grid keeps its thread count): the kernel appends per block behind two barriers, and the ncu
+        // source page showed a fifth of its stall samples right after them; with 4 warps per barrier instead of 8 the frame takes
+        // 273.4 ms instead of 279.0 (64 threads: 275.9). CRT_SHADE_BLOCK overrides.
+        static const int shadeBlock = std::getenv("CRT_SHADE_BLOCK") ? std::atoi(std::getenv("CRT_SHADE_BLOCK")) : 128;
+        if (shadeBlock > 0 && shadeBlock <= WF_BLOCK && shadeBlock % 32 == 0 && shadeThreads == WF_BLOCK) { shadeBlocks = shadeBlocks * WF_BLOCK / shadeBlock; shadeThreads = shadeBlock; }
+    }
     meshShadeKernel<<<shadeBlocks, shadeThreads, 0, stream>>>(mp, shadeScene(c), c.cam, cur);
     if (ev) cudaEventRecord(ev[2], stream);
 }
