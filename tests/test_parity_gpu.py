@@ -8,6 +8,7 @@ Stated bars (BASELINE.json north_star / SURVEY.md 8d):
   * against the CPU oracle (no FMA): >= 99.5 % of pixels within 1e-3, ids equal on >= 99.9 % of rays."""
 import json
 import os
+import sys
 import tempfile
 
 import numpy as np
@@ -465,6 +466,103 @@ def test_wide_tree_equals_exact_walk(crt, medium_scene):
         assert np.array_equal(e[k].view(np.uint32), w[k].view(np.uint32)), k
     assert np.array_equal(e[4], w[4]) and e[5] == w[5]
     assert e[6] == 0 and w[6] < 1e-3 * w[5]
+
+
+def _soup(rng, n, kind):
+    """n triangles in the 64-byte layout ((n, 16) float32: v[3], texCoords[3], meshID) of a kind that stresses the builder / walk."""
+    t = np.zeros((n, 16), np.float32)
+    if kind == "uniform":          # small triangles everywhere
+        c = rng.uniform(-50, 50, (n, 1, 3))
+        v = c + rng.uniform(-2, 2, (n, 3, 3))
+    elif kind == "mixed":          # a few huge triangles over many tiny ones, axis-aligned quads, needles
+        c = rng.uniform(-50, 50, (n, 1, 3))
+        size = np.where(rng.random((n, 1, 1)) < 0.02, 80.0, 0.5)
+        v = c + rng.uniform(-1, 1, (n, 3, 3)) * size
+        flat = rng.random(n) < 0.3
+        v[flat, :, 1] = np.round(v[flat, :1, 1])           # axis-aligned: zero extent in y
+        needle = rng.random(n) < 0.05
+        v[needle, 2] = v[needle, 1] + 1e-4                  # nearly degenerate
+    else:                          # "ties": every triangle twice (exact ties), some degenerate
+        half = n // 2
+        c = rng.uniform(-20, 20, (half, 1, 3))
+        v = c + rng.uniform(-3, 3, (half, 3, 3))
+        v = np.concatenate([v, v], axis=0)
+        v[:8, 2] = v[:8, 1]                                 # zero area
+        n = v.shape[0]
+        t = np.zeros((n, 16), np.float32)
+    t[:, :9] = v.reshape(n, 9).astype(np.float32)
+    t[:, 9:15] = rng.random((n, 6)).astype(np.float32)
+    t[:, 15] = (np.arange(n) % 20).astype(np.int32).view(np.float32)
+    return t
+
+
+@pytest.mark.parametrize("kind", ["uniform", "mixed", "ties"])
+def test_wide_tree_equals_exact_walk_on_triangle_soups(crt, kind, tmp_path):
+    """Geometry that is not the staircase: random soups with huge-over-tiny triangles, axis-aligned and nearly degenerate ones, and
+    exact duplicates (every hit a tie). Closest-hit and any-hit batches -- random rays, axis-parallel rays, -0.0 components, origins
+    on vertices -- through the renderer's own tree + certificate must equal the order-exact walk of the caller's tree bit for bit."""
+    rng = np.random.default_rng({"uniform": 1, "mixed": 2, "ties": 3}[kind])
+    tris = _soup(rng, 6000, kind)
+    scene = crt.Scene.from_triangles(tris, 5, 16)
+    n = 1 << 17
+    ro = np.zeros((n, 4), np.float32)
+    rd = np.zeros((n, 4), np.float32)
+    ro[:, :3] = rng.uniform(-60, 60, (n, 3))
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    k = n // 8
+    d[:k] = 0.0
+    d[np.arange(k), rng.integers(0, 3, k)] = rng.choice([-1.0, 1.0], k)          # axis-parallel
+    d[k:2 * k, 0] = -0.0                                                          # a signed zero component
+    verts = tris[:, :9].reshape(-1, 3)
+    ro[2 * k:3 * k, :3] = verts[rng.integers(0, verts.shape[0], k)]               # origins exactly on vertices
+    target = verts[rng.integers(0, verts.shape[0], k)]
+    aim = target - ro[3 * k:4 * k, :3]
+    d[3 * k:4 * k] = aim / np.maximum(np.linalg.norm(aim, axis=1, keepdims=True), 1e-9)  # aimed exactly at vertices (edge hits)
+    rd[:, :3] = d.astype(np.float32)
+    ro[:, 3] = 0.001
+    L = crt.device_lib()
+    res = {}
+    for mode in (crt.TRAVERSAL_EXACT, crt.TRAVERSAL_WIDE):
+        crt.set_traversal(mode)
+        with crt.Frame(scene, 64, 64, 8) as fr:
+            crt.set_traversal(-1)
+            out = []
+            dO, dD, dH, dM = (L.rendererDeviceAlloc(16 * n) for _ in range(4))
+            for any_hit, tmax in ((0, float(FLT_MAX)), (1, 40.0)):
+                rd[:, 3] = tmax
+                L.rendererCopyToDevice(dO, ro.ctypes.data, 16 * n)
+                L.rendererCopyToDevice(dD, rd.ctypes.data, 16 * n)
+                L.intersectBatchDeviceEx(dO, dD, n, dH, dM, any_hit)
+                hit, mesh = np.zeros((n, 4), np.float32), np.zeros(n, np.int32)
+                L.rendererCopyToHost(hit.ctypes.data, dH, 16 * n)
+                L.rendererCopyToHost(mesh.ctypes.data, dM, 4 * n)
+                out += [hit, mesh]
+            for p in (dO, dD, dH, dM):
+                L.rendererDeviceFree(p)
+            if mode == crt.TRAVERSAL_WIDE:
+                assert crt.wide_info().active == 1
+            out.append(fr.run(4))
+        res[mode] = out
+    e, w = res[crt.TRAVERSAL_EXACT], res[crt.TRAVERSAL_WIDE]
+    if HAVE_SHIM:  # and the reference's own hitMesh on the same file and rays: ids and mesh ids bit-exact, any-hit verdicts equal
+        sys.path.insert(0, os.path.join(os.path.dirname(G), "..", "oracle"))
+        import oracle as orc
+        path = str(tmp_path / "soup.bvh")
+        assert scene.save_bvh(path) == 0
+        rd[:, 3] = FLT_MAX
+        rhit, rmesh, _ = orc.ref_intersect_batch(path, 16, 5, ro, rd, False, str(tmp_path))
+        assert np.array_equal(w[0][:, 3].view(np.uint32), rhit[:, 3].view(np.uint32)) and np.array_equal(w[1], rmesh)
+        hit_ref = rmesh >= 0
+        assert np.array_equal(w[0][hit_ref, 0].view(np.uint32), rhit[hit_ref, 0].view(np.uint32))  # t to the bit
+        rd[:, 3] = 40.0
+        ohit, _, _ = orc.ref_intersect_batch(path, 16, 5, ro, rd, True, str(tmp_path))
+        assert np.array_equal(w[2][:, 0] == 0.0, ohit[:, 0] == 0.0)  # hitBvh returns 0.0f for an occluded shadow ray (kernels.cu:207)
+    scene.close()
+    assert (e[1] >= 0).mean() > 0.05  # the batch does hit things
+    for i in range(4):
+        assert np.array_equal(e[i].view(np.uint32), w[i].view(np.uint32)), i
+    assert np.array_equal(e[4], w[4])
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
