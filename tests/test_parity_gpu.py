@@ -184,6 +184,50 @@ def test_sphere_persistent_kernel_equals_the_wavefront(crt, monkeypatch):
     assert np.array_equal(mega, wave) and np.array_equal(mega, again)
 
 
+def _sphere_set(crt, rng, n, kind):
+    sph = (crt.Sphere * 1024)()
+    mats = (crt.Material * 1024)()
+    for i in range(n):
+        if kind == "ties" and i >= n // 2:       # every sphere twice: equal roots, the lower index must win
+            src = sph[i - n // 2]
+            c, r = (src.center.e[0], src.center.e[1], src.center.e[2]), src.radius
+        elif i < 3:                              # spheres the BVH keeps in its always-list (radius > 100), overlapping
+            c, r = (float(rng.uniform(-30, 30)), -150.0 - 10.0 * i, float(rng.uniform(-30, 30))), 150.0 + 10.0 * i
+        else:
+            big = rng.random() < 0.1
+            c = tuple(float(x) for x in rng.uniform(-6, 6, 3))
+            r = float(rng.uniform(1.0, 2.5) if big else rng.uniform(0.05, 0.6))   # overlapping, nested, tiny
+        for a in range(3):
+            sph[i].center.e[a] = c[a]
+        sph[i].radius = r
+        mats[i].type = int(rng.integers(0, 3))   # DIFFUSE / METAL / GLASS
+        for a in range(3):
+            mats[i].color.e[a] = float(rng.uniform(0.2, 1.0))
+        mats[i].param = float(rng.uniform(0.0, 0.4)) if mats[i].type == 1 else 1.5
+        mats[i].texId = -1
+    return sph, mats, n
+
+
+@pytest.mark.parametrize("kind,n", [("random", 300), ("ties", 200), ("single", 1), ("full", 1024)])
+def test_sphere_paths_agree_on_adversarial_sets(crt, monkeypatch, kind, n):
+    """Sphere sets that are not the README scene -- overlapping and nested spheres, three overlapping giants in the always-list,
+    exact duplicates (ties by index), one sphere, the full constant table: the persistent kernel over the SAH-split, octant-threaded
+    BVH and the wavefront over the brute-force loop give identical frames and ray counts."""
+    rng = np.random.default_rng(len(kind) + n)
+    scene = _sphere_set(crt, rng, n, kind)
+    nx, ny, ns = 160, 120, 6
+    monkeypatch.setenv("CRT_SPHERES_BRUTE", "1")
+    with crt.Frame(scene, nx, ny, 50) as fr:
+        brute = fr.run(ns)
+        rays_brute = crt.stats().raysExtend
+    monkeypatch.delenv("CRT_SPHERES_BRUTE")
+    with crt.Frame(scene, nx, ny, 50) as fr:
+        mega = fr.run(ns)
+        rays_mega = crt.stats().raysExtend
+    assert rays_mega == rays_brute and rays_mega >= nx * ny * ns
+    assert np.isfinite(mega).all() and np.array_equal(mega, brute)
+
+
 def test_ray_batch_vs_golden_hitmesh(crt, small_scene):
     z = np.load(os.path.join(G, "rays_8192.npz"))
     with crt.Frame(small_scene, 8, 8, 1):
